@@ -1,0 +1,133 @@
+/* libpcrl_b200.so -- C ABI of the B200-native PCRLv2 3-D pre-training hot path.
+ *
+ * The reference (RL4M/PCRLv2) is pure Python on top of PyTorch/cuDNN: it has no FFI of its own,
+ * so each entry point below names the torch call of the reference it replaces
+ * (paths relative to the reference root).  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (the library never allocates or
+ *     retains memory), sizes are plain ints, `stream` is a cudaStream_t passed as void*;
+ *   - calls are asynchronous on `stream`, never synchronise, and return 0 or a negative code
+ *     (PCRL_ERR_*); pcrl_last_error() returns the message of the calling thread's last failure;
+ *   - activations are "H-padded NDHWC" bf16: logical (N,C,D,H,W) stored as [N][D][H+1][W][C]
+ *     with row h'=0 of every plane all zero (voxel h lives at row h+1).  Producers in this
+ *     library write that zero row themselves; a caller-made tensor must honour it;
+ *   - 1-channel tensors (network input, masks) are plain fp32 [N][D][H][W].
+ */
+#ifndef PCRL_B200_H
+#define PCRL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCRL_OK 0
+#define PCRL_ERR_ARG (-1)
+#define PCRL_ERR_CUDA (-2)
+#define PCRL_ERR_UNSUPPORTED (-3)
+
+/* activation codes: models/pcrlv2_model_3d.py:20-27 */
+#define PCRL_ACT_RELU 0
+#define PCRL_ACT_PRELU 1
+#define PCRL_ACT_ELU 2
+#define PCRL_ACT_SIGMOID 3
+#define PCRL_ACT_NONE 4
+
+const char* pcrl_last_error(void);
+int pcrl_version(void);
+
+/* ---- weight layout converters (state_dict layout <-> tensor-core operand layout) ---------- */
+/* nn.Conv3d.weight (Cout,Cin,3,3,3) fp32 -> wf [27][Cout][Cin] bf16 (forward operand) and, if
+ * wd != NULL, wd [27][Cin][Cout] bf16 with mirrored taps (data-gradient operand).
+ * models/pcrlv2_model_3d.py:9 */
+int pcrl_pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, void* stream);
+/* packed weight gradient [27][Cout][Cin] fp32 -> (Cout,Cin,3,3,3) fp32 */
+int pcrl_unpack_conv3_wgrad(const float* gpk, float* g, int Cout, int Cin, void* stream);
+/* nn.ConvTranspose3d.weight (Cin,Cout,2,2,2) fp32 -> wf [(tap,Cout)][Cin] bf16 and
+ * wd [Cin][(tap,Cout)] bf16.  models/pcrlv2_model_3d.py:52 */
+int pcrl_pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, void* stream);
+int pcrl_unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, void* stream);
+
+/* ---- 3x3x3 convolution on tensor cores (tcgen05 implicit GEMM) ---------------------------- */
+/* y = conv3d(x, w, padding=1) WITHOUT bias (the bias cancels in the following normalisation and
+ * is folded into running_mean by pcrl_norm_finalize).  x [N][D][H+1][W][Cin], y
+ * [N][D][H+1][W][Cout] bf16 (out_fp32: fp32).  stats (nullable) [G][Cout][2] fp64 is
+ * ACCUMULATED with per-channel sum / sum of squares of the stored y (G = N if stats_per_sample
+ * else 1).  Replaces F.conv3d inside LUConv.forward, models/pcrlv2_model_3d.py:33. */
+int pcrl_conv3d_k3_fprop(const void* x, const void* wf, void* y, double* stats,
+                         int stats_per_sample, int out_fp32, int N, int D, int H, int W, int Cin,
+                         int Cout, void* stream);
+/* dx = conv3d data gradient; dy [N][D][H+1][W][Cout] (pad rows zero), wd from
+ * pcrl_pack_conv3_weights, dx [N][D][H+1][W][Cin] bf16.  Autograd of the call above. */
+int pcrl_conv3d_k3_dgrad(const void* dy, const void* wd, void* dx, int N, int D, int H, int W,
+                         int Cin, int Cout, void* stream);
+/* dw_packed [27][Cout][Cin] fp32 += weight gradient (caller zeroes or keeps a running sum).
+ * dy and x must have zero pad rows. */
+int pcrl_conv3d_k3_wgrad(const void* dy, const void* x, float* dw_packed, int N, int D, int H,
+                         int W, int Cin, int Cout, void* stream);
+
+/* ---- Conv3d(1 -> 32) stem (down_tr64.ops.0), models/pcrlv2_model_3d.py:114 ----------------- */
+int pcrl_stem_conv_fprop(const float* x, const float* w, void* y, double* stats,
+                         int stats_per_sample, int N, int D, int H, int W, void* stream);
+/* dw (32,1,3,3,3) fp32 += */
+int pcrl_stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int H, int W,
+                         void* stream);
+
+/* ---- ConvTranspose3d(k=2, s=2), models/pcrlv2_model_3d.py:52,64 ---------------------------- */
+/* y_fine [N][2D][2H+1][2W][Cout] bf16 = convT(x [N][D][H+1][W][Cin]) + bias (pad rows zeroed). */
+int pcrl_convT3d_k2s2_fprop(const void* x, const void* wf, const float* bias, void* y_fine, int N,
+                            int D, int H, int W, int Cin, int Cout, void* stream);
+/* Backward.  g_fine [N][2D][2H+1][2W][Cout] bf16; scratch [N*D*(H+1)*W][8*Cout] bf16;
+ * dx [N][D][H+1][W][Cin] bf16; dw_packed [(tap,Cout)][Cin] fp32 += ; dbias [Cout] fp32 += .
+ * x may be NULL together with dw_packed to skip the weight gradient. */
+int pcrl_convT3d_k2s2_bwd(const void* g_fine, const void* x, const void* wd, void* scratch,
+                          void* dx, float* dw_packed, float* dbias, int N, int D, int H, int W,
+                          int Cin, int Cout, void* stream);
+
+/* ---- normalisation + activation (+ max-pool, + average-pool sums) -------------------------- */
+/* BatchNorm3d / InstanceNorm3d statistics -> scale/shift; updates running stats (BatchNorm) and
+ * num_batches_tracked.  models/pcrlv2_model_3d.py:11-16 (F.batch_norm / F.instance_norm). */
+int pcrl_norm_finalize(const double* stats, double count, const float* gamma, const float* beta,
+                       const float* conv_bias, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, float momentum, float eps, float* scale,
+                       float* shift, float* mean, float* invstd, int G, int C, void* stream);
+/* a = act(y*scale + shift); optional 2x2x2 max-pool (nn.MaxPool3d(2), :100) and per-(n,c) sums
+ * for F.adaptive_avg_pool3d (:67). */
+int pcrl_norm_act_fwd(const void* y, const float* scale, const float* shift, const float* prelu,
+                      void* a_out, void* pool_out, float* avg_sum, int per_sample, int act,
+                      int pool, int N, int D, int H, int W, int C, void* stream);
+/* two-pass backward: pass 0 accumulates sums [G][C][3] fp64, pass 1 writes dy. */
+int pcrl_norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gavg,
+                      const float* scale, const float* shift, const float* mean,
+                      const float* invstd, const float* gamma, const float* prelu, double* sums,
+                      void* dy, double count, int per_sample, int act, int pool, int pass, int N,
+                      int D, int H, int W, int C, void* stream);
+int pcrl_zero_pad_rows(void* t, long long planes, int H1, int row_elems, void* stream);
+
+/* ---- single-channel heads ------------------------------------------------------------------ */
+/* y1 = Conv3d(C->1,k3,p1)(a) + b3 (deep_supervision_head.conv1, :60); optionally also
+ * y0 = Conv3d(C->1,k1)(a) + b1 (out_tr.final_conv, :78).  w3 is [27][C] fp32 (tap-major). */
+int pcrl_head_fwd(const void* a, const float* w3, const float* b3, const float* w1,
+                  const float* b1, float* y1, float* y0, int N, int D, int H, int W, int C,
+                  void* stream);
+int pcrl_head_bwd_data(const float* dy1, const float* w3, const float* dy0, const float* w1,
+                       void* da, int N, int D, int H, int W, int C, void* stream);
+int pcrl_head_bwd_weight(const void* a, const float* dy1, const float* dy0, float* dw3,
+                         float* dw1, int N, int D, int H, int W, int C, void* stream);
+
+/* ---- plain tensor-core GEMMs (bf16 in, fp32 accumulate) ------------------------------------ */
+/* C[rows][cols] = A[rows][K] * B[cols][K]^T (+ bias[col]); ldc in elements. */
+int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
+                 int cols, int ldc, int out_fp32, void* stream);
+/* C[P][Q] (fp32) += A[rows][P]^T * B[rows][Q] */
+int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q,
+                 void* stream);
+
+/* ---- optimizer: torch.optim.SGD(momentum, weight_decay), train_3d.py:48-51,151 ------------- */
+int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf,
+                  const long long* seg_offsets, const int* seg_active, const int* seg_first,
+                  int nseg, float lr, float momentum, float weight_decay, float grad_scale,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCRL_B200_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of libpcrl_b200.so (include/pcrl_b200.h).
+
+The library is the product: there is NO fallback.  If the shared object is missing or a call
+fails, an exception is raised; nothing in this package routes around the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcrl_b200.so")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_longlong
+_F = ctypes.c_float
+_D = ctypes.c_double
+
+# name -> argtypes, mirroring include/pcrl_b200.h (the header is the source of truth; the
+# "not gpu" test-suite checks that every symbol declared there is exported and listed here).
+SIGNATURES = {
+    "pcrl_pack_conv3_weights": [_P, _P, _P, _I, _I, _P],
+    "pcrl_unpack_conv3_wgrad": [_P, _P, _I, _I, _P],
+    "pcrl_pack_convT_weights": [_P, _P, _P, _I, _I, _P],
+    "pcrl_unpack_convT_wgrad": [_P, _P, _I, _I, _P],
+    "pcrl_conv3d_k3_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_conv3d_k3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_conv3d_k3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_stem_conv_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_stem_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "pcrl_convT3d_k2s2_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_convT3d_k2s2_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_norm_finalize": [_P, _D, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _P],
+    "pcrl_norm_act_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_norm_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I,
+                          _I, _I, _I, _I, _I, _P],
+    "pcrl_zero_pad_rows": [_P, _L, _I, _I, _P],
+    "pcrl_head_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_head_bwd_data": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_head_bwd_weight": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_gemm_nt": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "pcrl_gemm_tn": [_P, _P, _P, _L, _I, _I, _P],
+    "pcrl_sgd_flat": [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _P],
+}
+
+_lib = None
+
+
+class PcrlError(RuntimeError):
+    pass
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    if force:
+        for f in os.listdir(os.path.join(_HERE, "csrc", "build")) if os.path.isdir(
+                os.path.join(_HERE, "csrc", "build")) else []:
+            if f.endswith(".o"):
+                os.remove(os.path.join(_HERE, "csrc", "build", f))
+    subprocess.check_call(["bash", script])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PcrlError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (or pcrlv2_b200/csrc/build.sh).  There is no fallback path.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.pcrl_last_error.restype = ctypes.c_char_p
+        _lib.pcrl_version.restype = _I
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _I
+    return _lib
+
+
+def _conv(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda:
+            raise PcrlError("libpcrl_b200 was handed a CPU tensor; it only runs on the GPU")
+        return a.data_ptr()
+    return a
+
+
+def call(name: str, *args) -> None:
+    """Invoke an entry point on torch's current CUDA stream; the stream argument is appended."""
+    fn = getattr(lib(), name)
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = fn(*[_conv(a) for a in args], stream)
+    if rc != 0:
+        raise PcrlError(f"{name} failed ({rc}): {lib().pcrl_last_error().decode()}")

@@ -1,0 +1,196 @@
+// extern "C" surface of libpcrl_b200.so (see include/pcrl_b200.h).  Thin: argument checks and
+// forwarding to the kernel launchers in the other translation units.
+#include "common.cuh"
+#include "../../include/pcrl_b200.h"
+
+namespace pcrl {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// launchers defined in igemm_kmajor.cu / igemm_mnmajor.cu / streaming.cu / heads.cu
+int conv3d_k3_igemm(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, cudaStream_t);
+int gemm_nt_igemm(const void*, const void*, void*, const float*, long long, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int conv3d_k3_wgrad_igemm(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
+int gemm_tn_igemm(const void*, const void*, float*, long long, int, int, cudaStream_t);
+int pack_conv3_weights(const float*, void*, void*, int, int, cudaStream_t);
+int unpack_conv3_wgrad(const float*, float*, int, int, cudaStream_t);
+int pack_convT_weights(const float*, void*, void*, int, int, cudaStream_t);
+int unpack_convT_wgrad(const float*, float*, int, int, cudaStream_t);
+int stem_conv_fprop(const float*, const float*, void*, double*, int, int, int, int, int, cudaStream_t);
+int stem_conv_wgrad(const void*, const float*, float*, int, int, int, int, cudaStream_t);
+int norm_finalize(const double*, double, const float*, const float*, const float*, float*, float*, long long*, float, float, float*, float*, float*, float*, int, int, cudaStream_t);
+int norm_act_fwd(const void*, const float*, const float*, const float*, void*, void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
+int norm_act_bwd(const void*, const void*, const void*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, double*, void*, double, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int zero_pad_rows(void*, long long, int, int, cudaStream_t);
+int convT_unshuffle(const void*, void*, float*, int, int, int, int, int, cudaStream_t);
+int head_fwd(const void*, const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+int head_bwd_data(const float*, const float*, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
+int head_bwd_weight(const void*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+int sgd_flat(float*, const float*, float*, const long long*, const int*, const int*, int, float, float, float, float, cudaStream_t);
+
+}  // namespace pcrl
+
+using namespace pcrl;
+#define ST(s) ((cudaStream_t)(s))
+#define NONNULL(p) PCRL_REQUIRE((p) != nullptr, "%s: argument %s is NULL", __func__, #p)
+
+extern "C" {
+
+const char* pcrl_last_error(void) { return last_error_buf(); }
+int pcrl_version(void) { return 100; }
+
+int pcrl_pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, void* stream) {
+  NONNULL(w); NONNULL(wf);
+  return pack_conv3_weights(w, wf, wd, Cout, Cin, ST(stream));
+}
+int pcrl_unpack_conv3_wgrad(const float* gpk, float* g, int Cout, int Cin, void* stream) {
+  NONNULL(gpk); NONNULL(g);
+  return unpack_conv3_wgrad(gpk, g, Cout, Cin, ST(stream));
+}
+int pcrl_pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, void* stream) {
+  NONNULL(w); NONNULL(wf); NONNULL(wd);
+  return pack_convT_weights(w, wf, wd, Cin, Cout, ST(stream));
+}
+int pcrl_unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, void* stream) {
+  NONNULL(gpk); NONNULL(g);
+  return unpack_convT_wgrad(gpk, g, Cin, Cout, ST(stream));
+}
+
+int pcrl_conv3d_k3_fprop(const void* x, const void* wf, void* y, double* stats, int stats_per_sample,
+                         int out_fp32, int N, int D, int H, int W, int Cin, int Cout, void* stream) {
+  NONNULL(x); NONNULL(wf); NONNULL(y);
+  return conv3d_k3_igemm(x, wf, y, stats, stats_per_sample, out_fp32, N, D, H, W, Cin, Cout, ST(stream));
+}
+int pcrl_conv3d_k3_dgrad(const void* dy, const void* wd, void* dx, int N, int D, int H, int W,
+                         int Cin, int Cout, void* stream) {
+  NONNULL(dy); NONNULL(wd); NONNULL(dx);
+  // the data gradient is a 3x3x3 convolution of dy (Cout channels) with the mirrored, transposed
+  // filter: same kernel with the channel roles swapped
+  return conv3d_k3_igemm(dy, wd, dx, nullptr, 0, 0, N, D, H, W, Cout, Cin, ST(stream));
+}
+int pcrl_conv3d_k3_wgrad(const void* dy, const void* x, float* dw_packed, int N, int D, int H, int W,
+                         int Cin, int Cout, void* stream) {
+  NONNULL(dy); NONNULL(x); NONNULL(dw_packed);
+  return conv3d_k3_wgrad_igemm(dy, x, dw_packed, N, D, H, W, Cin, Cout, ST(stream));
+}
+
+int pcrl_stem_conv_fprop(const float* x, const float* w, void* y, double* stats, int stats_per_sample,
+                         int N, int D, int H, int W, void* stream) {
+  NONNULL(x); NONNULL(w); NONNULL(y);
+  return stem_conv_fprop(x, w, y, stats, stats_per_sample, N, D, H, W, ST(stream));
+}
+int pcrl_stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int H, int W,
+                         void* stream) {
+  NONNULL(dy); NONNULL(x); NONNULL(dw);
+  return stem_conv_wgrad(dy, x, dw, N, D, H, W, ST(stream));
+}
+
+int pcrl_convT3d_k2s2_fprop(const void* x, const void* wf, const float* bias, void* y_fine, int N,
+                            int D, int H, int W, int Cin, int Cout, void* stream) {
+  NONNULL(x); NONNULL(wf); NONNULL(y_fine);
+  const long long rows = (long long)N * D * (H + 1) * W;
+  int rc = gemm_nt_igemm(x, wf, y_fine, bias, rows, Cin, 8 * Cout, Cout, 0, /*OUT_CONVT*/ 2, D, H, W,
+                         Cout, ST(stream));
+  if (rc) return rc;
+  return zero_pad_rows(y_fine, (long long)N * 2 * D, 2 * H + 1, 2 * W * Cout, ST(stream));
+}
+int pcrl_convT3d_k2s2_bwd(const void* g_fine, const void* x, const void* wd, void* scratch, void* dx,
+                          float* dw_packed, float* dbias, int N, int D, int H, int W, int Cin,
+                          int Cout, void* stream) {
+  NONNULL(g_fine); NONNULL(scratch);
+  const long long rows = (long long)N * D * (H + 1) * W;
+  int rc = convT_unshuffle(g_fine, scratch, dbias, N, D, H, W, Cout, ST(stream));
+  if (rc) return rc;
+  if (dx) {
+    NONNULL(wd);
+    rc = gemm_nt_igemm(scratch, wd, dx, nullptr, rows, 8 * Cout, Cin, Cin, 0, /*OUT_ROWS*/ 1, 0, 0, 0, 0,
+                       ST(stream));
+    if (rc) return rc;
+  }
+  if (dw_packed) {
+    NONNULL(x);
+    rc = gemm_tn_igemm(scratch, x, dw_packed, rows, 8 * Cout, Cin, ST(stream));
+    if (rc) return rc;
+  }
+  return PCRL_OK;
+}
+
+int pcrl_norm_finalize(const double* stats, double count, const float* gamma, const float* beta,
+                       const float* conv_bias, float* running_mean, float* running_var,
+                       long long* nbt, float momentum, float eps, float* scale, float* shift,
+                       float* mean, float* invstd, int G, int C, void* stream) {
+  NONNULL(stats); NONNULL(gamma); NONNULL(beta); NONNULL(scale); NONNULL(shift); NONNULL(mean); NONNULL(invstd);
+  return norm_finalize(stats, count, gamma, beta, conv_bias, running_mean, running_var, nbt, momentum,
+                       eps, scale, shift, mean, invstd, G, C, ST(stream));
+}
+int pcrl_norm_act_fwd(const void* y, const float* scale, const float* shift, const float* prelu,
+                      void* a_out, void* pool_out, float* avg_sum, int per_sample, int act, int pool,
+                      int N, int D, int H, int W, int C, void* stream) {
+  NONNULL(y); NONNULL(scale); NONNULL(shift);
+  return norm_act_fwd(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H,
+                      W, C, ST(stream));
+}
+int pcrl_norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gavg,
+                      const float* scale, const float* shift, const float* mean, const float* invstd,
+                      const float* gamma, const float* prelu, double* sums, void* dy, double count,
+                      int per_sample, int act, int pool, int pass, int N, int D, int H, int W, int C,
+                      void* stream) {
+  NONNULL(y); NONNULL(scale); NONNULL(shift); NONNULL(mean); NONNULL(invstd); NONNULL(sums);
+  if (pass == 1) { NONNULL(dy); NONNULL(gamma); }
+  return norm_act_bwd(y, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu, sums, dy, count,
+                      per_sample, act, pool, pass, N, D, H, W, C, ST(stream));
+}
+int pcrl_zero_pad_rows(void* t, long long planes, int H1, int row_elems, void* stream) {
+  NONNULL(t);
+  return zero_pad_rows(t, planes, H1, row_elems, ST(stream));
+}
+
+int pcrl_head_fwd(const void* a, const float* w3, const float* b3, const float* w1, const float* b1,
+                  float* y1, float* y0, int N, int D, int H, int W, int C, void* stream) {
+  NONNULL(a); NONNULL(w3); NONNULL(b3); NONNULL(y1);
+  return head_fwd(a, w3, b3, w1, b1, y1, y0, N, D, H, W, C, ST(stream));
+}
+int pcrl_head_bwd_data(const float* dy1, const float* w3, const float* dy0, const float* w1, void* da,
+                       int N, int D, int H, int W, int C, void* stream) {
+  NONNULL(dy1); NONNULL(w3); NONNULL(da);
+  return head_bwd_data(dy1, w3, dy0, w1, da, N, D, H, W, C, ST(stream));
+}
+int pcrl_head_bwd_weight(const void* a, const float* dy1, const float* dy0, float* dw3, float* dw1,
+                         int N, int D, int H, int W, int C, void* stream) {
+  NONNULL(a); NONNULL(dy1); NONNULL(dw3);
+  return head_bwd_weight(a, dy1, dy0, dw3, dw1, N, D, H, W, C, ST(stream));
+}
+
+int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
+                 int cols, int ldc, int out_fp32, void* stream) {
+  NONNULL(a); NONNULL(b); NONNULL(c);
+  return gemm_nt_igemm(a, b, c, bias, rows, K, cols, ldc, out_fp32, /*OUT_ROWS*/ 1, 0, 0, 0, 0, ST(stream));
+}
+int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, void* stream) {
+  NONNULL(a); NONNULL(b); NONNULL(c);
+  return gemm_tn_igemm(a, b, c, rows, P, Q, ST(stream));
+}
+
+int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf, const long long* seg_offsets,
+                  const int* seg_active, const int* seg_first, int nseg, float lr, float momentum,
+                  float weight_decay, float grad_scale, void* stream) {
+  NONNULL(params); NONNULL(grads); NONNULL(momentum_buf); NONNULL(seg_offsets); NONNULL(seg_active); NONNULL(seg_first);
+  return sgd_flat(params, grads, momentum_buf, seg_offsets, seg_active, seg_first, nseg, lr, momentum,
+                  weight_decay, grad_scale, ST(stream));
+}
+
+}  // extern "C"

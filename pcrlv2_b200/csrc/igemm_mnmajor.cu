@@ -1,0 +1,300 @@
+// MN-major implicit-GEMM on tcgen05 (sm_100a): weight gradients.
+//
+//   dW[tap][co][ci] += sum_{n, f} dY[n][f][co] * X[n][f + shift(tap)][ci]       (3x3x3 conv)
+//   dW[p][q]        += sum_r A[r][p] * B[r][q]                                 (plain A^T B)
+//
+// Both operands keep the reduction index (the voxel / row) as their slab row and the channel as
+// the contiguous dimension, i.e. they are "MN-major" for the tensor core: no transposes are
+// materialised.  The reduction is split over CTAs (grid.x); every CTA adds its fp32 partial into
+// dW with 16-byte vector reductions (red.global.add.v4.f32), so dW must be zeroed (or hold a
+// running sum) on entry.  In CONV mode a CTA owns one (dz, dy) pair and computes the three dx
+// taps from one X slab (row-shifted views), K-stages are `nrows` merged rows of one sample in the
+// flat index space of common.cuh; tails of the stage buffers are zero so the K loop can run in
+// whole 16-row steps.
+// Reference: autograd of nn.Conv3d / nn.ConvTranspose3d / nn.Linear weights reached from
+// train_3d.py:148 (loss.backward()).
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace pcrl {
+
+enum { WG_CONV = 0, WG_PLAIN = 1 };
+
+struct WgradParams {
+  int mode;
+  int W, Wp, H1, MR, nsamples;
+  int nrows;          // merged rows per K-stage (CONV) / rows per K-stage (PLAIN)
+  int kr;             // reduction rows per stage: nrows*Wp (CONV) / nrows (PLAIN)
+  int ksteps;         // ceil(kr/16)
+  int stages_per_sample, total_stages, stages_per_cta;
+  int mc, nc;         // M (dY / A channels) and N (X / B channels) per CTA
+  int a_row_bytes, b_row_bytes;          // 128 (64-channel chunks) or 64 (32-channel chunk)
+  int a_chunks, b_chunks;                // 64-channel chunks in mc / nc
+  int a_chunk_bytes, b_chunk_bytes;      // bytes of one chunk region in smem (1024-aligned)
+  int b_box_rows;                        // rows written by the X TMA box
+  int ntaps;                             // taps per CTA (3 in CONV, 1 in PLAIN)
+  int stages, tmem_cols;
+  int m_chunks_total;                    // Cout / mc
+  int cout, cin;                         // leading dims of dW: [tap][cout][cin]
+  long long rows_total;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(128)
+igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb,
+                     const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_stage_bytes = p.a_chunks * p.a_chunk_bytes;
+  const int b_stage_bytes = p.b_chunks * p.b_chunk_bytes;
+  const int stage_bytes = a_stage_bytes + b_stage_bytes;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* acc_full = empty + p.stages;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunk = blockIdx.x;
+  const int grp = blockIdx.y;  // (dz,dy) pair in CONV mode
+  const int mchunk = blockIdx.z % p.m_chunks_total, nchunk = blockIdx.z / p.m_chunks_total;
+  const int dzo = grp / 3 - 1, dyo = grp % 3 - 1;
+
+  // zero all stage buffers once: tails beyond what TMA writes must be finite (dY tails: zero)
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = p.stages * stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&ta);
+    tma_prefetch_desc(&tb);
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  fence_proxy_async();  // generic-proxy zero fill must be visible to the async proxy (TMA / MMA)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int s_begin = kchunk * p.stages_per_cta;
+  const int s_end = min(s_begin + p.stages_per_cta, p.total_stages);
+
+  if (warp == 0 && lane == 0) {
+    int st = 0, ph = 0;
+    const uint32_t tx = (uint32_t)(p.a_chunks * p.kr * p.a_row_bytes +
+                                   p.b_chunks * p.b_box_rows * p.b_row_bytes);
+    for (int s = s_begin; s < s_end; s++) {
+      mbar_wait(&empty[st], ph ^ 1);
+      mbar_expect_tx(&full[st], tx);
+      uint8_t* a_dst = smem + (size_t)st * stage_bytes;
+      uint8_t* b_dst = a_dst + a_stage_bytes;
+      if (p.mode == WG_CONV) {
+        const int n = s / p.stages_per_sample;
+        const int mr0 = (s % p.stages_per_sample) * p.nrows;
+        for (int c = 0; c < p.a_chunks; c++)
+          tma_load_4d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st],
+                      mchunk * p.mc + c * 64, -1, mr0, n);
+        for (int c = 0; c < p.b_chunks; c++)
+          tma_load_4d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st],
+                      nchunk * p.nc + c * 64, -1, mr0 + dzo * p.H1 + dyo - 1, n);
+      } else {
+        const int r0 = s * p.nrows;
+        for (int c = 0; c < p.a_chunks; c++)
+          tma_load_2d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st], mchunk * p.mc + c * 64, r0);
+        for (int c = 0; c < p.b_chunks; c++)
+          tma_load_2d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st], nchunk * p.nc + c * 64, r0);
+      }
+      if (++st == p.stages) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    int st = 0, ph = 0;
+    const uint32_t idesc = make_idesc(1, (uint32_t)p.mc, (uint32_t)p.nc, 1, 1);
+    const uint64_t a_hi = make_smem_desc(0, p.a_chunk_bytes, 8 * p.a_row_bytes,
+                                         p.a_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
+    const uint64_t b_hi = make_smem_desc(0, p.b_chunk_bytes, 8 * p.b_row_bytes,
+                                         p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
+    uint32_t accumulate = 0;
+    for (int s = s_begin; s < s_end; s++) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + (size_t)st * stage_bytes);
+      const uint32_t b_base = a_base + a_stage_bytes;
+      for (int t = 0; t < p.ntaps; t++) {
+        const int b_row0 = (p.mode == WG_CONV) ? (p.Wp + (t - 1)) : 0;
+        for (int ks = 0; ks < p.ksteps; ks++) {
+          const uint32_t aa = a_base + (uint32_t)(ks * 16) * p.a_row_bytes;
+          const uint32_t ba = b_base + (uint32_t)(b_row0 + ks * 16) * p.b_row_bytes;
+          umma_bf16(tmem + t * p.nc, a_hi | (uint64_t)((aa >> 4) & 0x3FFF),
+                    b_hi | (uint64_t)((ba >> 4) & 0x3FFF), idesc, (ks > 0) ? 1u : accumulate);
+        }
+      }
+      accumulate = 1;
+      umma_commit(&empty[st]);
+      if (++st == p.stages) { st = 0; ph ^= 1; }
+    }
+    umma_commit(acc_full);
+  }
+  __syncwarp();
+
+  if (s_begin < s_end) {
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    // M = 128: accumulator row i sits in TMEM lane i.  M = 64: lane (i/16)*32 + i%16.
+    int row;
+    bool row_ok;
+    if (p.mc == 128) { row = warp * 32 + lane; row_ok = true; }
+    else { row = warp * 16 + lane; row_ok = lane < 16; }
+    for (int t = 0; t < p.ntaps; t++) {
+      const int tap = (p.mode == WG_CONV) ? grp * 3 + t : 0;
+      float* dst = p.dw + ((size_t)tap * p.cout + (size_t)mchunk * p.mc + row) * p.cin +
+                   (size_t)nchunk * p.nc;
+      for (int c = 0; c < p.nc; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + t * p.nc + c, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            red_add_v4(dst + c + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                       __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+static int launch_wgrad(WgradParams& p, const CUtensorMap& ta, const CUtensorMap& tb, dim3 grid,
+                        cudaStream_t stream) {
+  const int stage_bytes = p.a_chunks * p.a_chunk_bytes + p.b_chunks * p.b_chunk_bytes;
+  p.stages = 3;
+  while (p.stages > 2 && (size_t)p.stages * stage_bytes > 200 * 1024) p.stages--;
+  if ((size_t)p.stages * stage_bytes > 210 * 1024)
+    return fail(PCRL_ERR_ARG, "wgrad: stage of %d bytes does not fit shared memory", stage_bytes);
+  int cols = p.ntaps * p.nc, t = 32;
+  while (t < cols) t <<= 1;
+  p.tmem_cols = t;
+  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  igemm_mnmajor_kernel<<<grid, 128, smem, stream>>>(ta, tb, p);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// dW[27][Cout][Cin] (fp32) += conv3d_k3 weight gradient.
+//   dy: [N][D][H+1][W][Cout] bf16 (pad rows zero), x: [N][D][H+1][W][Cin] bf16 (pad rows zero)
+int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D, int H, int W,
+                          int Cin, int Cout, cudaStream_t stream) {
+  PCRL_REQUIRE(Cout % 64 == 0, "conv3d_k3_wgrad: Cout=%d must be a multiple of 64", Cout);
+  PCRL_REQUIRE(Cin == 32 || Cin % 64 == 0, "conv3d_k3_wgrad: Cin=%d must be 32 or a multiple of 64", Cin);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = WG_CONV;
+  p.W = W; p.Wp = W + 1; p.H1 = H + 1; p.MR = D * (H + 1); p.nsamples = N;
+  // merged rows per stage: aim at ~128..160 reduction rows
+  p.nrows = (128 + p.Wp - 1) / p.Wp;
+  if (p.nrows > p.MR) p.nrows = p.MR;
+  if (p.nrows + 2 > 256) return fail(PCRL_ERR_UNSUPPORTED, "conv3d_k3_wgrad: W too small");
+  p.kr = p.nrows * p.Wp;
+  p.ksteps = (p.kr + 15) / 16;
+  p.stages_per_sample = (p.MR + p.nrows - 1) / p.nrows;
+  p.total_stages = p.stages_per_sample * N;
+  p.mc = (Cout % 128 == 0) ? 128 : 64;
+  p.nc = (Cin % 128 == 0) ? 128 : (Cin % 64 == 0 ? 64 : 32);
+  p.a_row_bytes = 128; p.a_chunks = p.mc / 64;
+  p.b_row_bytes = (p.nc == 32) ? 64 : 128; p.b_chunks = (p.nc == 32) ? 1 : p.nc / 64;
+  p.a_chunk_bytes = round_up(p.ksteps * 16 * p.a_row_bytes, 1024);
+  p.b_box_rows = (p.nrows + 2) * p.Wp;
+  const int b_rows_needed = p.ksteps * 16 + p.Wp + 2;
+  p.b_chunk_bytes = round_up((b_rows_needed > p.b_box_rows ? b_rows_needed : p.b_box_rows) * p.b_row_bytes, 1024);
+  p.ntaps = 3;
+  p.m_chunks_total = Cout / p.mc;
+  p.cout = Cout; p.cin = Cin; p.dw = dw;
+  // split the reduction so that the grid has a few waves
+  const int other = 9 * (Cout / p.mc) * (Cin / p.nc);
+  int kchunks = (4 * num_sms() + other - 1) / other;
+  if (kchunks > p.total_stages) kchunks = p.total_stages;
+  if (kchunks < 1) kchunks = 1;
+  p.stages_per_cta = (p.total_stages + kchunks - 1) / kchunks;
+  kchunks = (p.total_stages + p.stages_per_cta - 1) / p.stages_per_cta;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)p.MR, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)p.MR * W * Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)p.Wp, (uint32_t)p.nrows, 1};
+    int rc = encode_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)p.MR, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)p.MR * W * Cin * 2};
+    uint32_t box[4] = {(uint32_t)(p.nc == 32 ? 32 : 64), (uint32_t)p.Wp, (uint32_t)(p.nrows + 2), 1};
+    int rc = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, str, box,
+                        p.nc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)kchunks, 9, (unsigned)((Cout / p.mc) * (Cin / p.nc)));
+  return launch_wgrad(p, ta, tb, grid, stream);
+}
+
+// dW[P][Q] (fp32, leading dimension Q) += A[rows][P]^T * B[rows][Q]; A, B bf16 row-major.
+int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P, int Q,
+                  cudaStream_t stream) {
+  PCRL_REQUIRE(P % 64 == 0 && Q % 64 == 0, "gemm_tn: P=%d, Q=%d must be multiples of 64", P, Q);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = WG_PLAIN;
+  p.nrows = 128; p.kr = 128; p.ksteps = 8;
+  p.total_stages = (int)((rows + 127) / 128);
+  p.stages_per_sample = p.total_stages;
+  p.mc = (P % 128 == 0) ? 128 : 64;
+  p.nc = (Q % 128 == 0) ? 128 : 64;
+  p.a_row_bytes = 128; p.b_row_bytes = 128;
+  p.a_chunks = p.mc / 64; p.b_chunks = p.nc / 64;
+  p.a_chunk_bytes = 128 * 128; p.b_chunk_bytes = 128 * 128;
+  p.b_box_rows = 128;
+  p.ntaps = 1;
+  p.m_chunks_total = P / p.mc;
+  p.cout = P; p.cin = Q; p.dw = dw; p.rows_total = rows;
+  const int other = (P / p.mc) * (Q / p.nc);
+  int kchunks = (2 * num_sms() + other - 1) / other;
+  if (kchunks > p.total_stages) kchunks = p.total_stages;
+  if (kchunks < 1) kchunks = 1;
+  p.stages_per_cta = (p.total_stages + kchunks - 1) / kchunks;
+  kchunks = (p.total_stages + p.stages_per_cta - 1) / p.stages_per_cta;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {(uint64_t)P, (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)P * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = encode_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Q, (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)Q * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)kchunks, 1, (unsigned)((P / p.mc) * (Q / p.nc)));
+  return launch_wgrad(p, ta, tb, grid, stream);
+}
+
+}  // namespace pcrl

@@ -1,0 +1,764 @@
+// HBM-bound kernels of the PCRLv2 3-D path: weight packers, the Cin=1 stem convolution, the
+// norm(+activation)(+2x2x2 max-pool)(+global-average-pool sums) forward pass and its two-pass
+// backward, ConvTranspose gradient un-shuffle.  All activations are H-padded NDHWC bf16
+// (common.cuh); every producer writes the zero pad row of each plane itself.
+//
+// Reference ops replaced (models/pcrlv2_model_3d.py): BatchNorm3d / InstanceNorm3d :11-16,
+// ReLU / PReLU / ELU / Sigmoid :20-27, MaxPool3d(2) :100,115-117, adaptive_avg_pool3d :67,
+// Conv3d(1->32) :114 (down_tr64.ops.0), ConvTranspose3d :52 (backward re-layout).
+#include "common.cuh"
+
+namespace pcrl {
+
+enum { ACT_RELU = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_SIGMOID = 3, ACT_NONE = 4 };
+
+struct bf16x8 {
+  uint4 u;
+};
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(z, 0.f);
+    case ACT_PRELU: return z > 0.f ? z : slope * z;
+    case ACT_ELU: return z > 0.f ? z : expm1f(z);
+    case ACT_SIGMOID: return 1.f / (1.f + __expf(-z));
+    default: return z;
+  }
+}
+// derivative of the activation wrt its input z
+__device__ __forceinline__ float act_bwd(float z, int act, float slope) {
+  switch (act) {
+    case ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case ACT_PRELU: return z > 0.f ? 1.f : slope;
+    case ACT_ELU: return z > 0.f ? 1.f : __expf(z);
+    case ACT_SIGMOID: { float s = 1.f / (1.f + __expf(-z)); return s * (1.f - s); }
+    default: return 1.f;
+  }
+}
+
+// ------------------------------------------------------------------------------ weight packers
+// w [Cout][Cin][27] fp32 -> wf [27][Cout][Cin] bf16 (forward) and wd [27][Cin][Cout] bf16 with
+// the taps mirrored (data gradient).
+__global__ void pack_conv3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
+  const long long total = (long long)Cout * Cin * 27;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 27);
+    const long long r = i / 27;
+    const int ci = (int)(r % Cin), co = (int)(r / Cin);
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    wf[((size_t)tap * Cout + co) * Cin + ci] = v;
+    if (wd) wd[((size_t)(26 - tap) * Cin + ci) * Cout + co] = v;
+  }
+}
+// gpk [27][Cout][Cin] fp32 -> g [Cout][Cin][27] fp32
+__global__ void unpack_conv3_wgrad_kernel(const float* __restrict__ gpk, float* __restrict__ g,
+                                          int Cout, int Cin) {
+  const long long total = (long long)Cout * Cin * 27;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 27);
+    const long long r = i / 27;
+    const int ci = (int)(r % Cin), co = (int)(r / Cin);
+    g[i] = gpk[((size_t)tap * Cout + co) * Cin + ci];
+  }
+}
+// w [Cin][Cout][8] fp32 -> wf [(t,co)][Cin] bf16 (forward B operand) and wd [Cin][(t,co)] bf16
+__global__ void pack_convT_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd, int Cin, int Cout) {
+  const long long total = (long long)Cin * Cout * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % 8);
+    const long long r = i / 8;
+    const int co = (int)(r % Cout), ci = (int)(r / Cout);
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    wf[((size_t)t * Cout + co) * Cin + ci] = v;
+    wd[(size_t)ci * (8 * Cout) + (size_t)t * Cout + co] = v;
+  }
+}
+// gpk [(t,co)][Cin] fp32 -> g [Cin][Cout][8]
+__global__ void unpack_convT_wgrad_kernel(const float* __restrict__ gpk, float* __restrict__ g,
+                                          int Cin, int Cout) {
+  const long long total = (long long)Cin * Cout * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % 8);
+    const long long r = i / 8;
+    const int co = (int)(r % Cout), ci = (int)(r / Cout);
+    g[i] = gpk[((size_t)t * Cout + co) * Cin + ci];
+  }
+}
+
+// ------------------------------------------------------------------------------ stem conv, Cin = 1
+// x [N][D][H][W] fp32 (C = 1, so NCDHW == NDHWC), w [32][27] fp32, y H-padded bf16 [N][D][H+1][W][32].
+// One thread per output voxel, 32 output channels in registers; statistics as in the igemm epilogue.
+__global__ void __launch_bounds__(128)
+stem_conv_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                       __nv_bfloat16* __restrict__ y, double* __restrict__ stats,
+                       int stats_per_sample, int N, int D, int H, int W) {
+  __shared__ float ws[27][32];
+  __shared__ float st[2][32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i % 27][i / 27] = w[i];
+  if (threadIdx.x < 64) st[threadIdx.x / 32][threadIdx.x % 32] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int H1 = H + 1;
+  const int slots = D * H1 * W;  // voxel slots of one sample, pad rows included
+  const int lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) acc[i] = 0.f;
+  bool real = false;
+  if (slot < slots) {
+    const int wq = slot % W;
+    const int hp = (slot / W) % H1;
+    const int d = slot / (W * H1);
+    real = hp >= 1;
+    if (real) {
+      const int h = hp - 1;
+      const float* xs = x + (size_t)n * D * H * W;
+#pragma unroll
+      for (int kz = 0; kz < 3; kz++) {
+        const int zz = d + kz - 1;
+        if (zz < 0 || zz >= D) continue;
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+          const int yy = h + ky - 1;
+          if (yy < 0 || yy >= H) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; kx++) {
+            const int xx = wq + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const float v = __ldg(&xs[((size_t)zz * H + yy) * W + xx]);
+            const float* wt = ws[(kz * 3 + ky) * 3 + kx];
+#pragma unroll
+            for (int c = 0; c < 32; c++) acc[c] = fmaf(v, wt[c], acc[c]);
+          }
+        }
+      }
+    }
+    // store (pad rows get zeros)
+    uint4* o = reinterpret_cast<uint4*>(y + ((size_t)n * slots + slot) * 32);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) f[j] = acc[8 * i + j];
+      const uint4 u = pack8(f);
+      o[i] = u;
+      float r[8];
+      unpack8(u, r);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[8 * i + j] = r[j];  // statistics over the stored values
+    }
+  }
+  if (stats) {
+    float s1[32], s2[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) { s1[i] = real ? acc[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; i++) {
+        const float a1 = up ? s1[i] : s1[i + s], k1 = up ? s1[i + s] : s1[i];
+        s1[i] = k1 + __shfl_xor_sync(0xffffffffu, a1, s);
+        const float a2 = up ? s2[i] : s2[i + s], k2 = up ? s2[i + s] : s2[i];
+        s2[i] = k2 + __shfl_xor_sync(0xffffffffu, a2, s);
+      }
+    }
+    atomicAdd(&st[0][lane], s1[0]);
+    atomicAdd(&st[1][lane], s2[0]);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double* g = stats + (stats_per_sample ? (size_t)n * 64 : 0);
+      atomicAdd(&g[threadIdx.x * 2 + 0], (double)st[0][threadIdx.x]);
+      atomicAdd(&g[threadIdx.x * 2 + 1], (double)st[1][threadIdx.x]);
+    }
+  }
+}
+
+// dw[32][27] += sum_v dy[v][co] * x[v + tap]; lane = output channel, one warp per run of voxels.
+__global__ void __launch_bounds__(256)
+stem_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                       float* __restrict__ dw, int N, int D, int H, int W, int vox_per_warp) {
+  __shared__ float red[27][32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) red[i / 32][i % 32] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = (long long)N * D * H * W;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; i++) acc[i] = 0.f;
+  const long long v0 = gw * vox_per_warp;
+  for (long long v = v0; v < v0 + vox_per_warp && v < total; v++) {
+    const int wq = (int)(v % W);
+    const int h = (int)((v / W) % H);
+    const int d = (int)((v / ((long long)W * H)) % D);
+    const int n = (int)(v / ((long long)W * H * D));
+    const float g = __bfloat162float(
+        dy[((((size_t)n * D + d) * (H + 1) + h + 1) * W + wq) * 32 + lane]);
+    const float* xs = x + (size_t)n * D * H * W;
+#pragma unroll
+    for (int kz = 0; kz < 3; kz++) {
+      const int zz = d + kz - 1;
+#pragma unroll
+      for (int ky = 0; ky < 3; ky++) {
+        const int yy = h + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+          const int xx = wq + kx - 1;
+          const bool in = zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
+          const float xv = in ? __ldg(&xs[((size_t)zz * H + yy) * W + xx]) : 0.f;
+          acc[(kz * 3 + ky) * 3 + kx] = fmaf(g, xv, acc[(kz * 3 + ky) * 3 + kx]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 27; t++) atomicAdd(&red[t][lane], acc[t]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) {
+    const int t = i / 32, co = i % 32;
+    atomicAdd(&dw[co * 27 + t], red[t][co]);
+  }
+}
+
+// ------------------------------------------------------------------------------ norm finalize
+// stats [G][C][2] fp64 (sum, sum of squares over `count` elements per (g, c)); G = 1 for
+// BatchNorm, N for InstanceNorm.  Produces scale/shift (y*scale + shift = gamma*xhat + beta) and
+// saves mean / invstd for the backward pass.  BatchNorm running statistics follow
+// torch.nn.functional.batch_norm(training=True, momentum): biased variance to normalise, unbiased
+// into running_var; `conv_bias` is the bias the convolution did NOT add (it cancels under the
+// normalisation, SURVEY note N1) and is folded into running_mean.
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, double count,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ conv_bias,
+                                     float* __restrict__ running_mean, float* __restrict__ running_var,
+                                     long long* __restrict__ num_batches_tracked, float momentum,
+                                     float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                     float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                     int G, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (i >= G * C) return;
+  const int c = i % C;
+  const double m = stats[2 * i] / count;
+  double var = stats[2 * i + 1] / count - m * m;
+  if (var < 0) var = 0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scale[i] = sc;
+  shift[i] = beta[c] - (float)m * sc;
+  mean_out[i] = (float)m;
+  invstd_out[i] = invstd;
+  if (running_mean) {
+    const float mb = (float)m + (conv_bias ? conv_bias[c] : 0.f);
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mb;
+    const double unb = count > 1 ? var * count / (count - 1) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+// ------------------------------------------------------------------------------ norm + act forward
+// y [N][D][H+1][W][C] bf16 -> a = act(y*scale + shift), written as
+//   a_out    full resolution (nullable),
+//   pool_out 2x2x2 max-pool, H-padded [N][D/2][H/2+1][W/2][C] (nullable),
+//   avg_sum  [N][C] fp32 += sum over voxels of a (nullable; caller zeroes; divide by D*H*W later).
+// One thread owns 8 channels of one 2x2x2 cell (pool) or one voxel (no pool).
+struct NormActFwdParams {
+  const __nv_bfloat16* y;
+  const float* scale; const float* shift; const float* prelu;
+  __nv_bfloat16* a_out; __nv_bfloat16* pool_out; float* avg_sum;
+  int per_sample, act, N, D, H, W, C;
+};
+
+template <bool POOL>
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParams p) {
+  extern __shared__ float red[];  // [blockDim.x][8] when avg_sum
+  const int n = blockIdx.y;
+  const int C8 = p.C >> 3;
+  const int H1 = p.H + 1;
+  const int cd = POOL ? p.D / 2 : p.D, ch = POOL ? p.H / 2 : p.H, cw = POOL ? p.W / 2 : p.W;
+  const int cells = cd * (ch + 1) * cw;  // +1: the pad row of the (pooled / full) output
+  const long long items = (long long)cells * C8;
+  float asum[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) asum[i] = 0.f;
+  // blockDim.x is a multiple of C8, gridDim.x*blockDim.x too: a thread keeps its channel group
+  const int c8 = threadIdx.x % C8;
+  float sc[8], sh[8], sl[8];
+  {
+    const size_t o = (p.per_sample ? (size_t)n * p.C : 0) + c8 * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      sc[i] = p.scale[o + i];
+      sh[i] = p.shift[o + i];
+      sl[i] = p.prelu ? p.prelu[c8 * 8 + i] : 0.f;
+    }
+  }
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(it / C8);
+    const int wq = cell % cw;
+    const int hp = (cell / cw) % (ch + 1);
+    const int d = cell / (cw * (ch + 1));
+    if (hp == 0) {  // pad rows of the outputs
+      if (POOL) {
+        if (p.pool_out)
+          *reinterpret_cast<uint4*>(p.pool_out + (((size_t)n * cd + d) * (ch + 1) * cw + wq) * p.C + c8 * 8) =
+              make_uint4(0, 0, 0, 0);
+        if (p.a_out) {  // two fine planes, their pad rows, two fine columns
+          for (int i = 0; i < 2; i++)
+            for (int k = 0; k < 2; k++)
+              *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * wq + k) * p.C + c8 * 8) =
+                  make_uint4(0, 0, 0, 0);
+        }
+      } else if (p.a_out) {
+        *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + d) * H1) * p.W + wq) * p.C + c8 * 8) =
+            make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    const int h = hp - 1;
+    if (POOL) {
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) mx[i] = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8;
+            float v[8];
+            unpack8(*reinterpret_cast<const uint4*>(p.y + off), v);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              v[q] = act_fwd(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
+              mx[q] = fmaxf(mx[q], v[q]);
+              asum[q] += v[q];
+            }
+            if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off) = pack8(v);
+          }
+      if (p.pool_out)
+        *reinterpret_cast<uint4*>(p.pool_out + ((((size_t)n * cd + d) * (ch + 1) + hp) * cw + wq) * p.C + c8 * 8) = pack8(mx);
+    } else {
+      const size_t off = ((((size_t)n * p.D + d) * H1 + hp) * p.W + wq) * p.C + c8 * 8;
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.y + off), v);
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        v[q] = act_fwd(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
+      }
+      const uint4 u = pack8(v);
+      if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off) = u;
+      if (p.avg_sum) {
+        float r[8];
+        unpack8(u, r);  // average the stored (rounded) activations
+#pragma unroll
+        for (int q = 0; q < 8; q++) asum[q] += r[q];
+      }
+    }
+  }
+  if (p.avg_sum) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) red[threadIdx.x * 8 + q] = asum[q];
+    __syncthreads();
+    if (threadIdx.x < C8) {
+      float t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) t[q] = 0.f;
+      for (int j = threadIdx.x; j < blockDim.x; j += C8)
+#pragma unroll
+        for (int q = 0; q < 8; q++) t[q] += red[j * 8 + q];
+#pragma unroll
+      for (int q = 0; q < 8; q++) atomicAdd(&p.avg_sum[(size_t)n * p.C + threadIdx.x * 8 + q], t[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ norm + act backward
+// Upstream gradient wrt a = act(z), z = y*scale + shift:
+//   g1: H-padded bf16, full resolution, or (POOL) the gradient wrt the 2x2x2 max-pooled tensor,
+//       routed to the first maximum of each cell (torch's MaxPool3d tie rule);
+//   g2: optional second full-resolution gradient (bf16), added;
+//   gavg: optional [N][C] fp32 gradient wrt the global average pool; adds gavg/(D*H*W).
+// pass 1 accumulates per (group, channel): sum dz, sum dz*xhat (and sum dA*min(z,0) for PReLU);
+// pass 2 writes dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), pad rows zero.
+struct NormActBwdParams {
+  const __nv_bfloat16* y; const __nv_bfloat16* g1; const __nv_bfloat16* g2; const float* gavg;
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  const float* gamma; const float* prelu;
+  double* sums;      // [G][C][3]
+  __nv_bfloat16* dy; // pass 2
+  double count;      // elements per (group, channel)
+  int per_sample, act, N, D, H, W, C;
+};
+
+template <bool POOL, bool APPLY>
+__global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParams p) {
+  extern __shared__ float red[];  // pass 1: [blockDim.x][24]
+  const int n = blockIdx.y;
+  const int C8 = p.C >> 3;
+  const int H1 = p.H + 1;
+  const int cd = POOL ? p.D / 2 : p.D, ch = POOL ? p.H / 2 : p.H, cw = POOL ? p.W / 2 : p.W;
+  const int cells = cd * (ch + 1) * cw;
+  const long long items = (long long)cells * C8;
+  const int c8 = threadIdx.x % C8;
+  const size_t so = (p.per_sample ? (size_t)n * p.C : 0) + c8 * 8;
+  float sc[8], sh[8], sl[8], mu[8], is[8], k1[8], k2[8], gs[8], ga[8];
+  const float inv_vol = 1.f / ((float)p.D * p.H * p.W);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    sc[i] = p.scale[so + i];
+    sh[i] = p.shift[so + i];
+    mu[i] = p.mean[so + i];
+    is[i] = p.invstd[so + i];
+    sl[i] = p.prelu ? p.prelu[c8 * 8 + i] : 0.f;
+    ga[i] = p.gavg ? p.gavg[(size_t)n * p.C + c8 * 8 + i] * inv_vol : 0.f;
+    if (APPLY) {
+      const double* s = p.sums + (so + i) * 3;
+      k1[i] = (float)(s[0] / p.count);
+      k2[i] = (float)(s[1] / p.count);
+      gs[i] = p.gamma[c8 * 8 + i] * is[i];
+    }
+  }
+  float a0[8], a1[8], a2[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a0[i] = a1[i] = a2[i] = 0.f;
+
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(it / C8);
+    const int wq = cell % cw;
+    const int hp = (cell / cw) % (ch + 1);
+    const int d = cell / (cw * (ch + 1));
+    if (hp == 0) {
+      if (APPLY) {
+        if (POOL) {
+          for (int i = 0; i < 2; i++)
+            for (int k = 0; k < 2; k++)
+              *reinterpret_cast<uint4*>(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * wq + k) * p.C + c8 * 8) =
+                  make_uint4(0, 0, 0, 0);
+        } else {
+          *reinterpret_cast<uint4*>(p.dy + ((((size_t)n * p.D + d) * H1) * p.W + wq) * p.C + c8 * 8) =
+              make_uint4(0, 0, 0, 0);
+        }
+      }
+      continue;
+    }
+    const int h = hp - 1;
+    if (POOL) {
+      float gp[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.g1 + ((((size_t)n * cd + d) * (ch + 1) + hp) * cw + wq) * p.C + c8 * 8), gp);
+      float yv[8][8];   // [position][channel]
+      float zv[8][8];
+      int arg[8];
+      float mx[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) { mx[q] = -INFINITY; arg[q] = 0; }
+#pragma unroll
+      for (int pos = 0; pos < 8; pos++) {
+        const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
+        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8;
+        unpack8(*reinterpret_cast<const uint4*>(p.y + off), yv[pos]);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          zv[pos][q] = fmaf(yv[pos][q], sc[q], sh[q]);
+          // same fp32 values and scan order as the forward pass: the first maximum wins
+          const float a = act_fwd(zv[pos][q], p.act, sl[q]);
+          if (a > mx[q]) { mx[q] = a; arg[q] = pos; }
+        }
+      }
+#pragma unroll
+      for (int pos = 0; pos < 8; pos++) {
+        const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
+        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8;
+        float g2v[8];
+        if (p.g2) unpack8(*reinterpret_cast<const uint4*>(p.g2 + off), g2v);
+        float out[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          float da = (arg[q] == pos ? gp[q] : 0.f) + ga[q];
+          if (p.g2) da += g2v[q];
+          const float dz = da * act_bwd(zv[pos][q], p.act, sl[q]);
+          const float xh = (yv[pos][q] - mu[q]) * is[q];
+          if (APPLY) {
+            out[q] = gs[q] * (dz - k1[q] - xh * k2[q]);
+          } else {
+            a0[q] += dz;
+            a1[q] += dz * xh;
+            a2[q] += da * fminf(zv[pos][q], 0.f);
+          }
+        }
+        if (APPLY) *reinterpret_cast<uint4*>(p.dy + off) = pack8(out);
+      }
+    } else {
+      const size_t off = ((((size_t)n * p.D + d) * H1 + hp) * p.W + wq) * p.C + c8 * 8;
+      float yv[8], g1v[8], g2v[8], out[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.y + off), yv);
+      if (p.g1) unpack8(*reinterpret_cast<const uint4*>(p.g1 + off), g1v);
+      if (p.g2) unpack8(*reinterpret_cast<const uint4*>(p.g2 + off), g2v);
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const float z = fmaf(yv[q], sc[q], sh[q]);
+        float da = ga[q];
+        if (p.g1) da += g1v[q];
+        if (p.g2) da += g2v[q];
+        const float dz = da * act_bwd(z, p.act, sl[q]);
+        const float xh = (yv[q] - mu[q]) * is[q];
+        if (APPLY) {
+          out[q] = gs[q] * (dz - k1[q] - xh * k2[q]);
+        } else {
+          a0[q] += dz;
+          a1[q] += dz * xh;
+          a2[q] += da * fminf(z, 0.f);
+        }
+      }
+      if (APPLY) *reinterpret_cast<uint4*>(p.dy + off) = pack8(out);
+    }
+  }
+  if (!APPLY) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      red[threadIdx.x * 24 + q] = a0[q];
+      red[threadIdx.x * 24 + 8 + q] = a1[q];
+      red[threadIdx.x * 24 + 16 + q] = a2[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < C8 * 3) {
+      const int grp = threadIdx.x % C8, which = threadIdx.x / C8;
+      float t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) t[q] = 0.f;
+      for (int j = grp; j < blockDim.x; j += C8)
+#pragma unroll
+        for (int q = 0; q < 8; q++) t[q] += red[j * 24 + which * 8 + q];
+      const size_t o = (p.per_sample ? (size_t)n * p.C : 0) + grp * 8;
+#pragma unroll
+      for (int q = 0; q < 8; q++) atomicAdd(&p.sums[(o + q) * 3 + which], (double)t[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ misc
+// zero the pad row (h' = 0) of every plane of an H-padded tensor with `row_elems` = W*C elements
+__global__ void zero_pad_rows_kernel(__nv_bfloat16* __restrict__ t, long long planes, int H1,
+                                     int row_elems) {
+  const int per = row_elems / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < planes * per;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pl = i / per;
+    const int e = (int)(i % per);
+    reinterpret_cast<uint4*>(t + (size_t)pl * H1 * row_elems)[e] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// ConvTranspose backward re-layout: fine gradient [N][2D][2H+1][2W][C] bf16 -> coarse-major
+// [N*D*(H+1)*W][8*C] bf16 (rows follow the coarse H-padded order, pad rows zero), plus the bias
+// gradient dbias[C] += sum over all fine voxels.
+__global__ void __launch_bounds__(256)
+convT_unshuffle_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ dbias, int N, int D, int H, int W, int C) {
+  extern __shared__ float red[];  // [blockDim.x][8]
+  const int C8 = C >> 3;
+  const long long rows = (long long)N * D * (H + 1) * W;
+  const long long items = rows * 8 * C8;
+  const int c8 = threadIdx.x % C8;
+  float bs[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) bs[i] = 0.f;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)((it / C8) % 8);
+    const long long r = it / (8 * C8);
+    const int w = (int)(r % W);
+    const int hp = (int)((r / W) % (H + 1));
+    const int d = (int)((r / ((long long)W * (H + 1))) % D);
+    const long long n = r / ((long long)W * (H + 1) * D);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (hp >= 1) {
+      const int i = t >> 2, j = (t >> 1) & 1, k = t & 1;
+      const size_t off = ((((size_t)n * 2 * D + 2 * d + i) * (2 * H + 1) + 2 * (hp - 1) + j + 1) * (2 * W) + 2 * w + k) * C + c8 * 8;
+      v = *reinterpret_cast<const uint4*>(g + off);
+      float f[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int q = 0; q < 8; q++) bs[q] += f[q];
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t)r * 8 + t) * C + c8 * 8) = v;
+  }
+  if (dbias) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) red[threadIdx.x * 8 + q] = bs[q];
+    __syncthreads();
+    if (threadIdx.x < C8) {
+      float t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) t[q] = 0.f;
+      for (int j = threadIdx.x; j < blockDim.x; j += C8)
+#pragma unroll
+        for (int q = 0; q < 8; q++) t[q] += red[j * 8 + q];
+#pragma unroll
+      for (int q = 0; q < 8; q++) atomicAdd(&dbias[threadIdx.x * 8 + q], t[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ launch wrappers
+static inline int grid_for(long long items, int block, int max_blocks) {
+  long long b = (items + block - 1) / block;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+// block size: a multiple of C/8 near 256 so that a thread's channel group is loop-invariant
+static inline int block_for_c8(int C8) {
+  int b = (256 / C8) * C8;
+  if (b == 0) b = C8;  // C8 > 256 cannot happen for C <= 2048
+  return b;
+}
+
+int pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s) {
+  const long long total = (long long)Cout * Cin * 27;
+  pack_conv3_kernel<<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+int unpack_conv3_wgrad(const float* gpk, float* g, int Cout, int Cin, cudaStream_t s) {
+  const long long total = (long long)Cout * Cin * 27;
+  unpack_conv3_wgrad_kernel<<<grid_for(total, 256, 4096), 256, 0, s>>>(gpk, g, Cout, Cin);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+int pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, cudaStream_t s) {
+  const long long total = (long long)Cin * Cout * 8;
+  pack_convT_kernel<<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cin, Cout);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+int unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, cudaStream_t s) {
+  const long long total = (long long)Cin * Cout * 8;
+  unpack_convT_wgrad_kernel<<<grid_for(total, 256, 4096), 256, 0, s>>>(gpk, g, Cin, Cout);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+int stem_conv_fprop(const float* x, const float* w, void* y, double* stats, int stats_per_sample,
+                    int N, int D, int H, int W, cudaStream_t s) {
+  const int slots = D * (H + 1) * W;
+  dim3 grid((slots + 127) / 128, N);
+  stem_conv_fprop_kernel<<<grid, 128, 0, s>>>(x, w, (__nv_bfloat16*)y, stats, stats_per_sample, N, D, H, W);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+int stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int H, int W,
+                    cudaStream_t s) {
+  const long long total = (long long)N * D * H * W;
+  const int warps = num_sms() * 16;
+  int vpw = (int)((total + warps - 1) / warps);
+  if (vpw < 1) vpw = 1;
+  const long long nwarps = (total + vpw - 1) / vpw;
+  const int blocks = (int)((nwarps + 7) / 8);
+  stem_conv_wgrad_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)dy, x, dw, N, D, H, W, vpw);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+int norm_finalize(const double* stats, double count, const float* gamma, const float* beta,
+                  const float* conv_bias, float* running_mean, float* running_var,
+                  long long* nbt, float momentum, float eps, float* scale, float* shift,
+                  float* mean, float* invstd, int G, int C, cudaStream_t s) {
+  norm_finalize_kernel<<<(G * C + 127) / 128, 128, 0, s>>>(stats, count, gamma, beta, conv_bias, running_mean,
+                                                          running_var, nbt, momentum, eps, scale, shift,
+                                                          mean, invstd, G, C);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+int norm_act_fwd(const void* y, const float* scale, const float* shift, const float* prelu,
+                 void* a_out, void* pool_out, float* avg_sum, int per_sample, int act, int pool,
+                 int N, int D, int H, int W, int C, cudaStream_t s) {
+  PCRL_REQUIRE(C % 8 == 0, "norm_act_fwd: C=%d must be a multiple of 8", C);
+  PCRL_REQUIRE(!pool || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "norm_act_fwd: pooling needs even dims");
+  PCRL_REQUIRE(!(pool && avg_sum), "norm_act_fwd: avg_sum with pool is not supported");
+  NormActFwdParams p{(const __nv_bfloat16*)y, scale, shift, prelu, (__nv_bfloat16*)a_out,
+                     (__nv_bfloat16*)pool_out, avg_sum, per_sample, act, N, D, H, W, C};
+  const int C8 = C / 8, block = block_for_c8(C8);
+  const long long cells = pool ? (long long)(D / 2) * (H / 2 + 1) * (W / 2) : (long long)D * (H + 1) * W;
+  const int per_thread = pool ? 1 : 4;
+  dim3 grid(grid_for((cells * C8 + per_thread - 1) / per_thread, block, 1 << 20), N);
+  const size_t smem = avg_sum ? (size_t)block * 8 * 4 : 0;
+  if (pool) norm_act_fwd_kernel<true><<<grid, block, smem, s>>>(p);
+  else norm_act_fwd_kernel<false><<<grid, block, smem, s>>>(p);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+// pass = 0: reduce into sums [G][C][3] (caller zeroes), pass = 1: apply (writes dy)
+int norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gavg,
+                 const float* scale, const float* shift, const float* mean, const float* invstd,
+                 const float* gamma, const float* prelu, double* sums, void* dy, double count,
+                 int per_sample, int act, int pool, int pass, int N, int D, int H, int W, int C,
+                 cudaStream_t s) {
+  PCRL_REQUIRE(C % 8 == 0, "norm_act_bwd: C=%d must be a multiple of 8", C);
+  PCRL_REQUIRE(!pool || g1, "norm_act_bwd: pooled backward needs g1");
+  NormActBwdParams p{(const __nv_bfloat16*)y, (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, gavg,
+                     scale, shift, mean, invstd, gamma, prelu, sums, (__nv_bfloat16*)dy, count,
+                     per_sample, act, N, D, H, W, C};
+  const int C8 = C / 8, block = block_for_c8(C8);
+  const long long cells = pool ? (long long)(D / 2) * (H / 2 + 1) * (W / 2) : (long long)D * (H + 1) * W;
+  const int per_thread = pool ? 1 : 4;
+  dim3 grid(grid_for((cells * C8 + per_thread - 1) / per_thread, block, 1 << 20), N);
+  if (pass == 0) {
+    const size_t smem = (size_t)block * 24 * 4;
+    if (pool) norm_act_bwd_kernel<true, false><<<grid, block, smem, s>>>(p);
+    else norm_act_bwd_kernel<false, false><<<grid, block, smem, s>>>(p);
+  } else {
+    if (pool) norm_act_bwd_kernel<true, true><<<grid, block, 0, s>>>(p);
+    else norm_act_bwd_kernel<false, true><<<grid, block, 0, s>>>(p);
+  }
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+int zero_pad_rows(void* t, long long planes, int H1, int row_elems, cudaStream_t s) {
+  PCRL_REQUIRE(row_elems % 8 == 0, "zero_pad_rows: row_elems=%d must be a multiple of 8", row_elems);
+  zero_pad_rows_kernel<<<grid_for(planes * (row_elems / 8), 256, 8192), 256, 0, s>>>((__nv_bfloat16*)t, planes, H1, row_elems);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+int convT_unshuffle(const void* g, void* out, float* dbias, int N, int D, int H, int W, int C,
+                    cudaStream_t s) {
+  PCRL_REQUIRE(C % 8 == 0, "convT_unshuffle: C=%d must be a multiple of 8", C);
+  const int C8 = C / 8, block = block_for_c8(C8);
+  const long long items = (long long)N * D * (H + 1) * W * 8 * C8;
+  const int blocks = grid_for((items + 3) / 4, block, 1 << 20);
+  convT_unshuffle_kernel<<<blocks, block, dbias ? (size_t)block * 8 * 4 : 0, s>>>((const __nv_bfloat16*)g, (__nv_bfloat16*)out, dbias, N, D, H, W, C);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+}  // namespace pcrl

@@ -1,0 +1,252 @@
+"""Tensor-level wrappers around the C ABI (pcrlv2_b200/_lib.py).
+
+Everything here allocates outputs with torch (device memory, stream ordering) and forwards raw
+pointers to libpcrl_b200.so.  Activations are "H-padded NDHWC" bf16 tensors of physical shape
+[N, D, H+1, W, C] (row 0 of every plane zero, voxel row h at index h+1) -- see
+csrc/common.cuh.  ``pad_ndhwc`` / ``unpad_ndhwc`` convert from / to the reference's NCDHW view.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+ACT = {"relu": 0, "prelu": 1, "elu": 2, "sigmoid": 3, "none": 4}
+BF16 = torch.bfloat16
+
+
+def pad_ndhwc(x: torch.Tensor) -> torch.Tensor:
+    """(N,C,D,H,W) float -> [N,D,H+1,W,C] bf16 with the zero pad row."""
+    n, c, d, h, w = x.shape
+    out = torch.zeros((n, d, h + 1, w, c), dtype=BF16, device=x.device)
+    out[:, :, 1:] = x.permute(0, 2, 3, 4, 1)
+    return out
+
+
+def unpad_ndhwc(p: torch.Tensor) -> torch.Tensor:
+    """[N,D,H+1,W,C] -> (N,C,D,H,W) fp32 (drops the pad row)."""
+    return p[:, :, 1:].permute(0, 4, 1, 2, 3).float()
+
+
+def dims_of(p: torch.Tensor):
+    n, d, h1, w, c = p.shape
+    return n, d, h1 - 1, w, c
+
+
+def _chk(t: torch.Tensor, dtype=None):
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    if dtype is not None:
+        assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
+    return t
+
+
+# ------------------------------------------------------------------------------ weights
+def pack_conv3_weights(w: torch.Tensor, need_dgrad: bool = True):
+    """(Cout,Cin,3,3,3) fp32 -> (wf [27,Cout,Cin] bf16, wd [27,Cin,Cout] bf16 or None)."""
+    _chk(w, torch.float32)
+    cout, cin = w.shape[0], w.shape[1]
+    wf = torch.empty((27, cout, cin), dtype=BF16, device=w.device)
+    wd = torch.empty((27, cin, cout), dtype=BF16, device=w.device) if need_dgrad else None
+    _lib.call("pcrl_pack_conv3_weights", w, wf, wd, cout, cin)
+    return wf, wd
+
+
+def unpack_conv3_wgrad(gpk: torch.Tensor) -> torch.Tensor:
+    _chk(gpk, torch.float32)
+    _, cout, cin = gpk.shape
+    g = torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=gpk.device)
+    _lib.call("pcrl_unpack_conv3_wgrad", gpk, g, cout, cin)
+    return g
+
+
+def pack_convT_weights(w: torch.Tensor):
+    """(Cin,Cout,2,2,2) fp32 -> (wf [8*Cout,Cin] bf16, wd [Cin,8*Cout] bf16)."""
+    _chk(w, torch.float32)
+    cin, cout = w.shape[0], w.shape[1]
+    wf = torch.empty((8 * cout, cin), dtype=BF16, device=w.device)
+    wd = torch.empty((cin, 8 * cout), dtype=BF16, device=w.device)
+    _lib.call("pcrl_pack_convT_weights", w, wf, wd, cin, cout)
+    return wf, wd
+
+
+def unpack_convT_wgrad(gpk: torch.Tensor, cin: int, cout: int) -> torch.Tensor:
+    _chk(gpk, torch.float32)
+    g = torch.empty((cin, cout, 2, 2, 2), dtype=torch.float32, device=gpk.device)
+    _lib.call("pcrl_unpack_convT_wgrad", gpk, g, cin, cout)
+    return g
+
+
+# ------------------------------------------------------------------------------ 3x3x3 conv
+def conv3d_k3_fprop(xp, wf, stats=None, per_sample=False, out_fp32=False):
+    _chk(xp, BF16), _chk(wf, BF16)
+    n, d, h, w, cin = dims_of(xp)
+    cout = wf.shape[1]
+    assert wf.shape == (27, cout, cin)
+    y = torch.empty((n, d, h + 1, w, cout), dtype=torch.float32 if out_fp32 else BF16,
+                    device=xp.device)
+    if stats is not None:
+        _chk(stats, torch.float64)
+    _lib.call("pcrl_conv3d_k3_fprop", xp, wf, y, stats, int(per_sample), int(out_fp32), n, d, h, w,
+              cin, cout)
+    return y
+
+
+def conv3d_k3_dgrad(dyp, wd):
+    _chk(dyp, BF16), _chk(wd, BF16)
+    n, d, h, w, cout = dims_of(dyp)
+    cin = wd.shape[1]
+    assert wd.shape == (27, cin, cout)
+    dx = torch.empty((n, d, h + 1, w, cin), dtype=BF16, device=dyp.device)
+    _lib.call("pcrl_conv3d_k3_dgrad", dyp, wd, dx, n, d, h, w, cin, cout)
+    return dx
+
+
+def conv3d_k3_wgrad(dyp, xp, out=None):
+    """Returns / accumulates into the packed gradient [27,Cout,Cin] fp32."""
+    _chk(dyp, BF16), _chk(xp, BF16)
+    n, d, h, w, cout = dims_of(dyp)
+    cin = xp.shape[-1]
+    if out is None:
+        out = torch.zeros((27, cout, cin), dtype=torch.float32, device=xp.device)
+    _lib.call("pcrl_conv3d_k3_wgrad", dyp, xp, out, n, d, h, w, cin, cout)
+    return out
+
+
+# ------------------------------------------------------------------------------ stem
+def stem_conv_fprop(x, w, stats=None, per_sample=False):
+    """x (N,1,D,H,W) fp32, w (32,1,3,3,3) fp32 -> H-padded bf16 [N,D,H+1,W,32]."""
+    _chk(x, torch.float32), _chk(w, torch.float32)
+    n, _, d, h, wd_ = x.shape
+    assert w.shape[0] == 32 and w.shape[1] == 1
+    y = torch.empty((n, d, h + 1, wd_, 32), dtype=BF16, device=x.device)
+    _lib.call("pcrl_stem_conv_fprop", x, w, y, stats, int(per_sample), n, d, h, wd_)
+    return y
+
+
+def stem_conv_wgrad(dyp, x):
+    _chk(dyp, BF16), _chk(x, torch.float32)
+    n, _, d, h, w = x.shape
+    dw = torch.zeros((32, 1, 3, 3, 3), dtype=torch.float32, device=x.device)
+    _lib.call("pcrl_stem_conv_wgrad", dyp, x, dw, n, d, h, w)
+    return dw
+
+
+# ------------------------------------------------------------------------------ ConvTranspose
+def convT_fprop(xp, wf, bias):
+    _chk(xp, BF16), _chk(wf, BF16)
+    n, d, h, w, cin = dims_of(xp)
+    cout = wf.shape[0] // 8
+    y = torch.empty((n, 2 * d, 2 * h + 1, 2 * w, cout), dtype=BF16, device=xp.device)
+    _lib.call("pcrl_convT3d_k2s2_fprop", xp, wf, bias, y, n, d, h, w, cin, cout)
+    return y
+
+
+def convT_bwd(gp, xp, wd, need_dx=True, need_dw=True):
+    """gp: gradient wrt the fine output.  Returns (dx padded bf16, dw_packed fp32, dbias fp32)."""
+    _chk(gp, BF16)
+    n, d2, h2, w2, cout = dims_of(gp)
+    d, h, w = d2 // 2, h2 // 2, w2 // 2
+    cin = wd.shape[0]
+    rows = n * d * (h + 1) * w
+    scratch = torch.empty((rows, 8 * cout), dtype=BF16, device=gp.device)
+    dx = torch.empty((n, d, h + 1, w, cin), dtype=BF16, device=gp.device) if need_dx else None
+    dw = torch.zeros((8 * cout, cin), dtype=torch.float32, device=gp.device) if need_dw else None
+    db = torch.zeros((cout,), dtype=torch.float32, device=gp.device)
+    _lib.call("pcrl_convT3d_k2s2_bwd", gp, xp if need_dw else None, wd, scratch, dx, dw, db,
+              n, d, h, w, cin, cout)
+    return dx, dw, db
+
+
+# ------------------------------------------------------------------------------ norm + act
+def norm_finalize(stats, count, gamma, beta, conv_bias=None, running_mean=None, running_var=None,
+                  nbt=None, momentum=0.1, eps=1e-5):
+    g, c = stats.shape[0], stats.shape[1]
+    dev = stats.device
+    scale = torch.empty((g, c), dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale)
+    invstd = torch.empty_like(scale)
+    _lib.call("pcrl_norm_finalize", stats, float(count), gamma, beta, conv_bias, running_mean,
+              running_var, nbt, float(momentum), float(eps), scale, shift, mean, invstd, g, c)
+    return scale, shift, mean, invstd
+
+
+def norm_act_fwd(yp, scale, shift, act="relu", prelu=None, want_full=True, want_pool=False,
+                 want_avg=False, per_sample=False):
+    _chk(yp, BF16)
+    n, d, h, w, c = dims_of(yp)
+    a = torch.empty_like(yp) if want_full else None
+    pool = (torch.empty((n, d // 2, h // 2 + 1, w // 2, c), dtype=BF16, device=yp.device)
+            if want_pool else None)
+    avg = torch.zeros((n, c), dtype=torch.float32, device=yp.device) if want_avg else None
+    _lib.call("pcrl_norm_act_fwd", yp, scale, shift, prelu, a, pool, avg, int(per_sample), ACT[act],
+              int(want_pool), n, d, h, w, c)
+    return a, pool, avg
+
+
+def norm_act_bwd(yp, g1, g2, gavg, scale, shift, mean, invstd, gamma, act="relu", prelu=None,
+                 pool=False, per_sample=False):
+    """Returns (dy padded bf16, sums [G,C,3] fp64 = (dbeta, dgamma, dprelu partial))."""
+    _chk(yp, BF16)
+    n, d, h, w, c = dims_of(yp)
+    g = scale.shape[0]
+    sums = torch.zeros((g, c, 3), dtype=torch.float64, device=yp.device)
+    count = float(d * h * w) if per_sample else float(n * d * h * w)
+    dy = torch.empty_like(yp)
+    for p in (0, 1):
+        _lib.call("pcrl_norm_act_bwd", yp, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu,
+                  sums, dy, count, int(per_sample), ACT[act], int(pool), p, n, d, h, w, c)
+    return dy, sums
+
+
+# ------------------------------------------------------------------------------ heads
+def head_fwd(ap, w3, b3, w1=None, b1=None):
+    """w3 [27,C] fp32 tap-major.  Returns (y1 (N,1,D,H,W) fp32, y0 or None)."""
+    _chk(ap, BF16)
+    n, d, h, w, c = dims_of(ap)
+    y1 = torch.empty((n, 1, d, h, w), dtype=torch.float32, device=ap.device)
+    y0 = torch.empty_like(y1) if w1 is not None else None
+    _lib.call("pcrl_head_fwd", ap, w3, b3, w1, b1, y1, y0, n, d, h, w, c)
+    return y1, y0
+
+
+def head_bwd_data(dy1, w3, dy0, w1, c):
+    n, _, d, h, w = dy1.shape
+    da = torch.empty((n, d, h + 1, w, c), dtype=BF16, device=dy1.device)
+    _lib.call("pcrl_head_bwd_data", dy1, w3, dy0, w1, da, n, d, h, w, c)
+    return da
+
+
+def head_bwd_weight(ap, dy1, dy0=None):
+    n, d, h, w, c = dims_of(ap)
+    dw3 = torch.zeros((27, c), dtype=torch.float32, device=ap.device)
+    dw1 = torch.zeros((c,), dtype=torch.float32, device=ap.device) if dy0 is not None else None
+    _lib.call("pcrl_head_bwd_weight", ap, dy1, dy0, dw3, dw1, n, d, h, w, c)
+    return dw3, dw1
+
+
+# ------------------------------------------------------------------------------ GEMMs / SGD
+def gemm_nt(a, b, bias=None, out_fp32=True):
+    _chk(a, BF16), _chk(b, BF16)
+    rows, k = a.shape
+    cols = b.shape[0]
+    c = torch.empty((rows, cols), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
+    _lib.call("pcrl_gemm_nt", a, b, c, bias, rows, k, cols, cols, int(out_fp32))
+    return c
+
+
+def gemm_tn(a, b, out=None):
+    _chk(a, BF16), _chk(b, BF16)
+    rows, p = a.shape
+    q = b.shape[1]
+    if out is None:
+        out = torch.zeros((p, q), dtype=torch.float32, device=a.device)
+    _lib.call("pcrl_gemm_tn", a, b, out, rows, p, q)
+    return out
+
+
+def sgd_flat(params, grads, bufs, seg_off, seg_active, seg_first, lr, momentum, weight_decay,
+             grad_scale=1.0):
+    nseg = seg_active.numel()
+    _lib.call("pcrl_sgd_flat", params, grads, bufs, seg_off, seg_active, seg_first, nseg, float(lr),
+              float(momentum), float(weight_decay), float(grad_scale))

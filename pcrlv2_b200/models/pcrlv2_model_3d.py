@@ -1,0 +1,342 @@
+"""B200-native PCRLv23d: same class surface as the reference ``models/pcrlv2_model_3d.py``
+(constructor signature :98, ``forward(x, local=False) -> (out, middle_features, middle_masks)``
+:112-133, ``state_dict()`` keys / shapes / dtypes), different engine.
+
+The nn.Conv3d / nn.BatchNorm3d / ... sub-modules below are *parameter containers* only -- they give
+the state_dict its reference layout and torch's default initialisation -- their ``forward`` is
+never called.  The arithmetic runs in libpcrl_b200.so (hand-written sm_100a kernels) through the
+autograd Functions in this file:
+
+  LUConv            conv3d 3x3x3 (tcgen05 implicit GEMM, fused norm statistics)
+                    -> norm finalize -> norm+act(+2x2x2 max-pool)(+avg-pool sums) streaming pass
+  UpTransition      ConvTranspose3d as a tensor-core GEMM with scatter epilogue, two LUConv, the
+                    1-channel deep-supervision conv (and, at the last stage, the 1x1x1 output conv)
+  backward          two-pass norm/act/pool backward, conv data gradient (same implicit GEMM with
+                    mirrored filters), MN-major split-K weight gradient
+
+Activations between kernels are bf16 "H-padded NDHWC" (csrc/common.cuh); accumulation, norm
+statistics, parameters and the tensors returned to the caller are fp32.  The convolution bias in
+front of a normalisation cancels exactly: it is not added, its gradient is exactly zero, and it
+is folded into ``running_mean`` (SURVEY note N1).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import kernels as K
+
+# bumped by pcrlv2_b200.train_3d.FlatSGD after every in-place parameter update made through raw
+# pointers (torch's version counter does not see those); part of the packed-weight cache key.
+_PARAM_EPOCH = [0]
+
+
+def bump_param_epoch():
+    _PARAM_EPOCH[0] += 1
+
+
+def _packed(module, kind):
+    """bf16 tensor-core layouts of a conv weight, cached until the parameter changes."""
+    w = module.weight
+    key = (w._version, _PARAM_EPOCH[0], w.data_ptr())
+    cache = getattr(module, "_pcrl_packed", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            if kind == "conv3":
+                pk = K.pack_conv3_weights(w.detach().contiguous())
+            elif kind == "convT":
+                pk = K.pack_convT_weights(w.detach().contiguous())
+            elif kind == "head3":   # (1,C,3,3,3) -> [27,C] fp32 tap-major
+                pk = (w.detach().reshape(w.shape[1], 27).t().contiguous(),)
+            else:
+                raise ValueError(kind)
+        cache = (key, pk)
+        module._pcrl_packed = cache
+    return cache[1]
+
+
+class _Cfg:
+    """Static (non-tensor) configuration of one fused LUConv call."""
+    __slots__ = ("stem", "pool", "tail", "final", "act", "norm", "training", "conv", "bn", "ds", "fin")
+
+    def __init__(self, **kw):
+        for k in self.__slots__:
+            setattr(self, k, kw.get(k))
+
+
+class _LUConvFn(torch.autograd.Function):
+    """conv3x3x3 -> norm -> act [-> maxpool] [-> avg-pool sums, 1-channel head convs]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, prelu, ds_w, ds_b, fin_w, fin_b, cfg):
+        ctx.set_materialize_grads(False)
+        per_sample = cfg.norm == "in"
+        cout = weight.shape[0]
+        use_batch_stats = cfg.training or per_sample
+        if cfg.stem:
+            n, _, d, h, w = x.shape
+        else:
+            n, d, h, w, _ = K.dims_of(x)
+        groups = n if per_sample else 1
+        stats = (torch.zeros((groups, cout, 2), dtype=torch.float64, device=x.device)
+                 if use_batch_stats else None)
+        if cfg.stem:
+            y = K.stem_conv_fprop(x.contiguous(), weight.detach().contiguous(), stats, per_sample)
+        else:
+            wf, _ = _packed(cfg.conv, "conv3")
+            y = K.conv3d_k3_fprop(x, wf, stats, per_sample)
+        if use_batch_stats:
+            count = d * h * w * (1 if per_sample else n)
+            bn = cfg.bn
+            track = (not per_sample) and cfg.training
+            scale, shift, mean, invstd = K.norm_finalize(
+                stats, count, gamma.detach(), beta.detach(), bias.detach(),
+                bn.running_mean if track else None, bn.running_var if track else None,
+                bn.num_batches_tracked if track else None, 0.1, 1e-5)
+        else:
+            bn = cfg.bn
+            invstd = torch.rsqrt(bn.running_var + 1e-5).unsqueeze(0)
+            mean = (bn.running_mean - bias.detach()).unsqueeze(0)
+            scale = (gamma.detach() * invstd).contiguous()
+            shift = (beta.detach() - mean * scale).contiguous()
+            mean, invstd = mean.contiguous(), invstd.contiguous()
+        slope = prelu.detach() if prelu is not None else None
+        a, pooled, avg = K.norm_act_fwd(y, scale, shift, cfg.act, slope, want_full=not cfg.pool,
+                                        want_pool=cfg.pool, want_avg=cfg.tail, per_sample=per_sample)
+        outs = [pooled if cfg.pool else a]
+        if cfg.tail:
+            (w3,) = _packed(cfg.ds, "head3")
+            w1 = fin_w.detach().reshape(-1).contiguous() if cfg.final else None
+            y1, y0 = K.head_fwd(a, w3, ds_b.detach(), w1, fin_b.detach() if cfg.final else None)
+            outs += [avg, y1]
+            if cfg.final:
+                outs.append(y0)
+        ctx.cfg = cfg
+        ctx.dims = (n, d, h, w, cout)
+        ctx.save_for_backward(x, y, scale, shift, mean, invstd, gamma, prelu,
+                              a if cfg.tail else None, ds_w, fin_w)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_out, g_avg=None, g_y1=None, g_y0=None):
+        cfg = ctx.cfg
+        x, y, scale, shift, mean, invstd, gamma, prelu, a, ds_w, fin_w = ctx.saved_tensors
+        n, d, h, w, cout = ctx.dims
+        per_sample = cfg.norm == "in"
+        grads = [None] * 11
+        g2 = None
+        if cfg.tail and (g_y1 is not None or g_y0 is not None):
+            dy1 = g_y1.contiguous() if g_y1 is not None else torch.zeros(
+                (n, 1, d, h, w), dtype=torch.float32, device=y.device)
+            dy0 = g_y0.contiguous() if (cfg.final and g_y0 is not None) else None
+            (w3,) = _packed(cfg.ds, "head3")
+            w1 = fin_w.detach().reshape(-1).contiguous() if dy0 is not None else None
+            g2 = K.head_bwd_data(dy1, w3, dy0, w1, cout)
+            dw3, dw1 = K.head_bwd_weight(a, dy1, dy0)
+            if g_y1 is not None:
+                grads[6] = dw3.t().reshape(1, cout, 3, 3, 3)
+                grads[7] = dy1.sum().reshape(1)
+            if dy0 is not None:
+                grads[8] = dw1.reshape(1, cout, 1, 1, 1)
+                grads[9] = dy0.sum().reshape(1)
+        if g_out is None and g2 is None and g_avg is None:
+            return tuple(grads)
+        g1 = g_out.contiguous() if g_out is not None else None
+        gavg = g_avg.contiguous() if g_avg is not None else None
+        dy, sums = K.norm_act_bwd(y, g1, g2, gavg, scale, shift, mean, invstd, gamma.detach(), cfg.act,
+                                  prelu.detach() if prelu is not None else None, pool=cfg.pool,
+                                  per_sample=per_sample)
+        sums = sums.sum(0).float()
+        grads[3] = sums[:, 1].contiguous()          # d gamma
+        grads[4] = sums[:, 0].contiguous()          # d beta
+        if prelu is not None:
+            grads[5] = sums[:, 2].contiguous()
+        grads[2] = torch.zeros(cout, dtype=torch.float32, device=y.device)  # conv bias: exactly 0
+        if cfg.stem:
+            grads[1] = K.stem_conv_wgrad(dy, x)
+        else:
+            _, wd = _packed(cfg.conv, "conv3")
+            if ctx.needs_input_grad[0]:
+                grads[0] = K.conv3d_k3_dgrad(dy, wd)
+            grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
+        return tuple(grads)
+
+
+class _ConvTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        wf, _ = _packed(mod, "convT")
+        ctx.mod = mod
+        ctx.save_for_backward(x)
+        ctx.shape = tuple(weight.shape)
+        return K.convT_fprop(x, wf, bias.detach().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        _, wd = _packed(ctx.mod, "convT")
+        cin, cout = ctx.shape[0], ctx.shape[1]
+        dx, dw, db = K.convT_bwd(g.contiguous(), x, wd, need_dx=ctx.needs_input_grad[0])
+        return dx, K.unpack_convT_wgrad(dw, cin, cout), db, None
+
+
+def _make_norm(norm, ch):
+    if norm == "bn":
+        return nn.BatchNorm3d(num_features=ch, momentum=0.1, affine=True)
+    if norm == "gn":
+        return nn.GroupNorm(num_groups=8, num_channels=ch, eps=1e-05, affine=True)
+    if norm == "in":
+        return nn.InstanceNorm3d(num_features=ch, momentum=0.1, affine=True)
+    raise ValueError("normalization type {} is not supported".format(norm))
+
+
+class LUConv(nn.Module):
+    """Conv3d(k3,p1) -> norm -> activation (reference :6-34)."""
+
+    def __init__(self, in_chan, out_chan, act, norm):
+        super().__init__()
+        self.conv1 = nn.Conv3d(in_chan, out_chan, kernel_size=3, padding=1)
+        self.bn1 = _make_norm(norm, out_chan)
+        if norm == "gn":
+            raise NotImplementedError(
+                "norm='gn' cannot be built by the reference either (GroupNorm(8) on the 1-channel "
+                "deep-supervision head raises); not supported")
+        if act == "relu":
+            self.activation = nn.ReLU(inplace=True)
+        elif act == "prelu":
+            self.activation = nn.PReLU(out_chan)
+        elif act == "elu":
+            self.activation = nn.ELU(inplace=True)
+        elif act == "sigmoid":
+            self.activation = nn.Sigmoid()
+        else:
+            raise ValueError("activation type {} is not supported".format(act))
+        self.act, self.norm = act, norm
+        self.in_chan, self.out_chan = in_chan, out_chan
+
+    def run(self, x, pool=False, tail=None, final=None):
+        """x: fp32 (N,1,D,H,W) for the stem, otherwise an H-padded bf16 activation."""
+        cfg = _Cfg(stem=self.in_chan == 1, pool=pool, tail=tail is not None, final=final is not None,
+                   act=self.act, norm=self.norm, training=self.training, conv=self.conv1, bn=self.bn1,
+                   ds=tail.conv1 if tail is not None else None, fin=final)
+        prelu = self.activation.weight if self.act == "prelu" else None
+        return _LUConvFn.apply(
+            x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, prelu,
+            tail.conv1.weight if tail is not None else None,
+            tail.conv1.bias if tail is not None else None,
+            final.weight if final is not None else None,
+            final.bias if final is not None else None, cfg)
+
+    def forward(self, x):
+        """Stand-alone use with the reference's NCDHW fp32 convention."""
+        inp = x.float() if self.in_chan == 1 else K.pad_ndhwc(x)
+        if self.in_chan != 1 and self.in_chan % 32:
+            raise NotImplementedError("LUConv needs in_chan == 1 or a multiple of 32")
+        return K.unpad_ndhwc(self.run(inp)[0])
+
+
+def _make_nConv(in_channel, depth, act, norm, double_chnnel=False):
+    if double_chnnel:
+        layer1 = LUConv(in_channel, 32 * (2 ** (depth + 1)), act, norm)
+        layer2 = LUConv(32 * (2 ** (depth + 1)), 32 * (2 ** (depth + 1)), act, norm)
+    else:
+        layer1 = LUConv(in_channel, 32 * (2 ** depth), act, norm)
+        layer2 = LUConv(32 * (2 ** depth), 32 * (2 ** depth) * 2, act, norm)
+    return nn.Sequential(layer1, layer2)
+
+
+class DownTransition(nn.Module):
+    def __init__(self, in_channel, depth, act, norm):
+        super().__init__()
+        self.ops = _make_nConv(in_channel, depth, act, norm)
+
+    def run(self, x, pool):
+        return self.ops[1].run(self.ops[0].run(x)[0], pool=pool)[0]
+
+
+class UpTransition(nn.Module):
+    """reference :48-72 (the skip concatenation is commented out there, :65)."""
+
+    def __init__(self, inChans, outChans, depth, act, norm):
+        super().__init__()
+        self.depth = depth
+        self.up_conv = nn.ConvTranspose3d(inChans, outChans, kernel_size=2, stride=2)
+        self.ops = _make_nConv(outChans, depth, act, norm, double_chnnel=True)
+        channels = 32 * (2 ** depth) * 2
+        self.bn = nn.BatchNorm1d(channels)
+        self.predictor_head = nn.Sequential(nn.Linear(channels, 2 * channels),
+                                            nn.BatchNorm1d(2 * channels),
+                                            nn.ReLU(inplace=True),
+                                            nn.Linear(2 * channels, channels))
+        self.deep_supervision_head = LUConv(channels, 1, "sigmoid", norm)
+        self.norm = norm
+
+    def run(self, x, final=None):
+        up = _ConvTFn.apply(x, self.up_conv.weight, self.up_conv.bias, self.up_conv)
+        h = self.ops[0].run(up)[0]
+        outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final)
+        a, avg, y1 = outs[0], outs[1], outs[2]
+        y0 = outs[3] if final is not None else None
+        n, d, hh, w, _ = K.dims_of(a)
+        x_pro = self.bn(avg / float(d * hh * w))
+        x_pre = self.predictor_head(x_pro)
+        ds = self.deep_supervision_head
+        if self.norm == "bn":
+            bn = ds.bn1
+            if self.training:
+                bn.num_batches_tracked += 1
+            z = F.batch_norm(y1, bn.running_mean, bn.running_var, bn.weight, bn.bias, self.training,
+                             0.1, 1e-5)
+        else:
+            z = F.instance_norm(y1, None, None, ds.bn1.weight, ds.bn1.bias, True, 0.1, 1e-5)
+        return a, x_pro, x_pre, torch.sigmoid(z), y0
+
+
+class OutputTransition(nn.Module):
+    def __init__(self, inChans, n_labels):
+        super().__init__()
+        if n_labels != 1:
+            raise NotImplementedError("the fused output head supports n_class == 1 (reference default)")
+        self.final_conv = nn.Conv3d(inChans, n_labels, kernel_size=1)
+        self.sigmoid = nn.Sigmoid()
+
+
+class PCRLv23d(nn.Module):
+    def __init__(self, n_class=1, act="relu", norm="bn", in_channels=1, low_dim=128, student=False):
+        super().__init__()
+        if in_channels != 1:
+            raise NotImplementedError("in_channels must be 1 (CT sub-volumes, the reference default)")
+        self.maxpool = nn.MaxPool3d(2)
+        self.down_tr64 = DownTransition(in_channels, 0, act, norm)
+        self.down_tr128 = DownTransition(64, 1, act, norm)
+        self.down_tr256 = DownTransition(128, 2, act, norm)
+        self.down_tr512 = DownTransition(256, 3, act, norm)
+        self.avg_pool = nn.AdaptiveAvgPool3d((1, 1, 1))
+        self.up_tr256 = UpTransition(512, 512, 2, act, norm)
+        self.up_tr128 = UpTransition(256, 256, 1, act, norm)
+        self.up_tr64 = UpTransition(128, 128, 0, act, norm)
+        self.out_tr = OutputTransition(64, n_class)
+        self.sigmoid = nn.Sigmoid()
+
+    def forward(self, x, local=False):
+        if not x.is_cuda:
+            raise RuntimeError("pcrlv2_b200.PCRLv23d runs on CUDA only (there is no CPU fallback)")
+        if x.dim() != 5 or x.shape[1] != 1 or any(s % 8 for s in x.shape[2:]):
+            raise ValueError("expected (B,1,D,H,W) with D,H,W multiples of 8, got %s" % (tuple(x.shape),))
+        x = x.float().contiguous()
+        h = self.down_tr64.run(x, pool=True)
+        h = self.down_tr128.run(h, pool=True)
+        h = self.down_tr256.run(h, pool=True)
+        h = self.down_tr512.run(h, pool=False)
+        h, pro_256, pre_256, m256, _ = self.up_tr256.run(h)
+        h, pro_128, pre_128, m128, _ = self.up_tr128.run(h)
+        h, pro_64, pre_64, m64, y0 = self.up_tr64.run(h, final=self.out_tr.final_conv)
+        middle_masks = []
+        if not local:
+            middle_masks.append(F.interpolate(m256, scale_factor=4, mode="trilinear"))
+            middle_masks.append(F.interpolate(m128, scale_factor=2, mode="trilinear"))
+            middle_masks.append(m64)
+        middle_features = [[pro_256, pre_256], [pro_128, pre_128], [pro_64, pre_64]]
+        out = torch.sigmoid(y0)
+        return out, middle_features, middle_masks

@@ -1,0 +1,283 @@
+"""Op-level parity of every CUDA kernel (through the C ABI) against plain torch fp32 ops on the
+same bf16-representable inputs.  Tolerances: fp32-output paths 2e-4 of the reference max
+(accumulation order only); bf16-output paths 1.2e-2 (one bf16 rounding of the result)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from pcrlv2_b200 import kernels as K
+
+DEV = "cuda"
+TOL32 = 2e-4
+TOL16 = 1.2e-2
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def q(t):  # bf16-representable fp32
+    return t.to(torch.bfloat16).float()
+
+
+CONV_SHAPES = [
+    (2, 4, 6, 8, 64, 64),
+    (1, 8, 8, 4, 128, 128),
+    (2, 3, 5, 16, 32, 64),
+    (1, 16, 16, 8, 64, 32),
+    (3, 2, 2, 2, 256, 128),
+    (2, 8, 12, 32, 64, 64),
+    (1, 4, 4, 4, 512, 256),
+    (1, 6, 10, 16, 128, 64),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3d_fprop(shape):
+    n, d, h, w, cin, cout = shape
+    torch.manual_seed(0)
+    x = q(torch.randn(n, cin, d, h, w, device=DEV))
+    wt = q(torch.randn(cout, cin, 3, 3, 3, device=DEV) / (27 * cin) ** 0.5)
+    ref = F.conv3d(x, wt, padding=1)
+    xp = K.pad_ndhwc(x)
+    wf, _ = K.pack_conv3_weights(wt)
+    y32 = K.conv3d_k3_fprop(xp, wf, out_fp32=True)
+    assert rel(K.unpad_ndhwc(y32), ref) < TOL32
+    stats = torch.zeros(cout, 2, dtype=torch.float64, device=DEV)
+    y16 = K.conv3d_k3_fprop(xp, wf, stats=stats)
+    got = K.unpad_ndhwc(y16)
+    assert rel(got, ref) < TOL16
+    s1 = got.double().sum(dim=(0, 2, 3, 4))
+    s2 = (got.double() ** 2).sum(dim=(0, 2, 3, 4))
+    assert rel(stats[:, 0], s1) < 1e-4 or (stats[:, 0] - s1).abs().max() < 1e-2
+    assert rel(stats[:, 1], s2) < 1e-5
+    # per-sample statistics (InstanceNorm)
+    st2 = torch.zeros(n, cout, 2, dtype=torch.float64, device=DEV)
+    K.conv3d_k3_fprop(xp, wf, stats=st2, per_sample=True)
+    assert rel(st2[..., 1], (got.double() ** 2).sum(dim=(2, 3, 4))) < 1e-5
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3d_dgrad(shape):
+    n, d, h, w, cin, cout = shape
+    torch.manual_seed(1)
+    x = q(torch.randn(n, cin, d, h, w, device=DEV)).requires_grad_(True)
+    wt = q(torch.randn(cout, cin, 3, 3, 3, device=DEV) / (27 * cin) ** 0.5)
+    dy = q(torch.randn(n, cout, d, h, w, device=DEV))
+    F.conv3d(x, wt, padding=1).backward(dy)
+    _, wd = K.pack_conv3_weights(wt)
+    dx = K.conv3d_k3_dgrad(K.pad_ndhwc(dy), wd)
+    assert rel(K.unpad_ndhwc(dx), x.grad) < TOL16
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3d_wgrad(shape):
+    n, d, h, w, cin, cout = shape
+    if cout % 64:
+        pytest.skip("weight gradient needs Cout % 64 == 0 (all reference layers satisfy it)")
+    torch.manual_seed(2)
+    x = q(torch.randn(n, cin, d, h, w, device=DEV))
+    wt = q(torch.randn(cout, cin, 3, 3, 3, device=DEV)).requires_grad_(True)
+    dy = q(torch.randn(n, cout, d, h, w, device=DEV))
+    F.conv3d(x, wt, padding=1).backward(dy)
+    gpk = K.conv3d_k3_wgrad(K.pad_ndhwc(dy), K.pad_ndhwc(x))
+    assert rel(K.unpack_conv3_wgrad(gpk), wt.grad) < TOL32
+    # accumulation into an existing buffer
+    gpk2 = K.conv3d_k3_wgrad(K.pad_ndhwc(dy), K.pad_ndhwc(x), out=gpk.clone())
+    assert rel(K.unpack_conv3_wgrad(gpk2), 2 * wt.grad) < TOL32
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 16, 16, 16), (3, 4, 6, 2), (2, 64, 64, 32)])
+def test_stem_conv(shape):
+    n, d, h, w = shape
+    torch.manual_seed(3)
+    x = torch.randn(n, 1, d, h, w, device=DEV)
+    wt = torch.randn(32, 1, 3, 3, 3, device=DEV, requires_grad=True)
+    ref = F.conv3d(x, wt, padding=1)
+    stats = torch.zeros(32, 2, dtype=torch.float64, device=DEV)
+    yp = K.stem_conv_fprop(x, wt.detach(), stats=stats)
+    got = K.unpad_ndhwc(yp)
+    assert rel(got, ref) < TOL16
+    assert yp[:, :, 0].abs().max().item() == 0
+    assert rel(stats[:, 1], (got.double() ** 2).sum(dim=(0, 2, 3, 4))) < 1e-5
+    dy = q(torch.randn_like(ref))
+    ref.backward(dy)
+    dw = K.stem_conv_wgrad(K.pad_ndhwc(dy), x)
+    assert rel(dw, wt.grad) < TOL32
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2, 2, 128, 128), (1, 4, 4, 2, 256, 256), (2, 8, 8, 4, 128, 128),
+                                   (1, 2, 3, 5, 512, 512)])
+def test_convT(shape):
+    n, d, h, w, cin, cout = shape
+    torch.manual_seed(4)
+    x = q(torch.randn(n, cin, d, h, w, device=DEV)).requires_grad_(True)
+    wt = q(torch.randn(cin, cout, 2, 2, 2, device=DEV) / cin ** 0.5).requires_grad_(True)
+    b = torch.randn(cout, device=DEV, requires_grad=True)
+    ref = F.conv_transpose3d(x, wt, b, stride=2)
+    wf, wd = K.pack_convT_weights(wt.detach())
+    xp = K.pad_ndhwc(x.detach())
+    yp = K.convT_fprop(xp, wf, b.detach())
+    assert rel(K.unpad_ndhwc(yp), ref) < TOL16
+    assert yp[:, :, 0].abs().max().item() == 0
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    dx, dw, db = K.convT_bwd(K.pad_ndhwc(g), xp, wd)
+    assert rel(K.unpad_ndhwc(dx), x.grad) < TOL16
+    assert dx[:, :, 0].abs().max().item() == 0
+    assert rel(K.unpack_convT_wgrad(dw, cin, cout), wt.grad) < TOL32
+    assert rel(db, b.grad) < TOL32
+
+
+def _norm_ref(y, gamma, beta, act, per_sample, slope=None):
+    if per_sample:
+        z = F.instance_norm(y, None, None, gamma, beta, True, 0.1, 1e-5)
+    else:
+        z = F.batch_norm(y, None, None, gamma, beta, True, 0.1, 1e-5)
+    if act == "relu":
+        return F.relu(z)
+    if act == "elu":
+        return F.elu(z)
+    if act == "prelu":
+        return F.prelu(z, slope)
+    if act == "sigmoid":
+        return torch.sigmoid(z)
+    return z
+
+
+@pytest.mark.parametrize("per_sample", [False, True])
+@pytest.mark.parametrize("act", ["relu", "elu", "prelu", "sigmoid"])
+@pytest.mark.parametrize("mode", ["full", "pool", "avg"])
+def test_norm_act(per_sample, act, mode):
+    n, c, d, h, w = 3, 64, 4, 6, 8
+    torch.manual_seed(5)
+    y = q(torch.randn(n, c, d, h, w, device=DEV) * 2 + 0.3).requires_grad_(True)
+    gamma = (torch.rand(c, device=DEV) + 0.5).requires_grad_(True)
+    beta = (torch.randn(c, device=DEV) * 0.2).requires_grad_(True)
+    slope = torch.full((c,), 0.25, device=DEV, requires_grad=True) if act == "prelu" else None
+    bias = torch.randn(c, device=DEV)
+    yp = K.pad_ndhwc(y.detach())
+    yp[:, :, 0] = 7.0  # pad rows of a raw conv output are garbage: nothing may depend on them
+    G = n if per_sample else 1
+    yd = y.detach().double()
+    dims = (2, 3, 4) if per_sample else (0, 2, 3, 4)
+    stats = torch.stack([yd.sum(dims), (yd ** 2).sum(dims)], -1).reshape(G, c, 2).contiguous()
+    count = d * h * w * (1 if per_sample else n)
+    rm = torch.zeros(c, device=DEV)
+    rv = torch.ones(c, device=DEV)
+    nbt = torch.zeros((), dtype=torch.long, device=DEV)
+    scale, shift, mean, invstd = K.norm_finalize(
+        stats, count, gamma.detach(), beta.detach(), bias, None if per_sample else rm,
+        None if per_sample else rv, None if per_sample else nbt)
+    if not per_sample:
+        rm_ref, rv_ref = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        F.batch_norm(y.detach() + bias.view(1, -1, 1, 1, 1), rm_ref, rv_ref, None, None, True, 0.1, 1e-5)
+        assert rel(rm, rm_ref) < 1e-5 and rel(rv, rv_ref) < 1e-5 and nbt.item() == 1
+    a_ref = _norm_ref(y, gamma, beta, act, per_sample, slope)
+    a, pool, avg = K.norm_act_fwd(yp, scale, shift, act, slope.detach() if slope is not None else None,
+                                  want_full=(mode != "pool"), want_pool=(mode == "pool"),
+                                  want_avg=(mode == "avg"), per_sample=per_sample)
+    if mode == "pool":
+        out_ref = F.max_pool3d(a_ref, 2)
+        assert rel(K.unpad_ndhwc(pool), out_ref) < TOL16
+        assert pool[:, :, 0].abs().max().item() == 0
+    else:
+        out_ref = a_ref
+        assert rel(K.unpad_ndhwc(a), a_ref) < TOL16
+        assert a[:, :, 0].abs().max().item() == 0
+    loss_terms = []
+    g1 = q(torch.randn_like(out_ref))
+    loss_terms.append((out_ref * g1).sum())
+    g2 = gavg = None
+    if mode == "avg":
+        assert rel(avg / (d * h * w), a_ref.mean(dim=(2, 3, 4))) < 2e-3
+        g2 = q(torch.randn_like(a_ref))
+        gavg = torch.randn(n, c, device=DEV)
+        loss_terms.append((a_ref * g2).sum())
+        loss_terms.append((a_ref.mean(dim=(2, 3, 4)) * gavg).sum())
+    sum(loss_terms).backward()
+    dy, sums = K.norm_act_bwd(yp, K.pad_ndhwc(g1), K.pad_ndhwc(g2) if g2 is not None else None, gavg,
+                              scale, shift, mean, invstd, gamma.detach(), act,
+                              slope.detach() if slope is not None else None, pool=(mode == "pool"),
+                              per_sample=per_sample)
+    assert rel(K.unpad_ndhwc(dy), y.grad) < 2e-2
+    assert dy[:, :, 0].abs().max().item() == 0
+    assert rel(sums[..., 0].sum(0), beta.grad) < 2e-3
+    assert rel(sums[..., 1].sum(0), gamma.grad) < 2e-3
+    if act == "prelu":
+        assert rel(sums[..., 2].sum(0), slope.grad) < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 6, 8, 64), (1, 8, 8, 4, 128), (3, 2, 2, 2, 256), (2, 16, 16, 16, 64)])
+@pytest.mark.parametrize("with_final", [False, True])
+def test_heads(shape, with_final):
+    n, d, h, w, c = shape
+    torch.manual_seed(6)
+    a = q(torch.randn(n, c, d, h, w, device=DEV)).requires_grad_(True)
+    w3 = (torch.randn(1, c, 3, 3, 3, device=DEV) / (27 * c) ** 0.5).requires_grad_(True)
+    b3 = torch.randn(1, device=DEV, requires_grad=True)
+    w1 = (torch.randn(1, c, 1, 1, 1, device=DEV) / c ** 0.5).requires_grad_(True)
+    b1 = torch.randn(1, device=DEV, requires_grad=True)
+    y1_ref = F.conv3d(a, w3, b3, padding=1)
+    y0_ref = F.conv3d(a, w1, b1)
+    ap = K.pad_ndhwc(a.detach())
+    w3p = w3.detach().reshape(c, 27).t().contiguous()
+    w1p = w1.detach().reshape(c).contiguous()
+    y1, y0 = K.head_fwd(ap, w3p, b3.detach(), w1p if with_final else None, b1.detach() if with_final else None)
+    assert rel(y1, y1_ref) < TOL32
+    dy1 = torch.randn_like(y1_ref)
+    dy0 = torch.randn_like(y0_ref)
+    loss = (y1_ref * dy1).sum()
+    if with_final:
+        assert rel(y0, y0_ref) < TOL32
+        loss = loss + (y0_ref * dy0).sum()
+    loss.backward()
+    da = K.head_bwd_data(dy1, w3p, dy0 if with_final else None, w1p if with_final else None, c)
+    assert rel(K.unpad_ndhwc(da), a.grad) < TOL16
+    assert da[:, :, 0].abs().max().item() == 0
+    dw3, dw1 = K.head_bwd_weight(ap, dy1, dy0 if with_final else None)
+    assert rel(dw3.t().reshape(1, c, 3, 3, 3), w3.grad) < TOL32
+    if with_final:
+        assert rel(dw1.reshape(1, c, 1, 1, 1), w1.grad) < TOL32
+
+
+@pytest.mark.parametrize("dims", [(300, 128, 256), (128, 64, 64), (1000, 512, 128), (77, 256, 512)])
+def test_gemms(dims):
+    rows, k, cols = dims
+    torch.manual_seed(7)
+    a = q(torch.randn(rows, k, device=DEV))
+    b = q(torch.randn(cols, k, device=DEV))
+    bias = torch.randn(cols, device=DEV)
+    c = K.gemm_nt(a.to(torch.bfloat16), b.to(torch.bfloat16), bias)
+    assert rel(c, a @ b.t() + bias) < TOL32
+    b2 = q(torch.randn(rows, cols, device=DEV))
+    c2 = K.gemm_tn(a.to(torch.bfloat16), b2.to(torch.bfloat16))
+    assert rel(c2, a.t() @ b2) < TOL32
+
+
+def test_sgd_flat():
+    torch.manual_seed(8)
+    sizes = [5, 1000, 64, 27 * 64 * 64, 3]
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + s)
+    tot = off[-1]
+    p = torch.randn(tot, device=DEV)
+    g = torch.randn(tot, device=DEV)
+    buf = torch.randn(tot, device=DEV)
+    active = torch.tensor([1, 0, 1, 1, 1], dtype=torch.int32, device=DEV)
+    first = torch.tensor([0, 0, 1, 0, 0], dtype=torch.int32, device=DEV)
+    seg = torch.tensor(off, dtype=torch.long, device=DEV)
+    p0, b0 = p.clone(), buf.clone()
+    K.sgd_flat(p, g, buf, seg, active, first, 0.01, 0.9, 1e-4)
+    for i, s in enumerate(sizes):
+        sl = slice(off[i], off[i + 1])
+        if not active[i]:
+            assert torch.equal(p[sl], p0[sl]) and torch.equal(buf[sl], b0[sl])
+            continue
+        d_ = g[sl] + 1e-4 * p0[sl]
+        m = d_ if first[i] else 0.9 * b0[sl] + d_
+        assert rel(buf[sl], m) < 1e-6 and rel(p[sl], p0[sl] - 0.01 * m) < 1e-6
