@@ -93,10 +93,28 @@ def _conv(a):
     return a
 
 
+# kernels launched by one call of each entry point (for bench.py's gpu_launches count)
+LAUNCHES = {"pcrl_convT3d_k2s2_fprop": 2, "pcrl_convT3d_k2s2_bwd": 3}
+launch_count = [0]
+# when set to a list, every call is bracketed by CUDA events on the launching stream and
+# (name, int-args, start, end) is appended -- bench.py uses this for the per-kernel roofline
+profile = [None]
+
+
 def call(name: str, *args) -> None:
     """Invoke an entry point on torch's current CUDA stream; the stream argument is appended."""
     fn = getattr(lib(), name)
+    cargs = [_conv(a) for a in args]          # raises on CPU tensors before touching CUDA
     stream = torch.cuda.current_stream().cuda_stream
-    rc = fn(*[_conv(a) for a in args], stream)
+    prof = profile[0]
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = fn(*cargs, stream)
     if rc != 0:
         raise PcrlError(f"{name} failed ({rc}): {lib().pcrl_last_error().decode()}")
+    launch_count[0] += LAUNCHES.get(name, 1)
+    if prof is not None:
+        e1.record()
+        prof.append((name, tuple(a for a in args if isinstance(a, int)), e0, e1))

@@ -109,7 +109,9 @@ class _LUConvFn(torch.autograd.Function):
             (w3,) = _packed(cfg.ds, "head3")
             w1 = fin_w.detach().reshape(-1).contiguous() if cfg.final else None
             y1, y0 = K.head_fwd(a, w3, ds_b.detach(), w1, fin_b.detach() if cfg.final else None)
-            outs += [avg, y1]
+            # the kernel accumulates sums; hand autograd the MEAN so that the incoming gradient is
+            # dL/d(mean), which is what norm_act_bwd expects for its gavg argument
+            outs += [avg * (1.0 / float(d * h * w)), y1]
             if cfg.final:
                 outs.append(y0)
         ctx.cfg = cfg
@@ -278,8 +280,7 @@ class UpTransition(nn.Module):
         outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final)
         a, avg, y1 = outs[0], outs[1], outs[2]
         y0 = outs[3] if final is not None else None
-        n, d, hh, w, _ = K.dims_of(a)
-        x_pro = self.bn(avg / float(d * hh * w))
+        x_pro = self.bn(avg)
         x_pre = self.predictor_head(x_pro)
         ds = self.deep_supervision_head
         if self.norm == "bn":

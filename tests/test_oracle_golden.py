@@ -1,0 +1,119 @@
+"""CPU: the oracle (oracle/pcrlv2_oracle.py) against the golden fixtures that
+oracle/make_golden.py produced by running the REFERENCE (model by file path, and the real
+train_3d.train_pcrlv2_inner for two iterations).  Runs without a GPU and without /root/reference."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pcrlv2_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def digest(t):
+    f = t.detach().double().flatten()
+    stride = max(1, f.numel() // 256)
+    head = torch.tensor([f.sum(), f.abs().sum(), (f * f).sum(), float(f.numel())], dtype=torch.float64)
+    return torch.cat([head, f[::stride][:256]]).numpy()
+
+
+def close(a, b, tol=1e-5):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+def test_state_spec_counts():
+    spec = orc.state_spec()
+    assert len(spec) == 169
+    n_par = 0
+    for k, shape, _ in spec:
+        if orc.is_param(k):
+            n = 1
+            for s in shape:
+                n *= s
+            n_par += n
+    assert n_par == 17111434          # SURVEY 8a6 (probe of the reference)
+    assert len(orc.state_spec(norm="in")) == 118
+
+
+@pytest.mark.parametrize("norm", ["bn", "in"])
+def test_forward_against_reference_fixture(norm):
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "forward_b2.npz"))
+    sd = orc.init_state(0, norm=norm)
+    x1, _, _, lv = orc.synthetic_batch(2, seed=42)
+    with torch.no_grad():
+        out, feats, masks = orc.forward(sd, x1, False, True, "relu", norm)
+        lout, lfeats, lmasks = orc.forward(sd, torch.cat(lv, 0), True, True, "relu", norm)
+    assert lmasks == []
+    assert close(digest(out), g[f"{norm}.out"])
+    assert close(digest(lout), g[f"{norm}.local_out"])
+    for s in range(3):
+        assert close(feats[s][0].numpy(), g[f"{norm}.pro{s}"], 1e-4)
+        assert close(feats[s][1].numpy(), g[f"{norm}.pre{s}"], 1e-4)
+        assert close(digest(masks[s]), g[f"{norm}.mask{s}"])
+        assert close(lfeats[s][0].numpy(), g[f"{norm}.local_pro{s}"], 1e-4)
+        assert close(lfeats[s][1].numpy(), g[f"{norm}.local_pre{s}"], 1e-4)
+    if norm == "bn":
+        for k in g.files:
+            if k.startswith("bn.buf."):
+                assert close(digest(sd[k[len("bn.buf."):]]), g[k]), k
+
+
+def test_two_training_steps_against_reference_trainer_fixture():
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "train_2steps_b2.npz"))
+    sd = orc.init_state(0)
+    bufs = {}
+    rng = random.Random(1234)
+    draws, scal = [], []
+    for seed in (42, 43):
+        b = orc.synthetic_batch(2, seed=seed)
+        s, d, grads = orc.train_step(sd, bufs, b[0], b[1], b[2], b[3], 0, 1e-3, rng)
+        draws.append(d)
+        scal.append(s)
+    assert np.array_equal(np.array(draws), g["draws"])
+    assert abs(sum(s["loss1"] for s in scal) / 2 - float(g["mg_avg"])) < 1e-6
+    assert abs(sum(s["local_loss"] for s in scal) / 2 - float(g["local_avg"])) < 1e-6
+    for k, v in sd.items():
+        ref = g[f"state.{k}"]
+        if v.numel() > 1:
+            assert close(digest(v), ref, 2e-5), k
+        else:
+            assert close(v.numpy(), ref, 2e-5), k
+    moved = {k[4:] for k in g.files if k.startswith("mom.")}
+    assert moved == set(bufs)
+    for k in moved:
+        assert close(digest(bufs[k]), g[f"mom.{k}"], 2e-5), k
+    # SURVEY note N3: parameters that no loss term reached are skipped by SGD entirely
+    untouched = [k for k in sd if orc.is_param(k) and k not in bufs]
+    init = orc.init_state(0)
+    for k in untouched:
+        assert torch.equal(sd[k], init[k]), k
+
+
+def test_known_answers():
+    """Closed forms verified against the reference ops."""
+    # trilinear x2 of [0,1,2,3] along one axis
+    x = torch.arange(4.0).view(1, 1, 1, 1, 4).expand(1, 1, 2, 2, 4).contiguous()
+    y = torch.nn.functional.interpolate(x, scale_factor=2, mode="trilinear")
+    assert torch.allclose(y[0, 0, 0, 0], torch.tensor([0, .25, .75, 1.25, 1.75, 2.25, 2.75, 3.0]))
+    # cosine similarity eps semantics and cos_loss symmetry / detach
+    a = [[torch.randn(4, 8), torch.randn(4, 8, requires_grad=True)] for _ in range(3)]
+    b = [[torch.randn(4, 8), torch.randn(4, 8, requires_grad=True)] for _ in range(3)]
+    loss, idx = orc.cos_loss(random.Random(0), a, b)
+    cs = torch.nn.functional.cosine_similarity
+    want = -(cs(a[idx][1], b[idx][0]).mean() + cs(b[idx][1], a[idx][0]).mean()) * 0.5
+    assert torch.allclose(loss, want)
+    # SGD with momentum: first step buf = g + wd*p
+    sd = {"w": torch.tensor([1.0, -2.0])}
+    bufs = {}
+    orc.sgd_step(sd, {"w": torch.tensor([0.5, 0.5]), "u": None}, bufs, lr=0.1, momentum=0.9, weight_decay=0.1)
+    assert torch.allclose(bufs["w"], torch.tensor([0.6, 0.3]))
+    assert torch.allclose(sd["w"], torch.tensor([0.94, -2.03]))
+    orc.sgd_step(sd, {"w": torch.tensor([0.5, 0.5])}, bufs, lr=0.1, momentum=0.9, weight_decay=0.1)
+    assert torch.allclose(bufs["w"], 0.9 * torch.tensor([0.6, 0.3]) + torch.tensor([0.5 + 0.094, 0.5 - 0.203]))
+    assert abs(orc.lr_at(120, 1e-3, 240) - 5e-4) < 1e-12
