@@ -35,8 +35,9 @@ const char* pcrl_last_error(void);
 int pcrl_version(void);
 
 /* ---- weight layout converters (state_dict layout <-> tensor-core operand layout) ---------- */
-/* nn.Conv3d.weight (Cout,Cin,3,3,3) fp32 -> wf [27][Cout][Cin] bf16 (forward operand) and, if
- * wd != NULL, wd [27][Cin][Cout] bf16 with mirrored taps (data-gradient operand).
+/* nn.Conv3d.weight (Cout,Cin,3,3,3) fp32 -> wf [9 (ky,kx)][3 (kz=2,1,0)][Cout][Cin] bf16 (forward
+ * operand) and, if wd != NULL, wd [9][3][Cin][Cout] bf16 with mirrored taps (data-gradient
+ * operand).
  * models/pcrlv2_model_3d.py:9 */
 int pcrl_pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, void* stream);
 /* packed weight gradient [27][Cout][Cin] fp32 -> (Cout,Cin,3,3,3) fp32 */

@@ -86,60 +86,72 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
   const int s_begin = kchunk * p.stages_per_cta;
   const int s_end = min(s_begin + p.stages_per_cta, p.total_stages);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+    // producer: the whole warp loops (operands stay warp-uniform), one elected lane issues
     int st = 0, ph = 0;
     const uint32_t tx = (uint32_t)(p.a_chunks * p.kr * p.a_row_bytes +
                                    p.b_chunks * p.b_box_rows * p.b_row_bytes);
     for (int s = s_begin; s < s_end; s++) {
       mbar_wait(&empty[st], ph ^ 1);
-      mbar_expect_tx(&full[st], tx);
       uint8_t* a_dst = smem + (size_t)st * stage_bytes;
       uint8_t* b_dst = a_dst + a_stage_bytes;
-      if (p.mode == WG_CONV) {
-        const int n = s / p.stages_per_sample;
-        const int mr0 = (s % p.stages_per_sample) * p.nrows;
-        for (int c = 0; c < p.a_chunks; c++)
-          tma_load_4d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st],
-                      mchunk * p.mc + c * 64, -1, mr0, n);
-        for (int c = 0; c < p.b_chunks; c++)
-          tma_load_4d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st],
-                      nchunk * p.nc + c * 64, -1, mr0 + dzo * p.H1 + dyo - 1, n);
-      } else {
-        const int r0 = s * p.nrows;
-        for (int c = 0; c < p.a_chunks; c++)
-          tma_load_2d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st], mchunk * p.mc + c * 64, r0);
-        for (int c = 0; c < p.b_chunks; c++)
-          tma_load_2d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st], nchunk * p.nc + c * 64, r0);
+      if (elect_one()) {
+        mbar_expect_tx(&full[st], tx);
+        if (p.mode == WG_CONV) {
+          const int n = s / p.stages_per_sample;
+          const int mr0 = (s % p.stages_per_sample) * p.nrows;
+          for (int c = 0; c < p.a_chunks; c++)
+            tma_load_4d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st],
+                        mchunk * p.mc + c * 64, -1, mr0, n);
+          for (int c = 0; c < p.b_chunks; c++)
+            tma_load_4d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st],
+                        nchunk * p.nc + c * 64, -1, mr0 + dzo * p.H1 + dyo - 1, n);
+        } else {
+          const int r0 = s * p.nrows;
+          for (int c = 0; c < p.a_chunks; c++)
+            tma_load_2d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st], mchunk * p.mc + c * 64, r0);
+          for (int c = 0; c < p.b_chunks; c++)
+            tma_load_2d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st], nchunk * p.nc + c * 64, r0);
+        }
       }
+      __syncwarp();
       if (++st == p.stages) { st = 0; ph ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     int st = 0, ph = 0;
     const uint32_t idesc = make_idesc(1, (uint32_t)p.mc, (uint32_t)p.nc, 1, 1);
     const uint64_t a_hi = make_smem_desc(0, p.a_chunk_bytes, 8 * p.a_row_bytes,
                                          p.a_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
     const uint64_t b_hi = make_smem_desc(0, p.b_chunk_bytes, 8 * p.b_row_bytes,
                                          p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
+    const uint32_t a_step = (uint32_t)(16 * p.a_row_bytes) >> 4, b_step = (uint32_t)(16 * p.b_row_bytes) >> 4;
     uint32_t accumulate = 0;
     for (int s = s_begin; s < s_end; s++) {
       mbar_wait(&full[st], ph);
       tc_fence_after();
       const uint32_t a_base = smem_u32(smem + (size_t)st * stage_bytes);
       const uint32_t b_base = a_base + a_stage_bytes;
-      for (int t = 0; t < p.ntaps; t++) {
-        const int b_row0 = (p.mode == WG_CONV) ? (p.Wp + (t - 1)) : 0;
-        for (int ks = 0; ks < p.ksteps; ks++) {
-          const uint32_t aa = a_base + (uint32_t)(ks * 16) * p.a_row_bytes;
-          const uint32_t ba = b_base + (uint32_t)(b_row0 + ks * 16) * p.b_row_bytes;
-          umma_bf16(tmem + t * p.nc, a_hi | (uint64_t)((aa >> 4) & 0x3FFF),
-                    b_hi | (uint64_t)((ba >> 4) & 0x3FFF), idesc, (ks > 0) ? 1u : accumulate);
+      if (elect_one()) {
+        for (int t = 0; t < p.ntaps; t++) {
+          const int b_row0 = (p.mode == WG_CONV) ? (p.Wp + (t - 1)) : 0;
+          uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
+          uint64_t bd = b_hi | (uint64_t)(((b_base + (uint32_t)b_row0 * p.b_row_bytes) >> 4) & 0x3FFF);
+          const uint32_t d = tmem + t * p.nc;
+          umma_bf16(d, ad, bd, idesc, accumulate);
+          for (int ks = 1; ks < p.ksteps; ks++) {
+            ad += a_step;
+            bd += b_step;
+            umma_bf16(d, ad, bd, idesc, 1u);
+          }
         }
+        umma_commit(&empty[st]);
       }
+      __syncwarp();
       accumulate = 1;
-      umma_commit(&empty[st]);
       if (++st == p.stages) { st = 0; ph ^= 1; }
     }
-    umma_commit(acc_full);
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
   }
   __syncwarp();
 

@@ -52,8 +52,10 @@ __device__ __forceinline__ float act_bwd(float z, int act, float slope) {
 }
 
 // ------------------------------------------------------------------------------ weight packers
-// w [Cout][Cin][27] fp32 -> wf [27][Cout][Cin] bf16 (forward) and wd [27][Cin][Cout] bf16 with
-// the taps mirrored (data gradient).
+// w [Cout][Cin][27] fp32 (tap = (kz*3+ky)*3+kx) -> tensor-core operand layouts of igemm_kmajor:
+//   wf [9 (ky,kx)][3 (kz = 2,1,0)][Cout][Cin] bf16   forward
+//   wd [9][3][Cin][Cout] bf16, taps mirrored          data gradient
+// (the kz-innermost order lets one TMA box fetch the filters of up to three stacked output planes)
 __global__ void pack_conv3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                   __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
   const long long total = (long long)Cout * Cin * 27;
@@ -62,9 +64,14 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, __nv_bfloat16* __
     const int tap = (int)(i % 27);
     const long long r = i / 27;
     const int ci = (int)(r % Cin), co = (int)(r / Cin);
+    const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
     const __nv_bfloat16 v = __float2bfloat16(w[i]);
-    wf[((size_t)tap * Cout + co) * Cin + ci] = v;
-    if (wd) wd[((size_t)(26 - tap) * Cin + ci) * Cout + co] = v;
+    const int tf = (ky * 3 + kx) * 3 + (2 - kz);
+    wf[((size_t)tf * Cout + co) * Cin + ci] = v;
+    if (wd) {
+      const int td = ((2 - ky) * 3 + (2 - kx)) * 3 + kz;
+      wd[((size_t)td * Cin + ci) * Cout + co] = v;
+    }
   }
 }
 // gpk [27][Cout][Cin] fp32 -> g [Cout][Cin][27] fp32
@@ -316,14 +323,55 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
       sl[i] = p.prelu ? p.prelu[c8 * 8 + i] : 0.f;
     }
   }
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int cell = (int)(it / C8);
-    const int wq = cell % cw;
-    const int hp = (cell / cw) % (ch + 1);
-    const int d = cell / (cw * (ch + 1));
-    if (hp == 0) {  // pad rows of the outputs
-      if (POOL) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (!POOL) {
+    // four independent voxels per thread per trip: all loads are issued before the first use
+    for (long long it0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += 4 * stride) {
+      uint4 yv[4];
+      size_t off[4];
+      int kind[4];  // 0 = out of range, 1 = pad row, 2 = voxel
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long it = it0 + u * stride;
+        kind[u] = 0;
+        off[u] = 0;
+        if (it < items) {
+          const int cell = (int)(it / C8);
+          const int wq = cell % cw;
+          const int hp = (cell / cw) % (ch + 1);
+          const int d = cell / (cw * (ch + 1));
+          off[u] = ((((size_t)n * p.D + d) * H1 + hp) * p.W + wq) * p.C + c8 * 8;
+          kind[u] = hp == 0 ? 1 : 2;
+          if (kind[u] == 2) yv[u] = *reinterpret_cast<const uint4*>(p.y + off[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (kind[u] == 1) {
+          if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off[u]) = make_uint4(0, 0, 0, 0);
+        } else if (kind[u] == 2) {
+          float v[8];
+          unpack8(yv[u], v);
+#pragma unroll
+          for (int q = 0; q < 8; q++) v[q] = act_fwd(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
+          const uint4 o = pack8(v);
+          if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off[u]) = o;
+          if (p.avg_sum) {
+            float r[8];
+            unpack8(o, r);  // average the stored (rounded) activations
+#pragma unroll
+            for (int q = 0; q < 8; q++) asum[q] += r[q];
+          }
+        }
+      }
+    }
+  } else {
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
+      const int cell = (int)(it / C8);
+      const int wq = cell % cw;
+      const int hp = (cell / cw) % (ch + 1);
+      const int d = cell / (cw * (ch + 1));
+      if (hp == 0) {  // pad rows of the outputs
         if (p.pool_out)
           *reinterpret_cast<uint4*>(p.pool_out + (((size_t)n * cd + d) * (ch + 1) * cw + wq) * p.C + c8 * 8) =
               make_uint4(0, 0, 0, 0);
@@ -333,52 +381,34 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
               *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * wq + k) * p.C + c8 * 8) =
                   make_uint4(0, 0, 0, 0);
         }
-      } else if (p.a_out) {
-        *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + d) * H1) * p.W + wq) * p.C + c8 * 8) =
-            make_uint4(0, 0, 0, 0);
+        continue;
       }
-      continue;
-    }
-    const int h = hp - 1;
-    if (POOL) {
+      const int h = hp - 1;
       float mx[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) mx[i] = -INFINITY;
+      uint4 yv[8];
 #pragma unroll
-      for (int i = 0; i < 2; i++)
+      for (int pos = 0; pos < 8; pos++) {
+        const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
+        yv[pos] = *reinterpret_cast<const uint4*>(
+            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8);
+      }
 #pragma unroll
-        for (int j = 0; j < 2; j++)
+      for (int pos = 0; pos < 8; pos++) {
+        const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
+        float v[8];
+        unpack8(yv[pos], v);
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8;
-            float v[8];
-            unpack8(*reinterpret_cast<const uint4*>(p.y + off), v);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              v[q] = act_fwd(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
-              mx[q] = fmaxf(mx[q], v[q]);
-              asum[q] += v[q];
-            }
-            if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off) = pack8(v);
-          }
+        for (int q = 0; q < 8; q++) {
+          v[q] = act_fwd(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
+          mx[q] = fmaxf(mx[q], v[q]);
+        }
+        if (p.a_out)
+          *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8) = pack8(v);
+      }
       if (p.pool_out)
         *reinterpret_cast<uint4*>(p.pool_out + ((((size_t)n * cd + d) * (ch + 1) + hp) * cw + wq) * p.C + c8 * 8) = pack8(mx);
-    } else {
-      const size_t off = ((((size_t)n * p.D + d) * H1 + hp) * p.W + wq) * p.C + c8 * 8;
-      float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(p.y + off), v);
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        v[q] = act_fwd(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
-      }
-      const uint4 u = pack8(v);
-      if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off) = u;
-      if (p.avg_sum) {
-        float r[8];
-        unpack8(u, r);  // average the stored (rounded) activations
-#pragma unroll
-        for (int q = 0; q < 8; q++) asum[q] += r[q];
-      }
     }
   }
   if (p.avg_sum) {
@@ -448,7 +478,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
 #pragma unroll
   for (int i = 0; i < 8; i++) a0[i] = a1[i] = a2[i] = 0.f;
 
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; POOL && it < items;
        it += (long long)gridDim.x * blockDim.x) {
     const int cell = (int)(it / C8);
     const int wq = cell % cw;
@@ -514,29 +544,61 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
         }
         if (APPLY) *reinterpret_cast<uint4*>(p.dy + off) = pack8(out);
       }
-    } else {
-      const size_t off = ((((size_t)n * p.D + d) * H1 + hp) * p.W + wq) * p.C + c8 * 8;
-      float yv[8], g1v[8], g2v[8], out[8];
-      unpack8(*reinterpret_cast<const uint4*>(p.y + off), yv);
-      if (p.g1) unpack8(*reinterpret_cast<const uint4*>(p.g1 + off), g1v);
-      if (p.g2) unpack8(*reinterpret_cast<const uint4*>(p.g2 + off), g2v);
+    }
+  }
+  if (!POOL) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long it0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += 4 * stride) {
+      uint4 yq[4], g1q[4], g2q[4];
+      size_t off[4];
+      int kind[4];
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const float z = fmaf(yv[q], sc[q], sh[q]);
-        float da = ga[q];
-        if (p.g1) da += g1v[q];
-        if (p.g2) da += g2v[q];
-        const float dz = da * act_bwd(z, p.act, sl[q]);
-        const float xh = (yv[q] - mu[q]) * is[q];
-        if (APPLY) {
-          out[q] = gs[q] * (dz - k1[q] - xh * k2[q]);
-        } else {
-          a0[q] += dz;
-          a1[q] += dz * xh;
-          a2[q] += da * fminf(z, 0.f);
+      for (int u = 0; u < 4; u++) {
+        const long long it = it0 + u * stride;
+        kind[u] = 0;
+        off[u] = 0;
+        if (it < items) {
+          const int cell = (int)(it / C8);
+          const int wq = cell % cw;
+          const int hp = (cell / cw) % (ch + 1);
+          const int d = cell / (cw * (ch + 1));
+          off[u] = ((((size_t)n * p.D + d) * H1 + hp) * p.W + wq) * p.C + c8 * 8;
+          kind[u] = hp == 0 ? 1 : 2;
+          if (kind[u] == 2) {
+            yq[u] = *reinterpret_cast<const uint4*>(p.y + off[u]);
+            if (p.g1) g1q[u] = *reinterpret_cast<const uint4*>(p.g1 + off[u]);
+            if (p.g2) g2q[u] = *reinterpret_cast<const uint4*>(p.g2 + off[u]);
+          }
         }
       }
-      if (APPLY) *reinterpret_cast<uint4*>(p.dy + off) = pack8(out);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (kind[u] == 1) {
+          if (APPLY) *reinterpret_cast<uint4*>(p.dy + off[u]) = make_uint4(0, 0, 0, 0);
+        } else if (kind[u] == 2) {
+          float yv[8], g1v[8], g2v[8], out[8];
+          unpack8(yq[u], yv);
+          if (p.g1) unpack8(g1q[u], g1v);
+          if (p.g2) unpack8(g2q[u], g2v);
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const float z = fmaf(yv[q], sc[q], sh[q]);
+            float da = ga[q];
+            if (p.g1) da += g1v[q];
+            if (p.g2) da += g2v[q];
+            const float dz = da * act_bwd(z, p.act, sl[q]);
+            const float xh = (yv[q] - mu[q]) * is[q];
+            if (APPLY) {
+              out[q] = gs[q] * (dz - k1[q] - xh * k2[q]);
+            } else {
+              a0[q] += dz;
+              a1[q] += dz * xh;
+              a2[q] += da * fminf(z, 0.f);
+            }
+          }
+          if (APPLY) *reinterpret_cast<uint4*>(p.dy + off[u]) = pack8(out);
+        }
+      }
     }
   }
   if (!APPLY) {
