@@ -291,7 +291,10 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, double co
 //   a_out    full resolution (nullable),
 //   pool_out 2x2x2 max-pool, H-padded [N][D/2][H/2+1][W/2][C] (nullable),
 //   avg_sum  [N][C] fp32 += sum over voxels of a (nullable; caller zeroes; divide by D*H*W later).
-// One thread owns 8 channels of one 2x2x2 cell (pool) or one voxel (no pool).
+// Work is mapped by merged row: a block owns whole rows of the (pooled) output, a thread owns 8
+// channels (16 bytes) of one column of the row and keeps that channel group for the whole kernel,
+// so the only integer division in the loop is the pad-row test.  RELU is specialised at compile
+// time (ACT = PCRL_ACT_RELU), every other activation takes the generic path (ACT = -1).
 struct NormActFwdParams {
   const __nv_bfloat16* y;
   const float* scale; const float* shift; const float* prelu;
@@ -299,61 +302,81 @@ struct NormActFwdParams {
   int per_sample, act, N, D, H, W, C;
 };
 
-template <bool POOL>
+struct RowMap {
+  int rows_per_iter, t_row, w, c8, items_per_row, chunks;
+};
+__device__ __forceinline__ RowMap make_row_map(int cw, int C8) {
+  RowMap m;
+  m.items_per_row = cw * C8;
+  m.rows_per_iter = (int)blockDim.x / m.items_per_row;
+  if (m.rows_per_iter < 1) m.rows_per_iter = 1;
+  m.chunks = (m.items_per_row + (int)blockDim.x - 1) / (int)blockDim.x;  // > 1 only for very wide rows
+  const int t_item = (int)threadIdx.x % m.items_per_row;
+  m.t_row = (int)threadIdx.x / m.items_per_row;
+  m.w = t_item / C8;
+  m.c8 = t_item % C8;
+  return m;
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_f(float z, int act, float slope) {
+  if (ACT == ACT_RELU) return fmaxf(z, 0.f);
+  return act_fwd(z, act, slope);
+}
+template <int ACT>
+__device__ __forceinline__ float act_d(float z, int act, float slope) {
+  if (ACT == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  return act_bwd(z, act, slope);
+}
+
+template <bool POOL, int ACT>
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParams p) {
   extern __shared__ float red[];  // [blockDim.x][8] when avg_sum
   const int n = blockIdx.y;
   const int C8 = p.C >> 3;
   const int H1 = p.H + 1;
   const int cd = POOL ? p.D / 2 : p.D, ch = POOL ? p.H / 2 : p.H, cw = POOL ? p.W / 2 : p.W;
-  const int cells = cd * (ch + 1) * cw;  // +1: the pad row of the (pooled / full) output
-  const long long items = (long long)cells * C8;
-  float asum[8];
+  const int R = cd * (ch + 1);                 // merged rows of the (pooled) output
+  const RowMap m = make_row_map(cw, C8);
+  const bool lane_ok = m.t_row < m.rows_per_iter && m.chunks == 1;
+  float asum[8], sc[8], sh[8], sl[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) asum[i] = 0.f;
-  // blockDim.x is a multiple of C8, gridDim.x*blockDim.x too: a thread keeps its channel group
-  const int c8 = threadIdx.x % C8;
-  float sc[8], sh[8], sl[8];
   {
-    const size_t o = (p.per_sample ? (size_t)n * p.C : 0) + c8 * 8;
+    const size_t o = (p.per_sample ? (size_t)n * p.C : 0) + m.c8 * 8;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       sc[i] = p.scale[o + i];
       sh[i] = p.shift[o + i];
-      sl[i] = p.prelu ? p.prelu[c8 * 8 + i] : 0.f;
+      sl[i] = p.prelu ? p.prelu[m.c8 * 8 + i] : 0.f;
     }
   }
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  if (!POOL) {
-    // four independent voxels per thread per trip: all loads are issued before the first use
-    for (long long it0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += 4 * stride) {
-      uint4 yv[4];
-      size_t off[4];
-      int kind[4];  // 0 = out of range, 1 = pad row, 2 = voxel
+  constexpr int U = POOL ? 1 : 4;
+  const size_t row_elems = (size_t)p.W * p.C;            // elements of one fine row
+  for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < R; row0 += gridDim.x * m.rows_per_iter * U) {
+    if (!POOL) {
+      uint4 yv[U];
+      int kind[U];
+      size_t off[U];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const long long it = it0 + u * stride;
+      for (int u = 0; u < U; u++) {
+        const int row = row0 + u * m.rows_per_iter + m.t_row;
         kind[u] = 0;
-        off[u] = 0;
-        if (it < items) {
-          const int cell = (int)(it / C8);
-          const int wq = cell % cw;
-          const int hp = (cell / cw) % (ch + 1);
-          const int d = cell / (cw * (ch + 1));
-          off[u] = ((((size_t)n * p.D + d) * H1 + hp) * p.W + wq) * p.C + c8 * 8;
-          kind[u] = hp == 0 ? 1 : 2;
+        if (lane_ok && row < R) {
+          off[u] = ((size_t)n * R + row) * row_elems + (size_t)m.w * p.C + m.c8 * 8;
+          kind[u] = (row % H1) == 0 ? 1 : 2;
           if (kind[u] == 2) yv[u] = *reinterpret_cast<const uint4*>(p.y + off[u]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < U; u++) {
         if (kind[u] == 1) {
           if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off[u]) = make_uint4(0, 0, 0, 0);
         } else if (kind[u] == 2) {
           float v[8];
           unpack8(yv[u], v);
 #pragma unroll
-          for (int q = 0; q < 8; q++) v[q] = act_fwd(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
+          for (int q = 0; q < 8; q++) v[q] = act_f<ACT>(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
           const uint4 o = pack8(v);
           if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off[u]) = o;
           if (p.avg_sum) {
@@ -364,36 +387,31 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
           }
         }
       }
-    }
-  } else {
-    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
-      const int cell = (int)(it / C8);
-      const int wq = cell % cw;
-      const int hp = (cell / cw) % (ch + 1);
-      const int d = cell / (cw * (ch + 1));
+    } else {
+      const int row = row0 + m.t_row;
+      if (!(lane_ok && row < R)) continue;
+      const int hp = row % (ch + 1), d = row / (ch + 1);
+      const size_t pooled_off = (((size_t)n * R + row) * cw + m.w) * p.C + m.c8 * 8;
       if (hp == 0) {  // pad rows of the outputs
-        if (p.pool_out)
-          *reinterpret_cast<uint4*>(p.pool_out + (((size_t)n * cd + d) * (ch + 1) * cw + wq) * p.C + c8 * 8) =
-              make_uint4(0, 0, 0, 0);
-        if (p.a_out) {  // two fine planes, their pad rows, two fine columns
+        if (p.pool_out) *reinterpret_cast<uint4*>(p.pool_out + pooled_off) = make_uint4(0, 0, 0, 0);
+        if (p.a_out)
           for (int i = 0; i < 2; i++)
             for (int k = 0; k < 2; k++)
-              *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * wq + k) * p.C + c8 * 8) =
+              *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8) =
                   make_uint4(0, 0, 0, 0);
-        }
         continue;
       }
       const int h = hp - 1;
-      float mx[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) mx[i] = -INFINITY;
       uint4 yv[8];
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
         yv[pos] = *reinterpret_cast<const uint4*>(
-            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8);
+            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
       }
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) mx[i] = -INFINITY;
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
@@ -401,21 +419,22 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
         unpack8(yv[pos], v);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          v[q] = act_fwd(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
+          v[q] = act_f<ACT>(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
           mx[q] = fmaxf(mx[q], v[q]);
         }
         if (p.a_out)
-          *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8) = pack8(v);
+          *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8) = pack8(v);
       }
-      if (p.pool_out)
-        *reinterpret_cast<uint4*>(p.pool_out + ((((size_t)n * cd + d) * (ch + 1) + hp) * cw + wq) * p.C + c8 * 8) = pack8(mx);
+      if (p.pool_out) *reinterpret_cast<uint4*>(p.pool_out + pooled_off) = pack8(mx);
     }
   }
   if (p.avg_sum) {
 #pragma unroll
-    for (int q = 0; q < 8; q++) red[threadIdx.x * 8 + q] = asum[q];
+    for (int q = 0; q < 8; q++) red[threadIdx.x * 8 + q] = lane_ok ? asum[q] : 0.f;
     __syncthreads();
     if (threadIdx.x < C8) {
+      // threads with the same channel group: t_item % C8 == c8, i.e. threadIdx % C8 when
+      // items_per_row is a multiple of C8 (it is: items_per_row = cw * C8)
       float t[8];
 #pragma unroll
       for (int q = 0; q < 8; q++) t[q] = 0.f;
@@ -446,124 +465,55 @@ struct NormActBwdParams {
   int per_sample, act, N, D, H, W, C;
 };
 
-template <bool POOL, bool APPLY>
+template <bool POOL, bool APPLY, int ACT>
 __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParams p) {
   extern __shared__ float red[];  // pass 1: [blockDim.x][24]
   const int n = blockIdx.y;
   const int C8 = p.C >> 3;
   const int H1 = p.H + 1;
   const int cd = POOL ? p.D / 2 : p.D, ch = POOL ? p.H / 2 : p.H, cw = POOL ? p.W / 2 : p.W;
-  const int cells = cd * (ch + 1) * cw;
-  const long long items = (long long)cells * C8;
-  const int c8 = threadIdx.x % C8;
-  const size_t so = (p.per_sample ? (size_t)n * p.C : 0) + c8 * 8;
-  float sc[8], sh[8], sl[8], mu[8], is[8], k1[8], k2[8], gs[8], ga[8];
+  const int R = cd * (ch + 1);
+  const RowMap m = make_row_map(cw, C8);
+  const bool lane_ok = m.t_row < m.rows_per_iter && m.chunks == 1;
+  const size_t so = (p.per_sample ? (size_t)n * p.C : 0) + m.c8 * 8;
+  // x_hat = y*is - mis ; z = y*sc + sh ; apply: dy = gs*dz - c1 - y*c2   (constants folded)
+  float sc[8], sh[8], sl[8], is[8], mis[8], c1[8], c2[8], gs[8], ga[8];
   const float inv_vol = 1.f / ((float)p.D * p.H * p.W);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     sc[i] = p.scale[so + i];
     sh[i] = p.shift[so + i];
-    mu[i] = p.mean[so + i];
     is[i] = p.invstd[so + i];
-    sl[i] = p.prelu ? p.prelu[c8 * 8 + i] : 0.f;
-    ga[i] = p.gavg ? p.gavg[(size_t)n * p.C + c8 * 8 + i] * inv_vol : 0.f;
+    mis[i] = p.mean[so + i] * is[i];
+    sl[i] = p.prelu ? p.prelu[m.c8 * 8 + i] : 0.f;
+    ga[i] = p.gavg ? p.gavg[(size_t)n * p.C + m.c8 * 8 + i] * inv_vol : 0.f;
+    gs[i] = c1[i] = c2[i] = 0.f;
     if (APPLY) {
       const double* s = p.sums + (so + i) * 3;
-      k1[i] = (float)(s[0] / p.count);
-      k2[i] = (float)(s[1] / p.count);
-      gs[i] = p.gamma[c8 * 8 + i] * is[i];
+      const float k1 = (float)(s[0] / p.count), k2 = (float)(s[1] / p.count);
+      gs[i] = p.gamma[m.c8 * 8 + i] * is[i];
+      // gs*(dz - k1 - xh*k2) with xh = y*is - mis
+      c1[i] = gs[i] * (k1 - mis[i] * k2);
+      c2[i] = gs[i] * k2 * is[i];
     }
   }
   float a0[8], a1[8], a2[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) a0[i] = a1[i] = a2[i] = 0.f;
-
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; POOL && it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int cell = (int)(it / C8);
-    const int wq = cell % cw;
-    const int hp = (cell / cw) % (ch + 1);
-    const int d = cell / (cw * (ch + 1));
-    if (hp == 0) {
-      if (APPLY) {
-        if (POOL) {
-          for (int i = 0; i < 2; i++)
-            for (int k = 0; k < 2; k++)
-              *reinterpret_cast<uint4*>(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * wq + k) * p.C + c8 * 8) =
-                  make_uint4(0, 0, 0, 0);
-        } else {
-          *reinterpret_cast<uint4*>(p.dy + ((((size_t)n * p.D + d) * H1) * p.W + wq) * p.C + c8 * 8) =
-              make_uint4(0, 0, 0, 0);
-        }
-      }
-      continue;
-    }
-    const int h = hp - 1;
-    if (POOL) {
-      float gp[8];
-      unpack8(*reinterpret_cast<const uint4*>(p.g1 + ((((size_t)n * cd + d) * (ch + 1) + hp) * cw + wq) * p.C + c8 * 8), gp);
-      float yv[8][8];   // [position][channel]
-      float zv[8][8];
-      int arg[8];
-      float mx[8];
+  constexpr int U = POOL ? 1 : 4;
+  const size_t row_elems = (size_t)p.W * p.C;
+  for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < R; row0 += gridDim.x * m.rows_per_iter * U) {
+    if (!POOL) {
+      uint4 yq[U], g1q[U], g2q[U];
+      int kind[U];
+      size_t off[U];
 #pragma unroll
-      for (int q = 0; q < 8; q++) { mx[q] = -INFINITY; arg[q] = 0; }
-#pragma unroll
-      for (int pos = 0; pos < 8; pos++) {
-        const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
-        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8;
-        unpack8(*reinterpret_cast<const uint4*>(p.y + off), yv[pos]);
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          zv[pos][q] = fmaf(yv[pos][q], sc[q], sh[q]);
-          // same fp32 values and scan order as the forward pass: the first maximum wins
-          const float a = act_fwd(zv[pos][q], p.act, sl[q]);
-          if (a > mx[q]) { mx[q] = a; arg[q] = pos; }
-        }
-      }
-#pragma unroll
-      for (int pos = 0; pos < 8; pos++) {
-        const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
-        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * wq + k) * p.C + c8 * 8;
-        float g2v[8];
-        if (p.g2) unpack8(*reinterpret_cast<const uint4*>(p.g2 + off), g2v);
-        float out[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          float da = (arg[q] == pos ? gp[q] : 0.f) + ga[q];
-          if (p.g2) da += g2v[q];
-          const float dz = da * act_bwd(zv[pos][q], p.act, sl[q]);
-          const float xh = (yv[pos][q] - mu[q]) * is[q];
-          if (APPLY) {
-            out[q] = gs[q] * (dz - k1[q] - xh * k2[q]);
-          } else {
-            a0[q] += dz;
-            a1[q] += dz * xh;
-            a2[q] += da * fminf(zv[pos][q], 0.f);
-          }
-        }
-        if (APPLY) *reinterpret_cast<uint4*>(p.dy + off) = pack8(out);
-      }
-    }
-  }
-  if (!POOL) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long it0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += 4 * stride) {
-      uint4 yq[4], g1q[4], g2q[4];
-      size_t off[4];
-      int kind[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const long long it = it0 + u * stride;
+      for (int u = 0; u < U; u++) {
+        const int row = row0 + u * m.rows_per_iter + m.t_row;
         kind[u] = 0;
-        off[u] = 0;
-        if (it < items) {
-          const int cell = (int)(it / C8);
-          const int wq = cell % cw;
-          const int hp = (cell / cw) % (ch + 1);
-          const int d = cell / (cw * (ch + 1));
-          off[u] = ((((size_t)n * p.D + d) * H1 + hp) * p.W + wq) * p.C + c8 * 8;
-          kind[u] = hp == 0 ? 1 : 2;
+        if (lane_ok && row < R) {
+          off[u] = ((size_t)n * R + row) * row_elems + (size_t)m.w * p.C + m.c8 * 8;
+          kind[u] = (row % H1) == 0 ? 1 : 2;
           if (kind[u] == 2) {
             yq[u] = *reinterpret_cast<const uint4*>(p.y + off[u]);
             if (p.g1) g1q[u] = *reinterpret_cast<const uint4*>(p.g1 + off[u]);
@@ -572,7 +522,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < U; u++) {
         if (kind[u] == 1) {
           if (APPLY) *reinterpret_cast<uint4*>(p.dy + off[u]) = make_uint4(0, 0, 0, 0);
         } else if (kind[u] == 2) {
@@ -586,27 +536,86 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
             float da = ga[q];
             if (p.g1) da += g1v[q];
             if (p.g2) da += g2v[q];
-            const float dz = da * act_bwd(z, p.act, sl[q]);
-            const float xh = (yv[q] - mu[q]) * is[q];
+            const float dz = da * act_d<ACT>(z, p.act, sl[q]);
             if (APPLY) {
-              out[q] = gs[q] * (dz - k1[q] - xh * k2[q]);
+              out[q] = fmaf(gs[q], dz, -fmaf(yv[q], c2[q], c1[q]));
             } else {
               a0[q] += dz;
-              a1[q] += dz * xh;
-              a2[q] += da * fminf(z, 0.f);
+              a1[q] = fmaf(dz, fmaf(yv[q], is[q], -mis[q]), a1[q]);
+              if (ACT != ACT_RELU) a2[q] += da * fminf(z, 0.f);
             }
           }
           if (APPLY) *reinterpret_cast<uint4*>(p.dy + off[u]) = pack8(out);
         }
+      }
+    } else {
+      const int row = row0 + m.t_row;
+      if (!(lane_ok && row < R)) continue;
+      const int hp = row % (ch + 1), d = row / (ch + 1);
+      if (hp == 0) {
+        if (APPLY)
+          for (int i = 0; i < 2; i++)
+            for (int k = 0; k < 2; k++)
+              *reinterpret_cast<uint4*>(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8) =
+                  make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      const int h = hp - 1;
+      float gp[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.g1 + (((size_t)n * R + row) * cw + m.w) * p.C + m.c8 * 8), gp);
+      uint4 yq[8];
+#pragma unroll
+      for (int pos = 0; pos < 8; pos++) {
+        const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
+        yq[pos] = *reinterpret_cast<const uint4*>(
+            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
+      }
+      int arg[8];
+      float mx[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) { mx[q] = -INFINITY; arg[q] = 0; }
+#pragma unroll
+      for (int pos = 0; pos < 8; pos++) {
+        float yv[8];
+        unpack8(yq[pos], yv);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          // same fp32 values and scan order as the forward pass: the first maximum wins
+          const float a = act_f<ACT>(fmaf(yv[q], sc[q], sh[q]), p.act, sl[q]);
+          if (a > mx[q]) { mx[q] = a; arg[q] = pos; }
+        }
+      }
+#pragma unroll
+      for (int pos = 0; pos < 8; pos++) {
+        const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
+        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8;
+        float yv[8], g2v[8], out[8];
+        unpack8(yq[pos], yv);
+        if (p.g2) unpack8(*reinterpret_cast<const uint4*>(p.g2 + off), g2v);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float z = fmaf(yv[q], sc[q], sh[q]);
+          float da = (arg[q] == pos ? gp[q] : 0.f) + ga[q];
+          if (p.g2) da += g2v[q];
+          const float dz = da * act_d<ACT>(z, p.act, sl[q]);
+          if (APPLY) {
+            out[q] = fmaf(gs[q], dz, -fmaf(yv[q], c2[q], c1[q]));
+          } else {
+            a0[q] += dz;
+            a1[q] = fmaf(dz, fmaf(yv[q], is[q], -mis[q]), a1[q]);
+            if (ACT != ACT_RELU) a2[q] += da * fminf(z, 0.f);
+          }
+        }
+        if (APPLY) *reinterpret_cast<uint4*>(p.dy + off) = pack8(out);
       }
     }
   }
   if (!APPLY) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-      red[threadIdx.x * 24 + q] = a0[q];
-      red[threadIdx.x * 24 + 8 + q] = a1[q];
-      red[threadIdx.x * 24 + 16 + q] = a2[q];
+      red[threadIdx.x * 24 + q] = lane_ok ? a0[q] : 0.f;
+      red[threadIdx.x * 24 + 8 + q] = lane_ok ? a1[q] : 0.f;
+      red[threadIdx.x * 24 + 16 + q] = lane_ok ? a2[q] : 0.f;
     }
     __syncthreads();
     if (threadIdx.x < C8 * 3) {
@@ -762,18 +771,29 @@ int norm_finalize(const double* stats, double count, const float* gamma, const f
 int norm_act_fwd(const void* y, const float* scale, const float* shift, const float* prelu,
                  void* a_out, void* pool_out, float* avg_sum, int per_sample, int act, int pool,
                  int N, int D, int H, int W, int C, cudaStream_t s) {
-  PCRL_REQUIRE(C % 8 == 0, "norm_act_fwd: C=%d must be a multiple of 8", C);
+  PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_fwd: C=%d must be 8 * 2^k", C);
   PCRL_REQUIRE(!pool || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "norm_act_fwd: pooling needs even dims");
   PCRL_REQUIRE(!(pool && avg_sum), "norm_act_fwd: avg_sum with pool is not supported");
+  const int cw = pool ? W / 2 : W;
+  PCRL_REQUIRE(cw * (C / 8) <= 256, "norm_act_fwd: row of %d x %d channels is too wide", cw, C);
   NormActFwdParams p{(const __nv_bfloat16*)y, scale, shift, prelu, (__nv_bfloat16*)a_out,
                      (__nv_bfloat16*)pool_out, avg_sum, per_sample, act, N, D, H, W, C};
-  const int C8 = C / 8, block = block_for_c8(C8);
-  const long long cells = pool ? (long long)(D / 2) * (H / 2 + 1) * (W / 2) : (long long)D * (H + 1) * W;
-  const int per_thread = pool ? 1 : 4;
-  dim3 grid(grid_for((cells * C8 + per_thread - 1) / per_thread, block, 1 << 20), N);
-  const size_t smem = avg_sum ? (size_t)block * 8 * 4 : 0;
-  if (pool) norm_act_fwd_kernel<true><<<grid, block, smem, s>>>(p);
-  else norm_act_fwd_kernel<false><<<grid, block, smem, s>>>(p);
+  const int items = cw * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
+  const int R = pool ? (D / 2) * (H / 2 + 1) : D * (H + 1);
+  int bx = (R + rpi * U - 1) / (rpi * U);
+  const int cap = (num_sms() * 8 + N - 1) / N;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, N);
+  const size_t smem = avg_sum ? (size_t)256 * 8 * 4 : 0;
+  const bool relu = act == ACT_RELU;
+  if (pool) {
+    if (relu) norm_act_fwd_kernel<true, ACT_RELU><<<grid, 256, smem, s>>>(p);
+    else norm_act_fwd_kernel<true, -1><<<grid, 256, smem, s>>>(p);
+  } else {
+    if (relu) norm_act_fwd_kernel<false, ACT_RELU><<<grid, 256, smem, s>>>(p);
+    else norm_act_fwd_kernel<false, -1><<<grid, 256, smem, s>>>(p);
+  }
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -784,23 +804,35 @@ int norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gav
                  const float* gamma, const float* prelu, double* sums, void* dy, double count,
                  int per_sample, int act, int pool, int pass, int N, int D, int H, int W, int C,
                  cudaStream_t s) {
-  PCRL_REQUIRE(C % 8 == 0, "norm_act_bwd: C=%d must be a multiple of 8", C);
+  PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_bwd: C=%d must be 8 * 2^k", C);
   PCRL_REQUIRE(!pool || g1, "norm_act_bwd: pooled backward needs g1");
+  const int cw = pool ? W / 2 : W;
+  PCRL_REQUIRE(cw * (C / 8) <= 256, "norm_act_bwd: row of %d x %d channels is too wide", cw, C);
   NormActBwdParams p{(const __nv_bfloat16*)y, (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, gavg,
                      scale, shift, mean, invstd, gamma, prelu, sums, (__nv_bfloat16*)dy, count,
                      per_sample, act, N, D, H, W, C};
-  const int C8 = C / 8, block = block_for_c8(C8);
-  const long long cells = pool ? (long long)(D / 2) * (H / 2 + 1) * (W / 2) : (long long)D * (H + 1) * W;
-  const int per_thread = pool ? 1 : 4;
-  dim3 grid(grid_for((cells * C8 + per_thread - 1) / per_thread, block, 1 << 20), N);
+  const int items = cw * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
+  const int R = pool ? (D / 2) * (H / 2 + 1) : D * (H + 1);
+  int bx = (R + rpi * U - 1) / (rpi * U);
+  const int cap = (num_sms() * 8 + N - 1) / N;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, N);
+  const bool relu = act == ACT_RELU;
+#define PCRL_LAUNCH_BWD(POOLV, APPLYV, SMEM)                                              \
+  do {                                                                                    \
+    if (relu) norm_act_bwd_kernel<POOLV, APPLYV, ACT_RELU><<<grid, 256, SMEM, s>>>(p);    \
+    else norm_act_bwd_kernel<POOLV, APPLYV, -1><<<grid, 256, SMEM, s>>>(p);               \
+  } while (0)
   if (pass == 0) {
-    const size_t smem = (size_t)block * 24 * 4;
-    if (pool) norm_act_bwd_kernel<true, false><<<grid, block, smem, s>>>(p);
-    else norm_act_bwd_kernel<false, false><<<grid, block, smem, s>>>(p);
+    const size_t smem = (size_t)256 * 24 * 4;
+    if (pool) PCRL_LAUNCH_BWD(true, false, smem);
+    else PCRL_LAUNCH_BWD(false, false, smem);
   } else {
-    if (pool) norm_act_bwd_kernel<true, true><<<grid, block, 0, s>>>(p);
-    else norm_act_bwd_kernel<false, true><<<grid, block, 0, s>>>(p);
+    if (pool) PCRL_LAUNCH_BWD(true, true, 0);
+    else PCRL_LAUNCH_BWD(false, true, 0);
   }
+#undef PCRL_LAUNCH_BWD
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
