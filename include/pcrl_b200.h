@@ -104,18 +104,33 @@ int pcrl_norm_act_bwd(const void* y, const void* g1, const void* g2, const float
 int pcrl_zero_pad_rows(void* t, long long planes, int H1, int row_elems, void* stream);
 
 /* ---- single-channel heads ------------------------------------------------------------------ */
-/* y1 = Conv3d(C->1,k3,p1)(a) + b3 (deep_supervision_head.conv1, :60); optionally also
- * y0 = Conv3d(C->1,k1)(a) + b1 (out_tr.final_conv, :78).  w3 is [27][C] fp32 (tap-major). */
-int pcrl_head_fwd(const void* a, const float* w3, const float* b3, const float* w1,
-                  const float* b1, float* y1, float* y0, int N, int D, int H, int W, int C,
-                  void* stream);
-int pcrl_head_bwd_data(const float* dy1, const float* w3, const float* dy0, const float* w1,
-                       void* da, int N, int D, int H, int W, int C, void* stream);
-int pcrl_head_bwd_weight(const void* a, const float* dy1, const float* dy0, float* dw3,
-                         float* dw1, int N, int D, int H, int W, int C, void* stream);
+/* The N=1 convolutions Conv3d(C->1,k3,p1) (deep_supervision_head.conv1, :60) and Conv3d(64->1,k1)
+ * (out_tr.final_conv, :78) are factored as  T = A * Wext^T  (pcrl_gemm_nt, 32 columns: 27 taps,
+ * the 1x1x1 conv, 4 zeros) followed by a 27-point gather; backward is the mirror image.
+ * w3 (1,C,3,3,3), w1 (1,C,1,1,1) or NULL -> wext [32][C] bf16, wextT [C][32] bf16. */
+int pcrl_head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C,
+                           void* stream);
+/* tT [32][rows] fp32 (rows = N*D*(H+1)*W) -> y1 (+ y0) [N][D][H][W] fp32; stats [G][2] fp64 +=
+ * (sum, sum of squares) of y1 for the 1-channel norm that follows. */
+int pcrl_head_gather(const float* tT, const float* b3, const float* b1, float* y1, float* y0,
+                     double* stats, int stats_per_sample, int N, int D, int H, int W, void* stream);
+/* dT [rows][32] bf16: dT[u][tap] = dy1[u - tap], dT[u][27] = dy0[u] (dy0 may be NULL). */
+int pcrl_head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W,
+                      void* stream);
+/* BatchNorm3d(1)/InstanceNorm3d(1) + Sigmoid of the head (:12,27) on fp32 [G][vol]. */
+int pcrl_chan1_sigmoid_fwd(const float* y, const float* scale, const float* shift, float* mask,
+                           int per_sample, int G, long long vol, void* stream);
+int pcrl_chan1_sigmoid_bwd(const float* y, const float* mask, const float* dmask, const float* mean,
+                           const float* invstd, const float* gamma, double* sums, float* dy,
+                           double count, int per_sample, int pass, int G, long long vol,
+                           void* stream);
+/* x [N][D][H][W] fp32 -> X27 [rows][32] bf16, X27[u][tap] = x[u + tap]: im2col of the 1-channel
+ * network input; the stem weight gradient is then pcrl_gemm_tn(dY, X27). */
+int pcrl_im2col27(const float* x, void* out, int N, int D, int H, int W, void* stream);
 
 /* ---- plain tensor-core GEMMs (bf16 in, fp32 accumulate) ------------------------------------ */
-/* C[rows][cols] = A[rows][K] * B[cols][K]^T (+ bias[col]); ldc in elements. */
+/* C[rows][cols] = A[rows][K] * B[cols][K]^T (+ bias[col]); ldc in elements.  out_fp32: 0 = bf16,
+ * 1 = fp32, 2 = fp32 transposed (C^T[cols][rows], ldc = rows). */
 int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
                  int cols, int ldc, int out_fp32, void* stream);
 /* C[P][Q] (fp32) += A[rows][P]^T * B[rows][Q] */

@@ -39,9 +39,12 @@ SIGNATURES = {
     "pcrl_norm_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I,
                           _I, _I, _I, _I, _I, _P],
     "pcrl_zero_pad_rows": [_P, _L, _I, _I, _P],
-    "pcrl_head_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "pcrl_head_bwd_data": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "pcrl_head_bwd_weight": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_head_pack_weights": [_P, _P, _P, _P, _I, _P],
+    "pcrl_head_gather": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_head_scatter": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "pcrl_chan1_sigmoid_fwd": [_P, _P, _P, _P, _I, _I, _L, _P],
+    "pcrl_chan1_sigmoid_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _L, _P],
+    "pcrl_im2col27": [_P, _P, _I, _I, _I, _I, _P],
     "pcrl_gemm_nt": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "pcrl_gemm_tn": [_P, _P, _P, _L, _I, _I, _P],
     "pcrl_sgd_flat": [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _P],

@@ -37,9 +37,12 @@ int norm_act_fwd(const void*, const float*, const float*, const float*, void*, v
 int norm_act_bwd(const void*, const void*, const void*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, double*, void*, double, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int zero_pad_rows(void*, long long, int, int, cudaStream_t);
 int convT_unshuffle(const void*, void*, float*, int, int, int, int, int, cudaStream_t);
-int head_fwd(const void*, const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
-int head_bwd_data(const float*, const float*, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
-int head_bwd_weight(const void*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+int head_pack_weights(const float*, const float*, void*, void*, int, cudaStream_t);
+int head_gather(const float*, const float*, const float*, float*, float*, double*, int, int, int, int, int, cudaStream_t);
+int head_scatter(const float*, const float*, void*, int, int, int, int, cudaStream_t);
+int im2col27(const float*, void*, int, int, int, int, cudaStream_t);
+int chan1_sigmoid_fwd(const float*, const float*, const float*, float*, int, int, long long, cudaStream_t);
+int chan1_sigmoid_bwd(const float*, const float*, const float*, const float*, const float*, const float*, double*, float*, double, int, int, int, long long, cudaStream_t);
 int sgd_flat(float*, const float*, float*, const long long*, const int*, const int*, int, float, float, float, float, cudaStream_t);
 
 }  // namespace pcrl
@@ -159,26 +162,41 @@ int pcrl_zero_pad_rows(void* t, long long planes, int H1, int row_elems, void* s
   return zero_pad_rows(t, planes, H1, row_elems, ST(stream));
 }
 
-int pcrl_head_fwd(const void* a, const float* w3, const float* b3, const float* w1, const float* b1,
-                  float* y1, float* y0, int N, int D, int H, int W, int C, void* stream) {
-  NONNULL(a); NONNULL(w3); NONNULL(b3); NONNULL(y1);
-  return head_fwd(a, w3, b3, w1, b1, y1, y0, N, D, H, W, C, ST(stream));
+int pcrl_head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C, void* stream) {
+  NONNULL(w3); NONNULL(wext); NONNULL(wextT);
+  return head_pack_weights(w3, w1, wext, wextT, C, ST(stream));
 }
-int pcrl_head_bwd_data(const float* dy1, const float* w3, const float* dy0, const float* w1, void* da,
-                       int N, int D, int H, int W, int C, void* stream) {
-  NONNULL(dy1); NONNULL(w3); NONNULL(da);
-  return head_bwd_data(dy1, w3, dy0, w1, da, N, D, H, W, C, ST(stream));
+int pcrl_head_gather(const float* tT, const float* b3, const float* b1, float* y1, float* y0, double* stats,
+                     int stats_per_sample, int N, int D, int H, int W, void* stream) {
+  NONNULL(tT); NONNULL(b3); NONNULL(y1);
+  return head_gather(tT, b3, b1, y1, y0, stats, stats_per_sample, N, D, H, W, ST(stream));
 }
-int pcrl_head_bwd_weight(const void* a, const float* dy1, const float* dy0, float* dw3, float* dw1,
-                         int N, int D, int H, int W, int C, void* stream) {
-  NONNULL(a); NONNULL(dy1); NONNULL(dw3);
-  return head_bwd_weight(a, dy1, dy0, dw3, dw1, N, D, H, W, C, ST(stream));
+int pcrl_head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W, void* stream) {
+  NONNULL(dy1); NONNULL(dT);
+  return head_scatter(dy1, dy0, dT, N, D, H, W, ST(stream));
+}
+int pcrl_chan1_sigmoid_fwd(const float* y, const float* scale, const float* shift, float* mask, int per_sample,
+                           int G, long long vol, void* stream) {
+  NONNULL(y); NONNULL(scale); NONNULL(shift); NONNULL(mask);
+  return chan1_sigmoid_fwd(y, scale, shift, mask, per_sample, G, vol, ST(stream));
+}
+int pcrl_chan1_sigmoid_bwd(const float* y, const float* mask, const float* dmask, const float* mean,
+                           const float* invstd, const float* gamma, double* sums, float* dy, double count,
+                           int per_sample, int pass, int G, long long vol, void* stream) {
+  NONNULL(y); NONNULL(mask); NONNULL(dmask); NONNULL(mean); NONNULL(invstd); NONNULL(sums);
+  if (pass == 1) { NONNULL(dy); NONNULL(gamma); }
+  return chan1_sigmoid_bwd(y, mask, dmask, mean, invstd, gamma, sums, dy, count, per_sample, pass, G, vol, ST(stream));
+}
+int pcrl_im2col27(const float* x, void* out, int N, int D, int H, int W, void* stream) {
+  NONNULL(x); NONNULL(out);
+  return im2col27(x, out, N, D, H, W, ST(stream));
 }
 
 int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
                  int cols, int ldc, int out_fp32, void* stream) {
   NONNULL(a); NONNULL(b); NONNULL(c);
-  return gemm_nt_igemm(a, b, c, bias, rows, K, cols, ldc, out_fp32, /*OUT_ROWS*/ 1, 0, 0, 0, 0, ST(stream));
+  return gemm_nt_igemm(a, b, c, bias, rows, K, cols, ldc, out_fp32 != 0, out_fp32 == 2 ? /*OUT_ROWS_T*/ 3 : /*OUT_ROWS*/ 1,
+                       0, 0, 0, 0, ST(stream));
 }
 int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, void* stream) {
   NONNULL(a); NONNULL(b); NONNULL(c);

@@ -1,57 +1,53 @@
-// Single-output-channel heads of the decoder and the fused SGD step.
+// Single-output-channel heads of the decoder, the 1-channel mask normalisation, the stem
+// weight-gradient staging and the fused SGD step.
 //
 //   deep-supervision head conv : Conv3d(C -> 1, k=3, p=1)   (models/pcrlv2_model_3d.py:60,71)
 //   output transition          : Conv3d(64 -> 1, k=1)        (models/pcrlv2_model_3d.py:78)
+//   BatchNorm3d(1) / InstanceNorm3d(1) + Sigmoid of the head (models/pcrlv2_model_3d.py:12,27)
 //   torch.optim.SGD(momentum, weight_decay)                  (train_3d.py:48-51,151)
 //
-// The head convolutions are GEMV-shaped (N = 1) and HBM/L2-bound: SIMT kernels, 8 channels
-// (16 bytes) per thread, shuffle reduction over the channel groups of a voxel.  Inputs are
-// H-padded NDHWC bf16 activations; the 1-channel outputs are plain fp32 [N][D][H][W].
+// The N=1 convolutions are factored so that the channel contraction runs on the tensor cores:
+//   T[u][tap] = sum_c a[u][c] * w[tap][c]        plain GEMM  [rows x C] x [C x 32]   (27 taps, the
+//                                                 1x1x1 output conv as column 27, 4 zero columns)
+//   y1[v]     = b + sum_tap T[v + tap][tap]      27-point gather on the 32-column fp32 tensor T
+// and the same in reverse for the backward pass (scatter dy1 into dT[u][tap] = dy1[u - tap], then
+// dA = dT * W and dW = dT^T * A as GEMMs).  Only the gather / scatter are SIMT kernels; they touch
+// 128 bytes per voxel instead of 27 * C * 2.
 #include "common.cuh"
 
 namespace pcrl {
 
-__device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return u;
+// w3 (1,C,3,3,3) fp32 [+ w1 (1,C,1,1,1)] -> wext [32][C] bf16 (rows = taps, row 27 = w1) and
+// wextT [C][32] bf16
+__global__ void head_pack_kernel(const float* __restrict__ w3, const float* __restrict__ w1,
+                                 __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ wextT, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * C) return;
+  const int tap = i / C, c = i % C;
+  float v = 0.f;
+  if (tap < 27) v = w3[c * 27 + tap];
+  else if (tap == 27 && w1) v = w1[c];
+  const __nv_bfloat16 b = __float2bfloat16(v);
+  wext[tap * C + c] = b;
+  wextT[c * 32 + tap] = b;
 }
 
-// y1[v] = b3 + sum_tap sum_c a[v+tap][c] * w3[tap][c];   y0[v] = b1 + sum_c a[v][c] * w1[c] (optional)
-// w3 is [27][C] fp32 (tap-major), w1 is [C].
+// tT [32][rows] fp32 (rows = N*D*(H+1)*W, H-padded order) -> y1 [N][D][H][W] (+ y0), and the
+// per-group sum / sum of squares of y1 for the 1-channel normalisation (stats [G][2] fp64).
 __global__ void __launch_bounds__(256)
-head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w3, const float* __restrict__ b3,
-                const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ y1,
-                float* __restrict__ y0, int N, int D, int H, int W, int C) {
-  extern __shared__ float ws[];  // [27][C] (+ [C])
-  const int C8 = C >> 3;
-  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) ws[i] = w3[i];
-  if (w1) for (int i = threadIdx.x; i < C; i += blockDim.x) ws[27 * C + i] = w1[i];
-  __syncthreads();
-  const long long total = (long long)N * D * H * W * C8;
-  const int c8 = threadIdx.x % C8;
-  // block-uniform loop bound: every lane takes part in the shuffles, tail lanes are clamped
-  for (long long base = (long long)blockIdx.x * blockDim.x; base < total;
-       base += (long long)gridDim.x * blockDim.x) {
-    const long long it = base + threadIdx.x;
-    const bool live = it < total;
-    const long long v = (live ? it : total - 1) / C8;
-    const int wq = (int)(v % W);
-    const int h = (int)((v / W) % H);
-    const int d = (int)((v / ((long long)W * H)) % D);
-    const long long n = v / ((long long)W * H * D);
-    float acc = 0.f, acc0 = 0.f;
+head_gather_kernel(const float* __restrict__ tT, const float* __restrict__ b3, const float* __restrict__ b1,
+                   float* __restrict__ y1, float* __restrict__ y0, double* __restrict__ stats,
+                   int stats_per_sample, long long rows, int N, int D, int H, int W) {
+  __shared__ float red[2][8];
+  const int n = blockIdx.y;
+  const int vol = D * H * W;
+  const float bias3 = b3[0], bias1 = b1 ? b1[0] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < vol; v += gridDim.x * blockDim.x) {
+    const int w = v % W;
+    const int h = (v / W) % H;
+    const int d = v / (W * H);
+    float acc = bias3;
 #pragma unroll
     for (int kz = 0; kz < 3; kz++) {
       const int zz = d + kz - 1;
@@ -62,153 +58,196 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w
         if (yy < 0 || yy >= H) continue;
 #pragma unroll
         for (int kx = 0; kx < 3; kx++) {
-          const int xx = wq + kx - 1;
+          const int xx = w + kx - 1;
           if (xx < 0 || xx >= W) continue;
-          float f[8];
-          unpack8h(*reinterpret_cast<const uint4*>(
-                       a + ((((size_t)n * D + zz) * (H + 1) + yy + 1) * W + xx) * C + c8 * 8), f);
-          const float* wt = ws + ((kz * 3 + ky) * 3 + kx) * C + c8 * 8;
-#pragma unroll
-          for (int q = 0; q < 8; q++) acc = fmaf(f[q], wt[q], acc);
-          if (w1 && kz == 1 && ky == 1 && kx == 1) {
-            const float* w1s = ws + 27 * C + c8 * 8;
-#pragma unroll
-            for (int q = 0; q < 8; q++) acc0 = fmaf(f[q], w1s[q], acc0);
-          }
+          const long long r = (((long long)n * D + zz) * (H + 1) + yy + 1) * W + xx;
+          acc += __ldg(&tT[(size_t)((kz * 3 + ky) * 3 + kx) * rows + r]);
         }
       }
     }
-    for (int s = C8 >> 1; s >= 1; s >>= 1) {
-      acc += __shfl_xor_sync(0xffffffffu, acc, s);
-      acc0 += __shfl_xor_sync(0xffffffffu, acc0, s);
+    y1[(size_t)n * vol + v] = acc;
+    if (y0) {
+      const long long r = (((long long)n * D + d) * (H + 1) + h + 1) * W + w;
+      y0[(size_t)n * vol + v] = __ldg(&tT[(size_t)27 * rows + r]) + bias1;
     }
-    if (c8 == 0 && live) {
-      y1[v] = acc + b3[0];
-      if (w1) y0[v] = acc0 + b1[0];
+    s1 += acc;
+    s2 += acc * acc;
+  }
+  if (stats) {
+    for (int o = 16; o >= 1; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float t = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[threadIdx.x][i];
+      atomicAdd(&stats[(stats_per_sample ? (size_t)n * 2 : 0) + threadIdx.x], (double)t);
     }
   }
 }
 
-// da[v][c] = sum_tap dy1[v - tap] * w3[tap][c]  (+ dy0[v] * w1[c]);  H-padded bf16 output
+// dT [rows][32] bf16: dT[u][tap] = dy1[u - tap] (0 outside / on pad rows), dT[u][27] = dy0[u]
 __global__ void __launch_bounds__(256)
-head_bwd_data_kernel(const float* __restrict__ dy1, const float* __restrict__ w3,
-                     const float* __restrict__ dy0, const float* __restrict__ w1,
-                     __nv_bfloat16* __restrict__ da, int N, int D, int H, int W, int C) {
-  extern __shared__ float ws[];
-  const int C8 = C >> 3;
-  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) ws[i] = w3[i];
-  if (w1) for (int i = threadIdx.x; i < C; i += blockDim.x) ws[27 * C + i] = w1[i];
-  __syncthreads();
-  const long long total = (long long)N * D * (H + 1) * W * C8;
-  const int c8 = threadIdx.x % C8;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const long long slot = it / C8;
-    const int wq = (int)(slot % W);
-    const int hp = (int)((slot / W) % (H + 1));
-    const int d = (int)((slot / ((long long)W * (H + 1))) % D);
-    const long long n = slot / ((long long)W * (H + 1) * D);
-    float out[8];
+head_scatter_kernel(const float* __restrict__ dy1, const float* __restrict__ dy0,
+                    __nv_bfloat16* __restrict__ dT, int N, int D, int H, int W) {
+  const long long rows = (long long)N * D * (H + 1) * W;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(r % W);
+    const int hp = (int)((r / W) % (H + 1));
+    const int d = (int)((r / ((long long)W * (H + 1))) % D);
+    const long long n = r / ((long long)W * (H + 1) * D);
+    float v[32];
 #pragma unroll
-    for (int q = 0; q < 8; q++) out[q] = 0.f;
+    for (int i = 0; i < 32; i++) v[i] = 0.f;
     if (hp >= 1) {
       const int h = hp - 1;
       const float* g = dy1 + (size_t)n * D * H * W;
 #pragma unroll
       for (int kz = 0; kz < 3; kz++) {
         const int zz = d - (kz - 1);
-        if (zz < 0 || zz >= D) continue;
 #pragma unroll
         for (int ky = 0; ky < 3; ky++) {
           const int yy = h - (ky - 1);
-          if (yy < 0 || yy >= H) continue;
 #pragma unroll
           for (int kx = 0; kx < 3; kx++) {
-            const int xx = wq - (kx - 1);
-            if (xx < 0 || xx >= W) continue;
-            const float gv = __ldg(&g[((size_t)zz * H + yy) * W + xx]);
-            const float* wt = ws + ((kz * 3 + ky) * 3 + kx) * C + c8 * 8;
-#pragma unroll
-            for (int q = 0; q < 8; q++) out[q] = fmaf(gv, wt[q], out[q]);
+            const int xx = w - (kx - 1);
+            const bool in = zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
+            v[(kz * 3 + ky) * 3 + kx] = in ? __ldg(&g[((size_t)zz * H + yy) * W + xx]) : 0.f;
           }
         }
       }
-      if (w1) {
-        const float g0 = __ldg(&dy0[(((size_t)n * D + d) * H + h) * W + wq]);
-        const float* w1s = ws + 27 * C + c8 * 8;
-#pragma unroll
-        for (int q = 0; q < 8; q++) out[q] = fmaf(g0, w1s[q], out[q]);
-      }
+      if (dy0) v[27] = __ldg(&dy0[(((size_t)n * D + d) * H + h) * W + w]);
     }
-    *reinterpret_cast<uint4*>(da + (size_t)slot * C + c8 * 8) = pack8h(out);
+    uint4* o = reinterpret_cast<uint4*>(dT + (size_t)r * 32);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint4 u;
+      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; j++) hh[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+      o[i] = u;
+    }
   }
 }
 
-// dw3[tap][c] += sum_u a[u][c] * dy1[u - tap];  dw1[c] += sum_u a[u][c] * dy0[u];
-// thread = (voxel run, channel group, dz plane of taps): 9 x 8 accumulators.
+// x [N][D][H][W] fp32 (C = 1) -> X27 [rows][32] bf16 in H-padded row order:
+// X27[u][tap] = x[u + tap] (0 outside, pad rows all zero).  Feeds the stem weight gradient GEMM.
 __global__ void __launch_bounds__(256)
-head_bwd_weight_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ dy1,
-                       const float* __restrict__ dy0, float* __restrict__ dw3, float* __restrict__ dw1,
-                       int N, int D, int H, int W, int C, int vox_per_thread) {
-  extern __shared__ float red[];  // [27][C] + [C]
-  const int C8 = C >> 3;
-  for (int i = threadIdx.x; i < 28 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  const int c8 = threadIdx.x % C8;
-  const int kz = (threadIdx.x / C8) % 3;
-  const int sub = threadIdx.x / (3 * C8);           // voxel lane inside the block
-  const int lanes = blockDim.x / (3 * C8);
-  const long long total = (long long)N * D * H * W;
-  float acc[9][8], acc1[8];
+im2col27_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int D, int H, int W) {
+  const long long rows = (long long)N * D * (H + 1) * W;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(r % W);
+    const int hp = (int)((r / W) % (H + 1));
+    const int d = (int)((r / ((long long)W * (H + 1))) % D);
+    const long long n = r / ((long long)W * (H + 1) * D);
+    float v[32];
 #pragma unroll
-  for (int t = 0; t < 9; t++)
+    for (int i = 0; i < 32; i++) v[i] = 0.f;
+    if (hp >= 1) {
+      const int h = hp - 1;
+      const float* g = x + (size_t)n * D * H * W;
 #pragma unroll
-    for (int q = 0; q < 8; q++) acc[t][q] = 0.f;
-#pragma unroll
-  for (int q = 0; q < 8; q++) acc1[q] = 0.f;
-  if (sub < lanes) {
-    const long long base = ((long long)blockIdx.x * lanes + sub) * vox_per_thread;
-    for (long long u = base; u < base + vox_per_thread && u < total; u++) {
-      const int wq = (int)(u % W);
-      const int h = (int)((u / W) % H);
-      const int d = (int)((u / ((long long)W * H)) % D);
-      const long long n = u / ((long long)W * H * D);
-      float f[8];
-      unpack8h(*reinterpret_cast<const uint4*>(
-                   a + ((((size_t)n * D + d) * (H + 1) + h + 1) * W + wq) * C + c8 * 8), f);
-      const float* g = dy1 + (size_t)n * D * H * W;
-      const int zz = d - (kz - 1);
-      if (zz >= 0 && zz < D) {
+      for (int kz = 0; kz < 3; kz++) {
+        const int zz = d + kz - 1;
 #pragma unroll
         for (int ky = 0; ky < 3; ky++) {
-          const int yy = h - (ky - 1);
+          const int yy = h + ky - 1;
 #pragma unroll
           for (int kx = 0; kx < 3; kx++) {
-            const int xx = wq - (kx - 1);
-            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-            const float gv = in ? __ldg(&g[((size_t)zz * H + yy) * W + xx]) : 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; q++) acc[ky * 3 + kx][q] = fmaf(gv, f[q], acc[ky * 3 + kx][q]);
+            const int xx = w + kx - 1;
+            const bool in = zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
+            v[(kz * 3 + ky) * 3 + kx] = in ? __ldg(&g[((size_t)zz * H + yy) * W + xx]) : 0.f;
           }
         }
       }
-      if (dy0 && kz == 1) {
-        const float g0 = __ldg(&dy0[(((size_t)n * D + d) * H + h) * W + wq]);
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc1[q] = fmaf(g0, f[q], acc1[q]);
-      }
     }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)r * 32);
 #pragma unroll
-    for (int t = 0; t < 9; t++)
+    for (int i = 0; i < 4; i++) {
+      uint4 u;
+      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-      for (int q = 0; q < 8; q++) atomicAdd(&red[(kz * 9 + t) * C + c8 * 8 + q], acc[t][q]);
-    if (dy0 && kz == 1)
-#pragma unroll
-      for (int q = 0; q < 8; q++) atomicAdd(&red[27 * C + c8 * 8 + q], acc1[q]);
+      for (int j = 0; j < 4; j++) hh[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+      o[i] = u;
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) atomicAdd(&dw3[i], red[i]);
-  if (dy0) for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dw1[i], red[27 * C + i]);
+}
+
+// ------------------------------------------------------------------------------ 1-channel norm + sigmoid
+// mask = sigmoid(y*scale + shift) on fp32 [G][vol] (G groups share nothing: scale/shift per group)
+__global__ void __launch_bounds__(256)
+chan1_sigmoid_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                         const float* __restrict__ shift, float* __restrict__ mask, int per_sample,
+                         long long vol) {
+  const int n = blockIdx.y;
+  const float sc = scale[per_sample ? n : 0], sh = shift[per_sample ? n : 0];
+  const float* yy = y + (size_t)n * vol;
+  float* mm = mask + (size_t)n * vol;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < vol;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(yy + i);
+    float4 o;
+    o.x = 1.f / (1.f + __expf(-fmaf(v.x, sc, sh)));
+    o.y = 1.f / (1.f + __expf(-fmaf(v.y, sc, sh)));
+    o.z = 1.f / (1.f + __expf(-fmaf(v.z, sc, sh)));
+    o.w = 1.f / (1.f + __expf(-fmaf(v.w, sc, sh)));
+    *reinterpret_cast<float4*>(mm + i) = o;
+  }
+}
+
+// backward of mask = sigmoid(norm(y)): pass 0 accumulates sums[g][3] = (sum dz, sum dz*xhat, 0),
+// pass 1 writes dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); dz = dmask*mask*(1-mask)
+__global__ void __launch_bounds__(256)
+chan1_sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ mask,
+                         const float* __restrict__ dmask, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                         double* __restrict__ sums, float* __restrict__ dy, double count,
+                         int per_sample, int pass, long long vol) {
+  __shared__ float red[2][8];
+  const int n = blockIdx.y;
+  const int g = per_sample ? n : 0;
+  const float mu = mean[g], is = invstd[g];
+  float k1 = 0.f, k2 = 0.f, gs = 0.f;
+  if (pass == 1) {
+    k1 = (float)(sums[(size_t)g * 3 + 0] / count);
+    k2 = (float)(sums[(size_t)g * 3 + 1] / count);
+    gs = gamma[0] * is;
+  }
+  float s0 = 0.f, s1 = 0.f;
+  const size_t base = (size_t)n * vol;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < vol;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    const float4 yv = *reinterpret_cast<const float4*>(y + base + i);
+    const float4 mv = *reinterpret_cast<const float4*>(mask + base + i);
+    const float4 gv = *reinterpret_cast<const float4*>(dmask + base + i);
+    const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+    float out[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float dz = ga[q] * ma[q] * (1.f - ma[q]);
+      const float xh = (ya[q] - mu) * is;
+      if (pass == 0) { s0 += dz; s1 += dz * xh; }
+      else out[q] = gs * (dz - k1 - xh * k2);
+    }
+    if (pass == 1) *reinterpret_cast<float4*>(dy + base + i) = make_float4(out[0], out[1], out[2], out[3]);
+  }
+  if (pass == 0) {
+    for (int o = 16; o >= 1; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float t = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[threadIdx.x][i];
+      atomicAdd(&sums[(size_t)g * 3 + threadIdx.x], (double)t);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------ fused SGD
@@ -238,46 +277,53 @@ sgd_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
 }
 
 // ------------------------------------------------------------------------------ wrappers
-int head_fwd(const void* a, const float* w3, const float* b3, const float* w1, const float* b1,
-             float* y1, float* y0, int N, int D, int H, int W, int C, cudaStream_t s) {
-  PCRL_REQUIRE(C % 8 == 0 && C / 8 <= 32 && ((C / 8) & (C / 8 - 1)) == 0,
-               "head_fwd: C=%d must be 8 * a power of two <= 256", C);
-  const int C8 = C / 8;
-  const long long total = (long long)N * D * H * W * C8;
-  long long blocks = (total + 255) / 256;
-  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  const size_t smem = (size_t)28 * C * 4;
-  head_fwd_kernel<<<(unsigned)blocks, 256, smem, s>>>((const __nv_bfloat16*)a, w3, b3, w1, b1, y1, y0, N, D, H, W, C);
+static inline unsigned blocks_for(long long items, int per_block, int cap) {
+  long long b = (items + per_block - 1) / per_block;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C, cudaStream_t s) {
+  head_pack_kernel<<<(32 * C + 255) / 256, 256, 0, s>>>(w3, w1, (__nv_bfloat16*)wext, (__nv_bfloat16*)wextT, C);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
-int head_bwd_data(const float* dy1, const float* w3, const float* dy0, const float* w1, void* da,
-                  int N, int D, int H, int W, int C, cudaStream_t s) {
-  PCRL_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "head_bwd_data: unsupported C=%d", C);
-  const int C8 = C / 8;
-  const long long total = (long long)N * D * (H + 1) * W * C8;
-  long long blocks = (total + 255) / 256;
-  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  head_bwd_data_kernel<<<(unsigned)blocks, 256, (size_t)28 * C * 4, s>>>(dy1, w3, dy0, w1, (__nv_bfloat16*)da, N, D, H, W, C);
+int head_gather(const float* tT, const float* b3, const float* b1, float* y1, float* y0, double* stats,
+                int stats_per_sample, int N, int D, int H, int W, cudaStream_t s) {
+  const long long rows = (long long)N * D * (H + 1) * W;
+  const int vol = D * H * W;
+  dim3 grid(blocks_for(vol, 256, (num_sms() * 8 + N - 1) / N), N);
+  head_gather_kernel<<<grid, 256, 0, s>>>(tT, b3, b1, y1, y0, stats, stats_per_sample, rows, N, D, H, W);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
-int head_bwd_weight(const void* a, const float* dy1, const float* dy0, float* dw3, float* dw1,
-                    int N, int D, int H, int W, int C, cudaStream_t s) {
-  PCRL_REQUIRE(C % 8 == 0 && 3 * (C / 8) <= 256, "head_bwd_weight: unsupported C=%d", C);
-  const int C8 = C / 8;
-  const int lanes = 256 / (3 * C8);
-  const long long total = (long long)N * D * H * W;
-  const long long threads_target = (long long)num_sms() * 8 * lanes;
-  int vpt = (int)((total + threads_target - 1) / threads_target);
-  if (vpt < 1) vpt = 1;
-  const long long blocks = (total + (long long)lanes * vpt - 1) / ((long long)lanes * vpt);
-  static bool configured = false;
-  if (!configured) {
-    PCRL_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = true;
-  }
-  head_bwd_weight_kernel<<<(unsigned)blocks, 256, (size_t)28 * C * 4, s>>>((const __nv_bfloat16*)a, dy1, dy0, dw3, dw1, N, D, H, W, C, vpt);
+int head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W, cudaStream_t s) {
+  const long long rows = (long long)N * D * (H + 1) * W;
+  head_scatter_kernel<<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(dy1, dy0, (__nv_bfloat16*)dT, N, D, H, W);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+int im2col27(const float* x, void* out, int N, int D, int H, int W, cudaStream_t s) {
+  const long long rows = (long long)N * D * (H + 1) * W;
+  im2col27_kernel<<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(x, (__nv_bfloat16*)out, N, D, H, W);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+int chan1_sigmoid_fwd(const float* y, const float* scale, const float* shift, float* mask, int per_sample,
+                      int G, long long vol, cudaStream_t s) {
+  PCRL_REQUIRE(vol % 4 == 0, "chan1_sigmoid_fwd: vol=%lld must be a multiple of 4", vol);
+  dim3 grid(blocks_for(vol / 4, 256, (num_sms() * 8 + G - 1) / G), G);
+  chan1_sigmoid_fwd_kernel<<<grid, 256, 0, s>>>(y, scale, shift, mask, per_sample, vol);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+int chan1_sigmoid_bwd(const float* y, const float* mask, const float* dmask, const float* mean,
+                      const float* invstd, const float* gamma, double* sums, float* dy, double count,
+                      int per_sample, int pass, int G, long long vol, cudaStream_t s) {
+  PCRL_REQUIRE(vol % 4 == 0, "chan1_sigmoid_bwd: vol=%lld must be a multiple of 4", vol);
+  dim3 grid(blocks_for(vol / 4, 256, (num_sms() * 8 + G - 1) / G), G);
+  chan1_sigmoid_bwd_kernel<<<grid, 256, 0, s>>>(y, mask, dmask, mean, invstd, gamma, sums, dy, count, per_sample, pass, vol);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

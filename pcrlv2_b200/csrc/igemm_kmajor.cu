@@ -29,7 +29,7 @@
 namespace pcrl {
 
 enum { IG_CONV = 0, IG_PLAIN = 1 };
-enum { OUT_FLAT = 0, OUT_ROWS = 1, OUT_CONVT = 2 };
+enum { OUT_FLAT = 0, OUT_ROWS = 1, OUT_CONVT = 2, OUT_ROWS_T = 3 };
 
 struct IgemmParams {
   int mode;
@@ -274,6 +274,11 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
             const long long r = (long long)tc.f0 + lrow;
             valid = r < p.rows_total;
             off = r * p.ldc + co0;
+          } else if (p.out_mode == OUT_ROWS_T) {
+            // transposed fp32 store out[col][row]: lanes hold consecutive rows -> coalesced
+            const long long r = (long long)tc.f0 + lrow;
+            valid = r < p.rows_total;
+            off = r;
           } else {
             // coarse H-padded row r = ((n*D + d)*(H+1) + h')*W + w  ->  fine voxel (2d+i, 2h+j, 2w+k)
             const long long r = (long long)tc.f0 + lrow;
@@ -299,7 +304,13 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
 #pragma unroll
               for (int i = 0; i < 32; i++) y[i] += __ldg(&p.bias[co0 + c + i]);
             }
-            if (p.out_fp32) {
+            if (p.out_mode == OUT_ROWS_T) {
+              if (valid) {
+                float* o = reinterpret_cast<float*>(p.out) + off;
+#pragma unroll
+                for (int i = 0; i < 32; i++) o[(size_t)(co0 + c + i) * p.ldc] = y[i];
+              }
+            } else if (p.out_fp32) {
               if (valid) {
                 float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c);
 #pragma unroll
@@ -490,14 +501,14 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
 int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
                   int cols, int ldc, int out_fp32, int out_mode, int ct_D, int ct_H, int ct_W,
                   int ct_cout, cudaStream_t stream) {
-  PCRL_REQUIRE(K % 64 == 0, "gemm_nt: K=%d must be a multiple of 64", K);
+  PCRL_REQUIRE(K % 64 == 0 || K == 32, "gemm_nt: K=%d must be 32 or a multiple of 64", K);
   PCRL_REQUIRE(cols % 32 == 0, "gemm_nt: cols=%d must be a multiple of 32", cols);
   PCRL_REQUIRE(rows < (1LL << 31), "gemm_nt: too many rows");
   IgemmLaunch L;
   memset(&L.p, 0, sizeof(L.p));
   IgemmParams& p = L.p;
   p.mode = IG_PLAIN;
-  p.kc = 64; p.row_bytes = 128; p.kblocks = K / 64; p.tpg = 1; p.P = 1;
+  p.kc = (K == 32) ? 32 : 64; p.row_bytes = p.kc * 2; p.kblocks = K / p.kc; p.tpg = 1; p.P = 1;
   p.nc = (cols % 128 == 0) ? 128 : (cols % 64 == 0 ? 64 : 32);
   if (out_mode == OUT_CONVT) {
     PCRL_REQUIRE(ct_cout % p.nc == 0, "convT: Cout=%d must be a multiple of %d", ct_cout, p.nc);
@@ -516,9 +527,9 @@ int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long
   p.has_bias = bias != nullptr; p.bias = bias; p.out = c;
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
   uint64_t str[1] = {(uint64_t)K * 2};
-  uint32_t box[2] = {64, 128};
+  uint32_t box[2] = {(uint32_t)p.kc, 128};
   int rc = encode_map(&L.ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, dims, str, box,
-                      CU_TENSOR_MAP_SWIZZLE_128B);
+                      p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   rc = make_b_maps(L, b, K, cols, 1);
   if (rc) return rc;

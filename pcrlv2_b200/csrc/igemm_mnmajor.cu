@@ -268,7 +268,7 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
 // dW[P][Q] (fp32, leading dimension Q) += A[rows][P]^T * B[rows][Q]; A, B bf16 row-major.
 int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P, int Q,
                   cudaStream_t stream) {
-  PCRL_REQUIRE(P % 64 == 0 && Q % 64 == 0, "gemm_tn: P=%d, Q=%d must be multiples of 64", P, Q);
+  PCRL_REQUIRE(P % 64 == 0 && (Q % 64 == 0 || Q == 32), "gemm_tn: P=%d (multiple of 64), Q=%d (32 or multiple of 64)", P, Q);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.mode = WG_PLAIN;
@@ -276,10 +276,10 @@ int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P
   p.total_stages = (int)((rows + 127) / 128);
   p.stages_per_sample = p.total_stages;
   p.mc = (P % 128 == 0) ? 128 : 64;
-  p.nc = (Q % 128 == 0) ? 128 : 64;
-  p.a_row_bytes = 128; p.b_row_bytes = 128;
-  p.a_chunks = p.mc / 64; p.b_chunks = p.nc / 64;
-  p.a_chunk_bytes = 128 * 128; p.b_chunk_bytes = 128 * 128;
+  p.nc = (Q % 128 == 0) ? 128 : (Q % 64 == 0 ? 64 : 32);
+  p.a_row_bytes = 128; p.b_row_bytes = (p.nc == 32) ? 64 : 128;
+  p.a_chunks = p.mc / 64; p.b_chunks = (p.nc == 32) ? 1 : p.nc / 64;
+  p.a_chunk_bytes = 128 * 128; p.b_chunk_bytes = 128 * p.b_row_bytes;
   p.b_box_rows = 128;
   p.ntaps = 1;
   p.m_chunks_total = P / p.mc;
@@ -301,8 +301,9 @@ int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P
   {
     uint64_t dims[2] = {(uint64_t)Q, (uint64_t)rows};
     uint64_t str[1] = {(uint64_t)Q * 2};
-    uint32_t box[2] = {64, 128};
-    int rc = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint32_t box[2] = {(uint32_t)(p.nc == 32 ? 32 : 64), 128};
+    int rc = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, dims, str, box,
+                        p.nc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   dim3 grid((unsigned)kchunks, 1, (unsigned)((P / p.mc) * (Q / p.nc)));

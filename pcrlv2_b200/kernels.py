@@ -200,29 +200,79 @@ def norm_act_bwd(yp, g1, g2, gavg, scale, shift, mean, invstd, gamma, act="relu"
 
 
 # ------------------------------------------------------------------------------ heads
-def head_fwd(ap, w3, b3, w1=None, b1=None):
-    """w3 [27,C] fp32 tap-major.  Returns (y1 (N,1,D,H,W) fp32, y0 or None)."""
-    _chk(ap, BF16)
+def head_pack_weights(w3, w1=None):
+    """(1,C,3,3,3) [+ (1,C,1,1,1)] fp32 -> (wext [32,C] bf16, wextT [C,32] bf16)."""
+    c = w3.shape[1]
+    wext = torch.empty((32, c), dtype=BF16, device=w3.device)
+    wext_t = torch.empty((c, 32), dtype=BF16, device=w3.device)
+    _lib.call("pcrl_head_pack_weights", w3.contiguous(), None if w1 is None else w1.contiguous(),
+              wext, wext_t, c)
+    return wext, wext_t
+
+
+def head_fwd(ap, wext, b3, b1=None, stats=None, per_sample=False):
+    """1-channel head convolutions of an H-padded activation: T = A * wext^T on the tensor cores,
+    then the 27-point gather.  Returns (y1 (N,1,D,H,W) fp32, y0 or None)."""
+    _chk(ap, BF16), _chk(wext, BF16)
     n, d, h, w, c = dims_of(ap)
+    rows = n * d * (h + 1) * w
+    t_t = torch.empty((32, rows), dtype=torch.float32, device=ap.device)
+    _lib.call("pcrl_gemm_nt", ap, wext, t_t, None, rows, c, 32, rows, 2)
     y1 = torch.empty((n, 1, d, h, w), dtype=torch.float32, device=ap.device)
-    y0 = torch.empty_like(y1) if w1 is not None else None
-    _lib.call("pcrl_head_fwd", ap, w3, b3, w1, b1, y1, y0, n, d, h, w, c)
+    y0 = torch.empty_like(y1) if b1 is not None else None
+    _lib.call("pcrl_head_gather", t_t, b3, b1, y1, y0, stats, int(per_sample), n, d, h, w)
     return y1, y0
 
 
-def head_bwd_data(dy1, w3, dy0, w1, c):
-    n, _, d, h, w = dy1.shape
-    da = torch.empty((n, d, h + 1, w, c), dtype=BF16, device=dy1.device)
-    _lib.call("pcrl_head_bwd_data", dy1, w3, dy0, w1, da, n, d, h, w, c)
-    return da
-
-
-def head_bwd_weight(ap, dy1, dy0=None):
+def head_bwd(ap, dy1, dy0, wext_t):
+    """Returns (dA H-padded bf16, dwext [C,32] fp32: columns 0..26 = d w3 (tap order), 27 = d w1)."""
     n, d, h, w, c = dims_of(ap)
-    dw3 = torch.zeros((27, c), dtype=torch.float32, device=ap.device)
-    dw1 = torch.zeros((c,), dtype=torch.float32, device=ap.device) if dy0 is not None else None
-    _lib.call("pcrl_head_bwd_weight", ap, dy1, dy0, dw3, dw1, n, d, h, w, c)
-    return dw3, dw1
+    rows = n * d * (h + 1) * w
+    d_t = torch.empty((rows, 32), dtype=BF16, device=ap.device)
+    _lib.call("pcrl_head_scatter", dy1, dy0, d_t, n, d, h, w)
+    da = torch.empty((n, d, h + 1, w, c), dtype=BF16, device=ap.device)
+    _lib.call("pcrl_gemm_nt", d_t, wext_t, da, None, rows, 32, c, c, 0)
+    dwext = torch.zeros((c, 32), dtype=torch.float32, device=ap.device)
+    _lib.call("pcrl_gemm_tn", ap, d_t, dwext, rows, c, 32)
+    return da, dwext
+
+
+def chan1_sigmoid_fwd(y, scale, shift, per_sample):
+    """mask = sigmoid(y*scale + shift); y (N,1,D,H,W) fp32; scale/shift [G] (G = N if per_sample)."""
+    mask = torch.empty_like(y)
+    n = y.shape[0]
+    vol = y.numel() // n
+    g, v = (n, vol) if per_sample else (1, y.numel())
+    _lib.call("pcrl_chan1_sigmoid_fwd", y, scale, shift, mask, int(per_sample), g, v)
+    return mask
+
+
+def chan1_sigmoid_bwd(y, mask, dmask, mean, invstd, gamma, per_sample):
+    """Returns (dy, sums [G,3] fp64 with (d beta, d gamma, 0) partials)."""
+    n = y.shape[0]
+    vol = y.numel() // n
+    g, v = (n, vol) if per_sample else (1, y.numel())
+    sums = torch.zeros((g, 3), dtype=torch.float64, device=y.device)
+    dy = torch.empty_like(y)
+    for p in (0, 1):
+        _lib.call("pcrl_chan1_sigmoid_bwd", y, mask, dmask, mean, invstd, gamma, sums, dy, float(v),
+                  int(per_sample), p, g, v)
+    return dy, sums
+
+
+def stem_conv_wgrad_gemm(dyp, x):
+    """Stem weight gradient on the tensor cores: im2col of the 1-channel input to [rows,32]
+    (27 taps), rows paired into 64-wide operands, dW = sum of the diagonal 32x32 blocks of
+    gemm_tn(dY, X27)."""
+    _chk(dyp, BF16), _chk(x, torch.float32)
+    n, _, d, h, w = x.shape
+    rows = n * d * (h + 1) * w
+    x27 = torch.empty((rows, 32), dtype=BF16, device=x.device)
+    _lib.call("pcrl_im2col27", x, x27, n, d, h, w)
+    out = torch.zeros((64, 64), dtype=torch.float32, device=x.device)
+    _lib.call("pcrl_gemm_tn", dyp, x27, out, rows // 2, 64, 64)
+    dw = out[:32, :32] + out[32:, 32:]
+    return dw[:, :27].reshape(32, 1, 3, 3, 3).contiguous()
 
 
 # ------------------------------------------------------------------------------ GEMMs / SGD
@@ -230,6 +280,10 @@ def gemm_nt(a, b, bias=None, out_fp32=True):
     _chk(a, BF16), _chk(b, BF16)
     rows, k = a.shape
     cols = b.shape[0]
+    if out_fp32 == "transposed":
+        c = torch.empty((cols, rows), dtype=torch.float32, device=a.device)
+        _lib.call("pcrl_gemm_nt", a, b, c, bias, rows, k, cols, rows, 2)
+        return c
     c = torch.empty((rows, cols), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
     _lib.call("pcrl_gemm_nt", a, b, c, bias, rows, k, cols, cols, int(out_fp32))
     return c

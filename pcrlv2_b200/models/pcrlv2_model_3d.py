@@ -47,12 +47,26 @@ def _packed(module, kind):
                 pk = K.pack_conv3_weights(w.detach().contiguous())
             elif kind == "convT":
                 pk = K.pack_convT_weights(w.detach().contiguous())
-            elif kind == "head3":   # (1,C,3,3,3) -> [27,C] fp32 tap-major
-                pk = (w.detach().reshape(w.shape[1], 27).t().contiguous(),)
+            elif kind == "head":    # (ds conv, final conv or None) -> wext [32,C], wextT [C,32]
+                raise ValueError("use _packed_head")
             else:
                 raise ValueError(kind)
         cache = (key, pk)
         module._pcrl_packed = cache
+    return cache[1]
+
+
+def _packed_head(ds, fin):
+    """bf16 GEMM operands of the 1-channel head convolutions (deep-supervision conv [+ 1x1x1 output
+    conv]), cached until either weight changes."""
+    key = (ds.weight._version, ds.weight.data_ptr(), _PARAM_EPOCH[0],
+           None if fin is None else (fin.weight._version, fin.weight.data_ptr()))
+    cache = getattr(ds, "_pcrl_head", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            pk = K.head_pack_weights(ds.weight.detach(), None if fin is None else fin.weight.detach())
+        cache = (key, pk)
+        ds._pcrl_head = cache
     return cache[1]
 
 
@@ -106,14 +120,16 @@ class _LUConvFn(torch.autograd.Function):
                                         want_pool=cfg.pool, want_avg=cfg.tail, per_sample=per_sample)
         outs = [pooled if cfg.pool else a]
         if cfg.tail:
-            (w3,) = _packed(cfg.ds, "head3")
-            w1 = fin_w.detach().reshape(-1).contiguous() if cfg.final else None
-            y1, y0 = K.head_fwd(a, w3, ds_b.detach(), w1, fin_b.detach() if cfg.final else None)
+            wext, _ = _packed_head(cfg.ds, cfg.fin)
+            st1 = torch.zeros((groups, 1, 2), dtype=torch.float64, device=x.device)
+            y1, y0 = K.head_fwd(a, wext, ds_b.detach(), fin_b.detach() if cfg.final else None,
+                                st1, per_sample)
             # the kernel accumulates sums; hand autograd the MEAN so that the incoming gradient is
             # dL/d(mean), which is what norm_act_bwd expects for its gavg argument
-            outs += [avg * (1.0 / float(d * h * w)), y1]
+            outs += [avg * (1.0 / float(d * h * w)), y1, st1]
             if cfg.final:
                 outs.append(y0)
+            ctx.mark_non_differentiable(st1)
         ctx.cfg = cfg
         ctx.dims = (n, d, h, w, cout)
         ctx.save_for_backward(x, y, scale, shift, mean, invstd, gamma, prelu,
@@ -121,7 +137,7 @@ class _LUConvFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g_out, g_avg=None, g_y1=None, g_y0=None):
+    def backward(ctx, g_out, g_avg=None, g_y1=None, _g_st1=None, g_y0=None):
         cfg = ctx.cfg
         x, y, scale, shift, mean, invstd, gamma, prelu, a, ds_w, fin_w = ctx.saved_tensors
         n, d, h, w, cout = ctx.dims
@@ -132,15 +148,13 @@ class _LUConvFn(torch.autograd.Function):
             dy1 = g_y1.contiguous() if g_y1 is not None else torch.zeros(
                 (n, 1, d, h, w), dtype=torch.float32, device=y.device)
             dy0 = g_y0.contiguous() if (cfg.final and g_y0 is not None) else None
-            (w3,) = _packed(cfg.ds, "head3")
-            w1 = fin_w.detach().reshape(-1).contiguous() if dy0 is not None else None
-            g2 = K.head_bwd_data(dy1, w3, dy0, w1, cout)
-            dw3, dw1 = K.head_bwd_weight(a, dy1, dy0)
+            _, wext_t = _packed_head(cfg.ds, cfg.fin)
+            g2, dwext = K.head_bwd(a, dy1, dy0, wext_t)
             if g_y1 is not None:
-                grads[6] = dw3.t().reshape(1, cout, 3, 3, 3)
+                grads[6] = dwext[:, :27].reshape(1, cout, 3, 3, 3)
                 grads[7] = dy1.sum().reshape(1)
             if dy0 is not None:
-                grads[8] = dw1.reshape(1, cout, 1, 1, 1)
+                grads[8] = dwext[:, 27].reshape(1, cout, 1, 1, 1)
                 grads[9] = dy0.sum().reshape(1)
         if g_out is None and g2 is None and g_avg is None:
             return tuple(grads)
@@ -156,13 +170,47 @@ class _LUConvFn(torch.autograd.Function):
             grads[5] = sums[:, 2].contiguous()
         grads[2] = torch.zeros(cout, dtype=torch.float32, device=y.device)  # conv bias: exactly 0
         if cfg.stem:
-            grads[1] = K.stem_conv_wgrad(dy, x)
+            grads[1] = K.stem_conv_wgrad_gemm(dy, x)
         else:
             _, wd = _packed(cfg.conv, "conv3")
             if ctx.needs_input_grad[0]:
                 grads[0] = K.conv3d_k3_dgrad(dy, wd)
             grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
         return tuple(grads)
+
+
+class _Chan1NormSigmoidFn(torch.autograd.Function):
+    """mask = sigmoid(BatchNorm3d(1) / InstanceNorm3d(1) (y1)) of a deep-supervision head
+    (reference :12,27,71).  ``stats`` are the (sum, sum of squares) the head gather produced."""
+
+    @staticmethod
+    def forward(ctx, y1, gamma, beta, stats, bn, norm, training):
+        per_sample = norm == "in"
+        n = y1.shape[0]
+        vol = y1.numel() // n
+        if training or per_sample:
+            track = training and not per_sample
+            scale, shift, mean, invstd = K.norm_finalize(
+                stats, vol if per_sample else y1.numel(), gamma.detach(), beta.detach(), None,
+                bn.running_mean if track else None, bn.running_var if track else None,
+                bn.num_batches_tracked if track else None, 0.1, 1e-5)
+        else:
+            invstd = torch.rsqrt(bn.running_var + 1e-5).reshape(1, 1)
+            mean = bn.running_mean.reshape(1, 1).clone()
+            scale = (gamma.detach().reshape(1, 1) * invstd).contiguous()
+            shift = (beta.detach().reshape(1, 1) - mean * scale).contiguous()
+        mask = K.chan1_sigmoid_fwd(y1, scale, shift, per_sample)
+        ctx.per_sample = per_sample
+        ctx.save_for_backward(y1, mask, mean, invstd, gamma)
+        return mask
+
+    @staticmethod
+    def backward(ctx, dmask):
+        y1, mask, mean, invstd, gamma = ctx.saved_tensors
+        dy, sums = K.chan1_sigmoid_bwd(y1, mask, dmask.contiguous(), mean, invstd, gamma.detach(),
+                                       ctx.per_sample)
+        sums = sums.sum(0).float()
+        return dy, sums[1].reshape(1), sums[0].reshape(1), None, None, None, None
 
 
 class _ConvTFn(torch.autograd.Function):
@@ -278,20 +326,13 @@ class UpTransition(nn.Module):
         up = _ConvTFn.apply(x, self.up_conv.weight, self.up_conv.bias, self.up_conv)
         h = self.ops[0].run(up)[0]
         outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final)
-        a, avg, y1 = outs[0], outs[1], outs[2]
-        y0 = outs[3] if final is not None else None
+        a, avg, y1, st1 = outs[0], outs[1], outs[2], outs[3]
+        y0 = outs[4] if final is not None else None
         x_pro = self.bn(avg)
         x_pre = self.predictor_head(x_pro)
-        ds = self.deep_supervision_head
-        if self.norm == "bn":
-            bn = ds.bn1
-            if self.training:
-                bn.num_batches_tracked += 1
-            z = F.batch_norm(y1, bn.running_mean, bn.running_var, bn.weight, bn.bias, self.training,
-                             0.1, 1e-5)
-        else:
-            z = F.instance_norm(y1, None, None, ds.bn1.weight, ds.bn1.bias, True, 0.1, 1e-5)
-        return a, x_pro, x_pre, torch.sigmoid(z), y0
+        bn = self.deep_supervision_head.bn1
+        mask = _Chan1NormSigmoidFn.apply(y1, bn.weight, bn.bias, st1, bn, self.norm, self.training)
+        return a, x_pro, x_pre, mask, y0
 
 
 class OutputTransition(nn.Module):

@@ -46,7 +46,7 @@ class FlatSGD(torch.optim.Optimizer):
     parameters' ``.data`` / ``.grad`` are views into them, and ``step()`` is a single kernel.
 
     ``zero_grad()`` zero-fills the flat gradient buffer and marks every parameter "untouched"; a
-    post-accumulate hook marks the parameters autograd actually reached.  ``step()`` updates only
+    gradient hook marks the parameters autograd actually reached.  ``step()`` updates only
     those (no weight decay / momentum decay for the others), optionally after an NCCL all-reduce
     of the flat gradient buffer across ``process_group``.
     """
@@ -81,15 +81,19 @@ class FlatSGD(torch.optim.Optimizer):
         self._touched = [False] * len(ps)
         self._has_buf = [False] * len(ps)
         for i, p in enumerate(ps):
-            p.register_post_accumulate_grad_hook(self._make_hook(i))
+            p.register_hook(self._make_hook(i))
         self._distributed = (dist.is_available() and dist.is_initialized()
                              and dist.get_world_size(process_group) > 1) if distributed is None else distributed
         self._pg = process_group
         bump_param_epoch()
 
     def _make_hook(self, i):
-        def hook(_p):
-            self._touched[i] = True
+        def hook(grad):
+            # autograd also calls tensor hooks with None when a custom Function returned no
+            # gradient for this parameter: only a defined gradient counts
+            if grad is not None:
+                self._touched[i] = True
+            return None
         return hook
 
     def zero_grad(self, set_to_none=True):

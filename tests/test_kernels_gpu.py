@@ -214,34 +214,79 @@ def test_norm_act(per_sample, act, mode):
 @pytest.mark.parametrize("shape", [(2, 4, 6, 8, 64), (1, 8, 8, 4, 128), (3, 2, 2, 2, 256), (2, 16, 16, 16, 64)])
 @pytest.mark.parametrize("with_final", [False, True])
 def test_heads(shape, with_final):
+    """Conv3d(C->1,k3,p1) [+ Conv3d(C->1,k1)] factored as tensor-core GEMM + 27-point gather."""
     n, d, h, w, c = shape
     torch.manual_seed(6)
     a = q(torch.randn(n, c, d, h, w, device=DEV)).requires_grad_(True)
-    w3 = (torch.randn(1, c, 3, 3, 3, device=DEV) / (27 * c) ** 0.5).requires_grad_(True)
+    w3 = q(torch.randn(1, c, 3, 3, 3, device=DEV) / (27 * c) ** 0.5).requires_grad_(True)
     b3 = torch.randn(1, device=DEV, requires_grad=True)
-    w1 = (torch.randn(1, c, 1, 1, 1, device=DEV) / c ** 0.5).requires_grad_(True)
+    w1 = q(torch.randn(1, c, 1, 1, 1, device=DEV) / c ** 0.5).requires_grad_(True)
     b1 = torch.randn(1, device=DEV, requires_grad=True)
     y1_ref = F.conv3d(a, w3, b3, padding=1)
     y0_ref = F.conv3d(a, w1, b1)
     ap = K.pad_ndhwc(a.detach())
-    w3p = w3.detach().reshape(c, 27).t().contiguous()
-    w1p = w1.detach().reshape(c).contiguous()
-    y1, y0 = K.head_fwd(ap, w3p, b3.detach(), w1p if with_final else None, b1.detach() if with_final else None)
+    wext, wext_t = K.head_pack_weights(w3.detach(), w1.detach() if with_final else None)
+    stats = torch.zeros(1, 1, 2, dtype=torch.float64, device=DEV)
+    y1, y0 = K.head_fwd(ap, wext, b3.detach(), b1.detach() if with_final else None, stats)
     assert rel(y1, y1_ref) < TOL32
-    dy1 = torch.randn_like(y1_ref)
-    dy0 = torch.randn_like(y0_ref)
+    assert rel(stats[0, 0, 0:1], y1_ref.double().sum().reshape(1)) < 1e-4 or abs(stats[0, 0, 0].item() - y1_ref.double().sum().item()) < 1e-2
+    assert rel(stats[0, 0, 1:2], (y1_ref.double() ** 2).sum().reshape(1)) < 1e-4
+    st_n = torch.zeros(n, 1, 2, dtype=torch.float64, device=DEV)
+    K.head_fwd(ap, wext, b3.detach(), None, st_n, per_sample=True)
+    assert rel(st_n[:, 0, 1], (y1_ref.double() ** 2).sum(dim=(1, 2, 3, 4))) < 1e-4
+    dy1 = q(torch.randn_like(y1_ref))
+    dy0 = q(torch.randn_like(y0_ref))
     loss = (y1_ref * dy1).sum()
     if with_final:
         assert rel(y0, y0_ref) < TOL32
         loss = loss + (y0_ref * dy0).sum()
     loss.backward()
-    da = K.head_bwd_data(dy1, w3p, dy0 if with_final else None, w1p if with_final else None, c)
+    da, dwext = K.head_bwd(ap, dy1, dy0 if with_final else None, wext_t)
     assert rel(K.unpad_ndhwc(da), a.grad) < TOL16
     assert da[:, :, 0].abs().max().item() == 0
-    dw3, dw1 = K.head_bwd_weight(ap, dy1, dy0 if with_final else None)
-    assert rel(dw3.t().reshape(1, c, 3, 3, 3), w3.grad) < TOL32
+    assert rel(dwext[:, :27].reshape(1, c, 3, 3, 3), w3.grad) < TOL32
     if with_final:
-        assert rel(dw1.reshape(1, c, 1, 1, 1), w1.grad) < TOL32
+        assert rel(dwext[:, 27].reshape(1, c, 1, 1, 1), w1.grad) < TOL32
+
+
+@pytest.mark.parametrize("per_sample", [False, True])
+def test_chan1_norm_sigmoid(per_sample):
+    n, d, h, w = 3, 4, 6, 8
+    torch.manual_seed(9)
+    y = (torch.randn(n, 1, d, h, w, device=DEV) * 1.7 + 0.4).requires_grad_(True)
+    gamma = torch.tensor([1.3], device=DEV, requires_grad=True)
+    beta = torch.tensor([-0.2], device=DEV, requires_grad=True)
+    if per_sample:
+        ref = torch.sigmoid(F.instance_norm(y, None, None, gamma, beta, True, 0.1, 1e-5))
+    else:
+        ref = torch.sigmoid(F.batch_norm(y, None, None, gamma, beta, True, 0.1, 1e-5))
+    yd = y.detach().double()
+    dims = (1, 2, 3, 4) if per_sample else (0, 1, 2, 3, 4)
+    G = n if per_sample else 1
+    stats = torch.stack([yd.sum(dims), (yd ** 2).sum(dims)], -1).reshape(G, 1, 2).contiguous()
+    count = d * h * w * (1 if per_sample else n)
+    scale, shift, mean, invstd = K.norm_finalize(stats, count, gamma.detach(), beta.detach())
+    mask = K.chan1_sigmoid_fwd(y.detach().contiguous(), scale, shift, per_sample)
+    assert rel(mask, ref) < 1e-5
+    g = torch.randn_like(ref)
+    (ref * g).sum().backward()
+    dy, sums = K.chan1_sigmoid_bwd(y.detach().contiguous(), mask, g, mean, invstd, gamma.detach(), per_sample)
+    assert rel(dy, y.grad) < 1e-4
+    assert rel(sums[:, 1].sum().reshape(1), gamma.grad) < 1e-4
+    assert rel(sums[:, 0].sum().reshape(1), beta.grad) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 16, 16, 16), (3, 4, 6, 2), (2, 64, 64, 32)])
+def test_stem_wgrad_gemm(shape):
+    n, d, h, w = shape
+    torch.manual_seed(3)
+    x = q(torch.randn(n, 1, d, h, w, device=DEV))
+    wt = torch.randn(32, 1, 3, 3, 3, device=DEV, requires_grad=True)
+    ref = F.conv3d(x, wt, padding=1)
+    dy = q(torch.randn_like(ref))
+    ref.backward(dy)
+    dw = K.stem_conv_wgrad_gemm(K.pad_ndhwc(dy), x)
+    assert rel(dw, wt.grad) < TOL32
 
 
 @pytest.mark.parametrize("dims", [(300, 128, 256), (128, 64, 64), (1000, 512, 128), (77, 256, 512)])
@@ -256,6 +301,15 @@ def test_gemms(dims):
     b2 = q(torch.randn(rows, cols, device=DEV))
     c2 = K.gemm_tn(a.to(torch.bfloat16), b2.to(torch.bfloat16))
     assert rel(c2, a.t() @ b2) < TOL32
+    ct = K.gemm_nt(a.to(torch.bfloat16), b.to(torch.bfloat16), None, out_fp32="transposed")
+    assert rel(ct, (a @ b.t()).t()) < TOL32
+    # 32-wide operands (head GEMMs): K = 32 and Q = 32
+    a32 = q(torch.randn(rows, 32, device=DEV))
+    c3 = K.gemm_nt(a32.to(torch.bfloat16), q(torch.randn(cols, 32, device=DEV)).to(torch.bfloat16))
+    assert c3.shape == (rows, cols)
+    b32 = q(torch.randn(cols, 32, device=DEV))
+    assert rel(K.gemm_nt(a32.to(torch.bfloat16), b32.to(torch.bfloat16)), a32 @ b32.t()) < TOL32
+    assert rel(K.gemm_tn(a.to(torch.bfloat16), a32.to(torch.bfloat16)), a.t() @ a32) < TOL32
 
 
 def test_sgd_flat():
