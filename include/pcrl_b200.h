@@ -60,6 +60,13 @@ int pcrl_conv3d_k3_fprop(const void* x, const void* wf, void* y, double* stats,
  * pcrl_pack_conv3_weights, dx [N][D][H+1][W][Cin] bf16.  Autograd of the call above. */
 int pcrl_conv3d_k3_dgrad(const void* dy, const void* wd, void* dx, int N, int D, int H, int W,
                          int Cin, int Cout, void* stream);
+/* Same data gradient, stored for the ConvTranspose3d(k2,s2) that produced x: coarse-major
+ * [N*(D/2)*(H/2+1)*(W/2)][8][Cin] bf16 (pad rows zeroed) -- the operand layout of
+ * pcrl_convT3d_k2s2_bwd with g_fine = NULL.  colsum (nullable) [Cin][2] fp64 += per-channel
+ * (sum, sum of squares) of dx: column 0 is the ConvTranspose bias gradient. */
+int pcrl_conv3d_k3_dgrad_unshuffled(const void* dy, const void* wd, void* dx_coarse_major,
+                                    double* colsum, int N, int D, int H, int W, int Cin, int Cout,
+                                    void* stream);
 /* dw_packed [27][Cout][Cin] fp32 += weight gradient (caller zeroes or keeps a running sum).
  * dy and x must have zero pad rows. */
 int pcrl_conv3d_k3_wgrad(const void* dy, const void* x, float* dw_packed, int N, int D, int H,
@@ -78,7 +85,8 @@ int pcrl_convT3d_k2s2_fprop(const void* x, const void* wf, const float* bias, vo
                             int D, int H, int W, int Cin, int Cout, void* stream);
 /* Backward.  g_fine [N][2D][2H+1][2W][Cout] bf16; scratch [N*D*(H+1)*W][8*Cout] bf16;
  * dx [N][D][H+1][W][Cin] bf16; dw_packed [(tap,Cout)][Cin] fp32 += ; dbias [Cout] fp32 += .
- * x may be NULL together with dw_packed to skip the weight gradient. */
+ * x may be NULL together with dw_packed to skip the weight gradient; g_fine may be NULL when
+ * scratch already holds the coarse-major gradient (pcrl_conv3d_k3_dgrad_unshuffled). */
 int pcrl_convT3d_k2s2_bwd(const void* g_fine, const void* x, const void* wd, void* scratch,
                           void* dx, float* dw_packed, float* dbias, int N, int D, int H, int W,
                           int Cin, int Cout, void* stream);

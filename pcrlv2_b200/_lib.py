@@ -29,6 +29,7 @@ SIGNATURES = {
     "pcrl_unpack_convT_wgrad": [_P, _P, _I, _I, _P],
     "pcrl_conv3d_k3_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "pcrl_conv3d_k3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_conv3d_k3_dgrad_unshuffled": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pcrl_conv3d_k3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pcrl_stem_conv_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pcrl_stem_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
@@ -97,7 +98,7 @@ def _conv(a):
 
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches count)
-LAUNCHES = {"pcrl_convT3d_k2s2_fprop": 2, "pcrl_convT3d_k2s2_bwd": 3}
+LAUNCHES = {"pcrl_convT3d_k2s2_fprop": 2, "pcrl_convT3d_k2s2_bwd": 3, "pcrl_conv3d_k3_dgrad_unshuffled": 2}
 launch_count = [0]
 # when set to a list, every call is bracketed by CUDA events on the launching stream and
 # (name, int-args, start, end) is appended -- bench.py uses this for the per-kernel roofline

@@ -22,7 +22,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 // launchers defined in igemm_kmajor.cu / igemm_mnmajor.cu / streaming.cu / heads.cu
-int conv3d_k3_igemm(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, cudaStream_t);
+int conv3d_k3_igemm(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, cudaStream_t, int);
 int gemm_nt_igemm(const void*, const void*, void*, const float*, long long, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv3d_k3_wgrad_igemm(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
 int gemm_tn_igemm(const void*, const void*, float*, long long, int, int, cudaStream_t);
@@ -76,14 +76,22 @@ int pcrl_unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, void*
 int pcrl_conv3d_k3_fprop(const void* x, const void* wf, void* y, double* stats, int stats_per_sample,
                          int out_fp32, int N, int D, int H, int W, int Cin, int Cout, void* stream) {
   NONNULL(x); NONNULL(wf); NONNULL(y);
-  return conv3d_k3_igemm(x, wf, y, stats, stats_per_sample, out_fp32, N, D, H, W, Cin, Cout, ST(stream));
+  return conv3d_k3_igemm(x, wf, y, stats, stats_per_sample, out_fp32, N, D, H, W, Cin, Cout, ST(stream), 0);
 }
 int pcrl_conv3d_k3_dgrad(const void* dy, const void* wd, void* dx, int N, int D, int H, int W,
                          int Cin, int Cout, void* stream) {
   NONNULL(dy); NONNULL(wd); NONNULL(dx);
   // the data gradient is a 3x3x3 convolution of dy (Cout channels) with the mirrored, transposed
   // filter: same kernel with the channel roles swapped
-  return conv3d_k3_igemm(dy, wd, dx, nullptr, 0, 0, N, D, H, W, Cout, Cin, ST(stream));
+  return conv3d_k3_igemm(dy, wd, dx, nullptr, 0, 0, N, D, H, W, Cout, Cin, ST(stream), 0);
+}
+int pcrl_conv3d_k3_dgrad_unshuffled(const void* dy, const void* wd, void* dx_coarse_major, double* colsum,
+                                    int N, int D, int H, int W, int Cin, int Cout, void* stream) {
+  NONNULL(dy); NONNULL(wd); NONNULL(dx_coarse_major);
+  int rc = conv3d_k3_igemm(dy, wd, dx_coarse_major, colsum, 0, 0, N, D, H, W, Cout, Cin, ST(stream), 1);
+  if (rc) return rc;
+  // pad rows (coarse h' = 0) of the coarse-major tensor feed the ConvTranspose GEMMs: zero them
+  return zero_pad_rows(dx_coarse_major, (long long)N * (D / 2), H / 2 + 1, (W / 2) * 8 * Cin, ST(stream));
 }
 int pcrl_conv3d_k3_wgrad(const void* dy, const void* x, float* dw_packed, int N, int D, int H, int W,
                          int Cin, int Cout, void* stream) {
@@ -114,10 +122,13 @@ int pcrl_convT3d_k2s2_fprop(const void* x, const void* wf, const float* bias, vo
 int pcrl_convT3d_k2s2_bwd(const void* g_fine, const void* x, const void* wd, void* scratch, void* dx,
                           float* dw_packed, float* dbias, int N, int D, int H, int W, int Cin,
                           int Cout, void* stream) {
-  NONNULL(g_fine); NONNULL(scratch);
+  NONNULL(scratch);
   const long long rows = (long long)N * D * (H + 1) * W;
-  int rc = convT_unshuffle(g_fine, scratch, dbias, N, D, H, W, Cout, ST(stream));
-  if (rc) return rc;
+  int rc = PCRL_OK;
+  if (g_fine) {   // otherwise `scratch` already holds the coarse-major gradient
+    rc = convT_unshuffle(g_fine, scratch, dbias, N, D, H, W, Cout, ST(stream));
+    if (rc) return rc;
+  }
   if (dx) {
     NONNULL(wd);
     rc = gemm_nt_igemm(scratch, wd, dx, nullptr, rows, 8 * Cout, Cin, Cin, 0, /*OUT_ROWS*/ 1, 0, 0, 0, 0,

@@ -29,7 +29,7 @@
 namespace pcrl {
 
 enum { IG_CONV = 0, IG_PLAIN = 1 };
-enum { OUT_FLAT = 0, OUT_ROWS = 1, OUT_CONVT = 2, OUT_ROWS_T = 3 };
+enum { OUT_FLAT = 0, OUT_ROWS = 1, OUT_CONVT = 2, OUT_ROWS_T = 3, OUT_UNSHUFFLE = 4 };
 
 struct IgemmParams {
   int mode;
@@ -265,11 +265,21 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
         for (int pp = 0; pp < p.P; pp++) {
           bool valid;
           long long off;
-          if (p.out_mode == OUT_FLAT) {
+          if (p.out_mode == OUT_FLAT || p.out_mode == OUT_UNSHUFFLE) {
             const int f = tc.f0 + pp * p.PL + lrow;
             const int mr = f / p.Wp, wq = f - mr * p.Wp;
-            valid = (wq >= 1) && (mr < p.MR) && ((mr % p.H1) >= 1) && (tc.t_local + lrow < p.seg_len);
-            off = (((long long)tc.n * p.MR + mr) * p.W + (wq - 1)) * p.ldc + co0;
+            const int hp = mr % p.H1;
+            valid = (wq >= 1) && (mr < p.MR) && (hp >= 1) && (tc.t_local + lrow < p.seg_len);
+            if (p.out_mode == OUT_FLAT) {
+              off = (((long long)tc.n * p.MR + mr) * p.W + (wq - 1)) * p.ldc + co0;
+            } else {
+              // fine voxel (d2, h2, w2) -> coarse-major [coarse H-padded row][tap][C] (the layout
+              // the ConvTranspose gradient GEMMs consume); ct_* are the coarse dims
+              const int d2 = mr / p.H1, h2 = hp - 1, w2 = wq - 1;
+              const int t = ((d2 & 1) << 2) | ((h2 & 1) << 1) | (w2 & 1);
+              const long long crow = (((long long)tc.n * p.ct_D + (d2 >> 1)) * (p.ct_H + 1) + (h2 >> 1) + 1) * p.ct_W + (w2 >> 1);
+              off = (crow * 8 + t) * p.ldc + co0;
+            }
           } else if (p.out_mode == OUT_ROWS) {
             const long long r = (long long)tc.f0 + lrow;
             valid = r < p.rows_total;
@@ -443,7 +453,7 @@ static int make_b_maps(IgemmLaunch& L, const void* w, int K, int cols, int taps)
 //   stats (optional): [Cout][2] (or [N][Cout][2]) fp64, ACCUMULATED (caller zeroes)
 int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int stats_per_sample,
                     int out_fp32, int N, int D, int H, int W, int Cin, int Cout,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, int unshuffle) {
   PCRL_REQUIRE(Cin == 32 || Cin % 64 == 0, "conv3d_k3: Cin=%d must be 32 or a multiple of 64", Cin);
   PCRL_REQUIRE(Cout % 32 == 0, "conv3d_k3: Cout=%d must be a multiple of 32", Cout);
   PCRL_REQUIRE(W + 1 <= 256 && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_k3: bad dims");
@@ -481,7 +491,11 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
   p.nh_box = (p.m_cta + 3 * p.Wp + 1 + p.Wp - 1) / p.Wp;
   if (p.nh_box > 256) return fail(PCRL_ERR_UNSUPPORTED, "conv3d_k3: W=%d too small for box", W);
   p.slab_bytes = ((p.nh_box * p.Wp * p.row_bytes + 1023) / 1024) * 1024;
-  p.out_mode = OUT_FLAT; p.out_fp32 = out_fp32; p.ldc = Cout; p.cout_total = Cout;
+  p.out_mode = unshuffle ? OUT_UNSHUFFLE : OUT_FLAT; p.out_fp32 = out_fp32; p.ldc = Cout; p.cout_total = Cout;
+  if (unshuffle) {
+    PCRL_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && !out_fp32, "conv3d_k3: unshuffle needs even dims, bf16");
+    p.ct_D = D / 2; p.ct_H = H / 2; p.ct_W = W / 2;
+  }
   p.has_stats = stats != nullptr; p.stats_per_sample = stats_per_sample;
   p.out = y; p.stats = stats;
   uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)p.MR, (uint64_t)N};

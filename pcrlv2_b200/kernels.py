@@ -101,6 +101,29 @@ def conv3d_k3_dgrad(dyp, wd):
     return dx
 
 
+def conv3d_k3_dgrad_unshuffled(dyp, wd):
+    """Data gradient written coarse-major for the ConvTranspose that produced the conv input.
+    Returns (scratch [N*(D/2)*(H/2+1)*(W/2), 8*Cin] bf16, colsum [Cin,2] fp64)."""
+    _chk(dyp, BF16), _chk(wd, BF16)
+    n, d, h, w, cout = dims_of(dyp)
+    cin = wd.shape[1]
+    rows = n * (d // 2) * (h // 2 + 1) * (w // 2)
+    scratch = torch.empty((rows, 8 * cin), dtype=BF16, device=dyp.device)
+    colsum = torch.zeros((cin, 2), dtype=torch.float64, device=dyp.device)
+    _lib.call("pcrl_conv3d_k3_dgrad_unshuffled", dyp, wd, scratch, colsum, n, d, h, w, cin, cout)
+    return scratch, colsum
+
+
+def convT_bwd_from_scratch(scratch, xp, wd, need_dx=True):
+    """ConvTranspose3d(k2,s2) gradient GEMMs on an already coarse-major output gradient."""
+    n, d, h, w, cin = dims_of(xp)
+    cout = scratch.shape[1] // 8
+    dx = torch.empty((n, d, h + 1, w, cin), dtype=BF16, device=xp.device) if need_dx else None
+    dw = torch.zeros((8 * cout, cin), dtype=torch.float32, device=xp.device)
+    _lib.call("pcrl_convT3d_k2s2_bwd", None, xp, wd, scratch, dx, dw, None, n, d, h, w, cin, cout)
+    return dx, dw
+
+
 def conv3d_k3_wgrad(dyp, xp, out=None):
     """Returns / accumulates into the packed gradient [27,Cout,Cin] fp32."""
     _chk(dyp, BF16), _chk(xp, BF16)

@@ -72,7 +72,7 @@ def _packed_head(ds, fin):
 
 class _Cfg:
     """Static (non-tensor) configuration of one fused LUConv call."""
-    __slots__ = ("stem", "pool", "tail", "final", "act", "norm", "training", "conv", "bn", "ds", "fin")
+    __slots__ = ("stem", "pool", "tail", "final", "act", "norm", "training", "conv", "bn", "ds", "fin", "up")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -80,14 +80,24 @@ class _Cfg:
 
 
 class _LUConvFn(torch.autograd.Function):
-    """conv3x3x3 -> norm -> act [-> maxpool] [-> avg-pool sums, 1-channel head convs]."""
+    """[ConvTranspose3d(k2,s2) ->] conv3x3x3 -> norm -> act [-> maxpool]
+    [-> avg-pool sums, 1-channel head convs].
+
+    With ``cfg.up`` set the ConvTranspose that feeds the convolution is part of the same node, so
+    the backward pass can have the data-gradient kernel write straight into the coarse-major
+    layout the ConvTranspose gradient GEMMs read (no re-layout pass over the largest tensors)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, prelu, ds_w, ds_b, fin_w, fin_b, cfg):
+    def forward(ctx, x, weight, bias, gamma, beta, prelu, ds_w, ds_b, fin_w, fin_b, up_w, up_b, cfg):
         ctx.set_materialize_grads(False)
         per_sample = cfg.norm == "in"
         cout = weight.shape[0]
         use_batch_stats = cfg.training or per_sample
+        x_coarse = None
+        if cfg.up is not None:
+            wtf, _ = _packed(cfg.up, "convT")
+            x_coarse = x
+            x = K.convT_fprop(x, wtf, up_b.detach().contiguous())
         if cfg.stem:
             n, _, d, h, w = x.shape
         else:
@@ -133,16 +143,16 @@ class _LUConvFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.dims = (n, d, h, w, cout)
         ctx.save_for_backward(x, y, scale, shift, mean, invstd, gamma, prelu,
-                              a if cfg.tail else None, ds_w, fin_w)
+                              a if cfg.tail else None, ds_w, fin_w, x_coarse)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, g_out, g_avg=None, g_y1=None, _g_st1=None, g_y0=None):
         cfg = ctx.cfg
-        x, y, scale, shift, mean, invstd, gamma, prelu, a, ds_w, fin_w = ctx.saved_tensors
+        x, y, scale, shift, mean, invstd, gamma, prelu, a, ds_w, fin_w, x_coarse = ctx.saved_tensors
         n, d, h, w, cout = ctx.dims
         per_sample = cfg.norm == "in"
-        grads = [None] * 11
+        grads = [None] * 13
         g2 = None
         if cfg.tail and (g_y1 is not None or g_y0 is not None):
             dy1 = g_y1.contiguous() if g_y1 is not None else torch.zeros(
@@ -173,9 +183,18 @@ class _LUConvFn(torch.autograd.Function):
             grads[1] = K.stem_conv_wgrad_gemm(dy, x)
         else:
             _, wd = _packed(cfg.conv, "conv3")
-            if ctx.needs_input_grad[0]:
-                grads[0] = K.conv3d_k3_dgrad(dy, wd)
             grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
+            if cfg.up is not None:
+                # data gradient lands coarse-major; its column sums are the ConvTranspose bias gradient
+                scratch, colsum = K.conv3d_k3_dgrad_unshuffled(dy, wd)
+                _, wtd = _packed(cfg.up, "convT")
+                dxc, dwt = K.convT_bwd_from_scratch(scratch, x_coarse, wtd, need_dx=ctx.needs_input_grad[0])
+                cin_t, cout_t = cfg.up.weight.shape[0], cfg.up.weight.shape[1]
+                grads[0] = dxc
+                grads[10] = K.unpack_convT_wgrad(dwt, cin_t, cout_t)
+                grads[11] = colsum[:, 0].float().contiguous()
+            elif ctx.needs_input_grad[0]:
+                grads[0] = K.conv3d_k3_dgrad(dy, wd)
         return tuple(grads)
 
 
@@ -265,18 +284,21 @@ class LUConv(nn.Module):
         self.act, self.norm = act, norm
         self.in_chan, self.out_chan = in_chan, out_chan
 
-    def run(self, x, pool=False, tail=None, final=None):
-        """x: fp32 (N,1,D,H,W) for the stem, otherwise an H-padded bf16 activation."""
+    def run(self, x, pool=False, tail=None, final=None, up=None):
+        """x: fp32 (N,1,D,H,W) for the stem, otherwise an H-padded bf16 activation.  ``up``: the
+        ConvTranspose3d module to apply to x first (UpTransition)."""
         cfg = _Cfg(stem=self.in_chan == 1, pool=pool, tail=tail is not None, final=final is not None,
                    act=self.act, norm=self.norm, training=self.training, conv=self.conv1, bn=self.bn1,
-                   ds=tail.conv1 if tail is not None else None, fin=final)
+                   ds=tail.conv1 if tail is not None else None, fin=final, up=up)
         prelu = self.activation.weight if self.act == "prelu" else None
         return _LUConvFn.apply(
             x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, prelu,
             tail.conv1.weight if tail is not None else None,
             tail.conv1.bias if tail is not None else None,
             final.weight if final is not None else None,
-            final.bias if final is not None else None, cfg)
+            final.bias if final is not None else None,
+            up.weight if up is not None else None,
+            up.bias if up is not None else None, cfg)
 
     def forward(self, x):
         """Stand-alone use with the reference's NCDHW fp32 convention."""
@@ -323,8 +345,7 @@ class UpTransition(nn.Module):
         self.norm = norm
 
     def run(self, x, final=None):
-        up = _ConvTFn.apply(x, self.up_conv.weight, self.up_conv.bias, self.up_conv)
-        h = self.ops[0].run(up)[0]
+        h = self.ops[0].run(x, up=self.up_conv)[0]
         outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final)
         a, avg, y1, st1 = outs[0], outs[1], outs[2], outs[3]
         y0 = outs[4] if final is not None else None

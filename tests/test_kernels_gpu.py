@@ -335,3 +335,26 @@ def test_sgd_flat():
         d_ = g[sl] + 1e-4 * p0[sl]
         m = d_ if first[i] else 0.9 * b0[sl] + d_
         assert rel(buf[sl], m) < 1e-6 and rel(p[sl], p0[sl] - 0.01 * m) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 4, 4, 64, 128), (1, 8, 8, 8, 128, 64), (2, 2, 6, 4, 128, 256)])
+def test_dgrad_unshuffled_feeds_convT_bwd(shape):
+    """conv data gradient written coarse-major == unshuffle(conv data gradient), and the
+    ConvTranspose gradient GEMMs on it match autograd."""
+    n, d, h, w, cin, cout = shape          # fine dims of the conv; cin = channels of the convT output
+    torch.manual_seed(11)
+    xc = q(torch.randn(n, cin, d // 2, h // 2, w // 2, device=DEV)).requires_grad_(True)
+    wt = q(torch.randn(cin, cin, 2, 2, 2, device=DEV) / cin ** 0.5).requires_grad_(True)
+    bt = torch.randn(cin, device=DEV, requires_grad=True)
+    wc = q(torch.randn(cout, cin, 3, 3, 3, device=DEV) / (27 * cin) ** 0.5)
+    up = F.conv_transpose3d(xc, wt, bt, stride=2)
+    y = F.conv3d(up, wc, padding=1)
+    dy = q(torch.randn_like(y))
+    y.backward(dy)
+    _, wd = K.pack_conv3_weights(wc)
+    _, wtd = K.pack_convT_weights(wt.detach())
+    scratch, colsum = K.conv3d_k3_dgrad_unshuffled(K.pad_ndhwc(dy), wd)
+    dxc, dwt = K.convT_bwd_from_scratch(scratch, K.pad_ndhwc(xc.detach()), wtd)
+    assert rel(K.unpad_ndhwc(dxc), xc.grad) < 2e-2
+    assert rel(K.unpack_convT_wgrad(dwt, cin, cin), wt.grad) < 2e-2
+    assert rel(colsum[:, 0], bt.grad) < 2e-2
