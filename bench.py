@@ -250,13 +250,14 @@ def run_ours(args):
         if name == "pcrl_conv3d_k3_fprop":
             _, _, n_, d_, h_, w_, ci, co = ints
             d["flops"] += 2.0 * n_ * d_ * h_ * w_ * 27 * ci * co
-        elif name in ("pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_wgrad"):
+        elif name in ("pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_wgrad", "pcrl_conv3d_k3_dgrad_unshuffled"):
             n_, d_, h_, w_, ci, co = ints
             d["flops"] += 2.0 * n_ * d_ * h_ * w_ * 27 * ci * co
     peaks, peak_src = measured_peaks()
-    kmajor_ms = per.get("pcrl_conv3d_k3_fprop", {"ms": 0})["ms"] + per.get("pcrl_conv3d_k3_dgrad", {"ms": 0})["ms"]
-    kmajor_fl = per.get("pcrl_conv3d_k3_fprop", {"flops": 0})["flops"] + per.get("pcrl_conv3d_k3_dgrad", {"flops": 0})["flops"]
-    n_kmajor = per.get("pcrl_conv3d_k3_fprop", {"n": 0})["n"] + per.get("pcrl_conv3d_k3_dgrad", {"n": 0})["n"]
+    fam = ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_dgrad_unshuffled")
+    kmajor_ms = sum(per[k]["ms"] for k in fam if k in per)
+    kmajor_fl = sum(per[k]["flops"] for k in fam if k in per)
+    n_kmajor = sum(per[k]["n"] for k in fam if k in per)
     achieved = kmajor_fl / (kmajor_ms / 1e3) / 1e12 if kmajor_ms > 0 else 0.0
     peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     step_ms_prof = sum(d["ms"] for d in per.values())

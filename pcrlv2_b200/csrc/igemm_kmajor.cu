@@ -19,12 +19,14 @@
 // layers, where a single N=64 MMA only reaches ~46 % of the tensor-pipe rate.
 // Weights stream through a second TMA ring ([cnt*nc x kc] per tap).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+// Warp roles (224 threads): warp 0 = slab TMA producer, warp 6 = filter TMA producer, warp 1 = MMA
+// issuer, warps 2..5 = epilogue.
 // Accumulators live in TMEM, double-buffered when 2*mt*P*nc <= 512 columns so that the epilogue
 // of tile i (tcgen05.ld -> bias -> bf16/fp32 store, per-channel sum / sum-of-squares for the
 // following BatchNorm / InstanceNorm) overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "sm100.cuh"
+#include <stdlib.h>
 
 namespace pcrl {
 
@@ -72,7 +74,7 @@ __device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, long long 
   return c;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(224, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb1,
                     const __grid_constant__ CUtensorMap tb2, const __grid_constant__ CUtensorMap tb3,
                     const IgemmParams p) {
@@ -114,9 +116,9 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
   const int nslab = (p.mode == IG_CONV) ? p.P + 2 : 1;
 
   if (warp == 0) {
-    // =============================== TMA producer (whole warp runs the loop so that every operand
-    // stays warp-uniform; one elected lane issues)
-    int sa = 0, pa = 0, sb = 0, pb = 0;
+    // =============================== TMA producer for the activation slabs (whole warp runs the
+    // loop so that every operand stays warp-uniform; one elected lane issues)
+    int sa = 0, pa = 0;
     const uint32_t a_tx = (p.mode == IG_CONV) ? (uint32_t)(p.nh_box * p.Wp * p.row_bytes)
                                               : (uint32_t)(p.mt * 128 * p.row_bytes);
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -128,12 +130,6 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
           const int q = s - 1;
           mbar_wait(&a_empty[sa], pa ^ 1);
           uint8_t* dst = a_s + (size_t)sa * p.slab_bytes;
-          int cnt = 1, dzr_lo = 0;
-          if (p.mode == IG_CONV) {
-            const int p_lo = max(0, q - 1), p_hi = min(p.P - 1, q + 1);
-            cnt = p_hi - p_lo + 1;
-            dzr_lo = p_lo - (q - 1);
-          }
           if (elect_one()) {
             mbar_expect_tx(&a_full[sa], a_tx);
             if (p.mode == IG_CONV) {
@@ -146,6 +142,24 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
           }
           __syncwarp();
           if (++sa == p.sa) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // =============================== TMA producer for the filter tiles: its own warp, so weight
+    // prefetch runs sb tiles ahead of the MMAs independently of the slab ring
+    int sb = 0, pb = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(p, tile);
+      for (int kb = 0; kb < p.kblocks; kb++) {
+        for (int s = 0; s < nslab; s++) {
+          const int q = s - 1;
+          int cnt = 1, dzr_lo = 0;
+          if (p.mode == IG_CONV) {
+            const int p_lo = max(0, q - 1), p_hi = min(p.P - 1, q + 1);
+            cnt = p_hi - p_lo + 1;
+            dzr_lo = p_lo - (q - 1);
+          }
           const CUtensorMap* tb = cnt == 1 ? &tb1 : (cnt == 2 ? &tb2 : &tb3);
           const uint32_t b_tx = (uint32_t)(cnt * p.nc * p.row_bytes);
           for (int j = 0; j < p.tpg; j++) {
@@ -229,7 +243,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // =============================== epilogue warps (warp w owns TMEM lanes 32*(w%4) .. +31)
     const int quad = warp & 3;
     int it = 0;
@@ -410,16 +424,21 @@ static int finish_and_launch(IgemmLaunch& L, cudaStream_t stream) {
   p.tmem_cols = pow2_cols(p.nbuf * acc_cols);
   const int cnt_max = (p.mode == IG_CONV) ? (p.P >= 3 ? 3 : (p.P == 2 ? 2 : 1)) : 1;
   p.b_bytes = ((cnt_max * p.nc * p.row_bytes + 1023) / 1024) * 1024;
-  // stage counts: fill what shared memory allows, at least 2 + 2
+  // stage counts: a slab lasts nine taps, so two (three when cheap) are enough; everything else goes
+  // to the filter ring, whose depth is what hides the L2 latency of the per-tap weight tiles
   const size_t budget = 212 * 1024;
   p.sa = 2;
   p.sb = 2;
   if ((size_t)p.sa * p.slab_bytes + (size_t)p.sb * p.b_bytes > budget)
     return fail(PCRL_ERR_ARG, "igemm: tile does not fit shared memory (slab %d B, b %d B)",
                 p.slab_bytes, p.b_bytes);
-  while ((size_t)p.sa * p.slab_bytes + (size_t)(p.sb + 1) * p.b_bytes <= budget && p.sb < 4) p.sb++;
-  while ((size_t)(p.sa + 1) * p.slab_bytes + (size_t)p.sb * p.b_bytes <= budget && p.sa < 4) p.sa++;
-  while ((size_t)p.sa * p.slab_bytes + (size_t)(p.sb + 1) * p.b_bytes <= budget && p.sb < 8) p.sb++;
+  if (p.mode == IG_PLAIN) {
+    while ((size_t)(p.sa + 1) * (p.slab_bytes + p.b_bytes) <= budget && p.sa < 6) { p.sa++; p.sb++; }
+  } else {
+    while ((size_t)p.sa * p.slab_bytes + (size_t)(p.sb + 1) * p.b_bytes <= budget && p.sb < 6) p.sb++;
+    if ((size_t)(p.sa + 1) * p.slab_bytes + (size_t)p.sb * p.b_bytes <= budget) p.sa++;
+    while ((size_t)p.sa * p.slab_bytes + (size_t)(p.sb + 1) * p.b_bytes <= budget && p.sb < 10) p.sb++;
+  }
   const size_t smem = (size_t)p.sa * p.slab_bytes + (size_t)p.sb * p.b_bytes +
                       (2 * p.sa + 2 * p.sb + 4) * 8 + 16 + 2 * p.nc * 4 + 1024;
   static bool configured = false;
@@ -429,7 +448,7 @@ static int finish_and_launch(IgemmLaunch& L, cudaStream_t stream) {
     configured = true;
   }
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  igemm_kmajor_kernel<<<(unsigned)grid, 192, smem, stream>>>(L.ta, L.tb[0], L.tb[1], L.tb[2], p);
+  igemm_kmajor_kernel<<<(unsigned)grid, 224, smem, stream>>>(L.ta, L.tb[0], L.tb[1], L.tb[2], p);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -476,6 +495,13 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
     while (p.P > 1 && D % p.P) p.P >>= 1;
   }
   p.mt = (flat >= 256) ? 2 : 1;
+  {  // tuning overrides (experiments only)
+    const char* e = getenv("PCRL_IGEMM_MT");
+    if (e && atoi(e) > 0 && flat >= 128LL * atoi(e)) p.mt = atoi(e);
+    e = getenv("PCRL_IGEMM_P");
+    if (e && atoi(e) > 0 && p.P > 1) { p.P = atoi(e); while (p.P > 1 && D % p.P) p.P >>= 1; }
+    while (p.mt > 1 && p.mt * p.P * p.nc > 512) p.mt >>= 1;
+  }
   p.m_cta = p.mt * 128;
   if (p.P > 1) {
     p.seg_len = p.PL;
