@@ -234,14 +234,19 @@ def run_ours(args):
     e2e_value = world * B * k2 / e2e_t.item()
     h2d = sum(t.numel() * 4 for t in (host[0][0], host[0][1], host[0][2])) + sum(v.numel() * 4 for v in host[0][4])
 
-    if rank != 0:
-        return
-    # ---- per-kernel roofline: one instrumented step (events around every entry point)
+    # ---- per-kernel roofline: one instrumented step (events around every entry point).  Every
+    # rank runs it (the step contains the gradient all-reduce); only rank 0 reports.
     torch.cuda.synchronize()
     _lib.profile[0] = []
     device_step(0)
     torch.cuda.synchronize()
     prof, _lib.profile[0] = _lib.profile[0], None
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     per = {}
     for name, ints, a, b in prof:
         d = per.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
@@ -295,6 +300,8 @@ def run_ours(args):
         "clocks": clocks,
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
