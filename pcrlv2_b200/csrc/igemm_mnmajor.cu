@@ -15,6 +15,7 @@
 // train_3d.py:148 (loss.backward()).
 #include "common.cuh"
 #include "sm100.cuh"
+#include <stdlib.h>
 
 namespace pcrl {
 
@@ -34,6 +35,7 @@ struct WgradParams {
   int b_box_rows;                        // rows written by the X TMA box
   int ntaps;                             // taps per CTA (3 in CONV, 1 in PLAIN)
   int stages, tmem_cols;
+  int stack_dx;                          // CONV: one MMA of N = 3*nc covers the three dx taps
   int m_chunks_total;                    // Cout / mc
   int cout, cin;                         // leading dims of dW: [tap][cout][cin]
   long long rows_total;
@@ -125,6 +127,9 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     const uint64_t b_hi = make_smem_desc(0, p.b_chunk_bytes, 8 * p.b_row_bytes,
                                          p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
     const uint32_t a_step = (uint32_t)(16 * p.a_row_bytes) >> 4, b_step = (uint32_t)(16 * p.b_row_bytes) >> 4;
+    const uint32_t idesc_stack = make_idesc(1, (uint32_t)p.mc, (uint32_t)(3 * p.nc), 1, 1);
+    const uint64_t b_stack_hi = make_smem_desc(0, p.b_row_bytes, 8 * p.b_row_bytes,
+                                               p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
     uint32_t accumulate = 0;
     for (int s = s_begin; s < s_end; s++) {
       mbar_wait(&full[st], ph);
@@ -132,16 +137,30 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
       const uint32_t a_base = smem_u32(smem + (size_t)st * stage_bytes);
       const uint32_t b_base = a_base + a_stage_bytes;
       if (elect_one()) {
-        for (int t = 0; t < p.ntaps; t++) {
-          const int b_row0 = (p.mode == WG_CONV) ? (p.Wp + (t - 1)) : 0;
+        if (p.stack_dx) {
+          // the three dx taps are the same X slab shifted by one row each: with a single channel
+          // chunk per tap they form ONE MN-major operand of N = 3*nc whose chunk stride (LBO) is one
+          // slab row, so a single MMA fills the three accumulators (N = 96 / 192 instead of 3 x 32 / 64)
           uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
-          uint64_t bd = b_hi | (uint64_t)(((b_base + (uint32_t)b_row0 * p.b_row_bytes) >> 4) & 0x3FFF);
-          const uint32_t d = tmem + t * p.nc;
-          umma_bf16(d, ad, bd, idesc, accumulate);
+          uint64_t bd = b_stack_hi | (uint64_t)(((b_base + (uint32_t)(p.Wp - 1) * p.b_row_bytes) >> 4) & 0x3FFF);
+          umma_bf16(tmem, ad, bd, idesc_stack, accumulate);
           for (int ks = 1; ks < p.ksteps; ks++) {
             ad += a_step;
             bd += b_step;
-            umma_bf16(d, ad, bd, idesc, 1u);
+            umma_bf16(tmem, ad, bd, idesc_stack, 1u);
+          }
+        } else {
+          for (int t = 0; t < p.ntaps; t++) {
+            const int b_row0 = (p.mode == WG_CONV) ? (p.Wp + (t - 1)) : 0;
+            uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
+            uint64_t bd = b_hi | (uint64_t)(((b_base + (uint32_t)b_row0 * p.b_row_bytes) >> 4) & 0x3FFF);
+            const uint32_t d = tmem + t * p.nc;
+            umma_bf16(d, ad, bd, idesc, accumulate);
+            for (int ks = 1; ks < p.ksteps; ks++) {
+              ad += a_step;
+              bd += b_step;
+              umma_bf16(d, ad, bd, idesc, 1u);
+            }
           }
         }
         umma_commit(&empty[st]);
@@ -236,6 +255,7 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   const int b_rows_needed = p.ksteps * 16 + p.Wp + 2;
   p.b_chunk_bytes = round_up((b_rows_needed > p.b_box_rows ? b_rows_needed : p.b_box_rows) * p.b_row_bytes, 1024);
   p.ntaps = 3;
+  p.stack_dx = (p.b_chunks == 1 && !getenv("PCRL_WGRAD_NOSTACK")) ? 1 : 0;
   p.m_chunks_total = Cout / p.mc;
   p.cout = Cout; p.cin = Cin; p.dw = dw;
   // split the reduction so that the grid has a few waves
