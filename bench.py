@@ -161,7 +161,7 @@ def run_ours(args):
     torch.manual_seed(42)
     random.seed(42)
     B = args.batch
-    model = PCRLv23d().to(dev).train()
+    model = PCRLv23d(precision=args.precision).to(dev).train()
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, src=0)
@@ -279,9 +279,12 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"LUNA 3D pretrain 64x64x32 + 6x16^3 local views, b={B}/GPU, bf16 "
-                               f"(per-GPU shard of configs[2]: b=256 bf16 on 8xB200)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "tf32",
+        "data": "synthetic",
+        "config": {"workload": (f"LUNA 3D pretrain 64x64x32 + 6x16^3 local views, b={B}/GPU, bf16 "
+                                f"(per-GPU shard of configs[2]: b=256 bf16 on 8xB200)") if args.precision == "bf16" else
+                               (f"LUNA 3D pretrain 64x64x32 + 6x16^3 local views, b={B}, fp32 storage / TF32 tensor-core "
+                                f"operands (configs[1]: b=32 fp32 on 1xB200)"),
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "activation working set per step is tens of GB >> 126 MB L2; two input batches alternate",
                    "algorithmic_gflop_per_sample": round(fl / 1e9, 2)},
@@ -312,6 +315,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="activation storage / tensor-core operand type (fp32 = TF32 MMAs: configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -7,7 +7,9 @@
  *     retains memory), sizes are plain ints, `stream` is a cudaStream_t passed as void*;
  *   - calls are asynchronous on `stream`, never synchronise, and return 0 or a negative code
  *     (PCRL_ERR_*); pcrl_last_error() returns the message of the calling thread's last failure;
- *   - activations are "H-padded NDHWC" bf16: logical (N,C,D,H,W) stored as [N][D][H+1][W][C]
+ *   - `dtype` (PCRL_DTYPE_BF16 / PCRL_DTYPE_F32) is the storage type of activations and packed
+ *     operands: bf16 runs kind::f16 MMAs, fp32 runs kind::tf32 MMAs (fp32 accumulation in both);
+ *   - activations are "H-padded NDHWC": logical (N,C,D,H,W) stored as [N][D][H+1][W][C]
  *     with row h'=0 of every plane all zero (voxel h lives at row h+1).  Producers in this
  *     library write that zero row themselves; a caller-made tensor must honour it;
  *   - 1-channel tensors (network input, masks) are plain fp32 [N][D][H][W].
@@ -24,6 +26,10 @@ extern "C" {
 #define PCRL_ERR_CUDA (-2)
 #define PCRL_ERR_UNSUPPORTED (-3)
 
+/* storage type of activations and tensor-core operands: bf16 (kind::f16 MMA) or fp32 (kind::tf32) */
+#define PCRL_DTYPE_BF16 0
+#define PCRL_DTYPE_F32 1
+
 /* activation codes: models/pcrlv2_model_3d.py:20-27 */
 #define PCRL_ACT_RELU 0
 #define PCRL_ACT_PRELU 1
@@ -39,12 +45,14 @@ int pcrl_version(void);
  * operand) and, if wd != NULL, wd [9][3][Cin][Cout] bf16 with mirrored taps (data-gradient
  * operand).
  * models/pcrlv2_model_3d.py:9 */
-int pcrl_pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, void* stream);
+int pcrl_pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int dtype,
+                            void* stream);
 /* packed weight gradient [27][Cout][Cin] fp32 -> (Cout,Cin,3,3,3) fp32 */
 int pcrl_unpack_conv3_wgrad(const float* gpk, float* g, int Cout, int Cin, void* stream);
 /* nn.ConvTranspose3d.weight (Cin,Cout,2,2,2) fp32 -> wf [(tap,Cout)][Cin] bf16 and
  * wd [Cin][(tap,Cout)] bf16.  models/pcrlv2_model_3d.py:52 */
-int pcrl_pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, void* stream);
+int pcrl_pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, int dtype,
+                            void* stream);
 int pcrl_unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, void* stream);
 
 /* ---- 3x3x3 convolution on tensor cores (tcgen05 implicit GEMM) ---------------------------- */
@@ -55,41 +63,41 @@ int pcrl_unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, void*
  * else 1).  Replaces F.conv3d inside LUConv.forward, models/pcrlv2_model_3d.py:33. */
 int pcrl_conv3d_k3_fprop(const void* x, const void* wf, void* y, double* stats,
                          int stats_per_sample, int out_fp32, int N, int D, int H, int W, int Cin,
-                         int Cout, void* stream);
+                         int Cout, int dtype, void* stream);
 /* dx = conv3d data gradient; dy [N][D][H+1][W][Cout] (pad rows zero), wd from
  * pcrl_pack_conv3_weights, dx [N][D][H+1][W][Cin] bf16.  Autograd of the call above. */
 int pcrl_conv3d_k3_dgrad(const void* dy, const void* wd, void* dx, int N, int D, int H, int W,
-                         int Cin, int Cout, void* stream);
+                         int Cin, int Cout, int dtype, void* stream);
 /* Same data gradient, stored for the ConvTranspose3d(k2,s2) that produced x: coarse-major
  * [N*(D/2)*(H/2+1)*(W/2)][8][Cin] bf16 (pad rows zeroed) -- the operand layout of
  * pcrl_convT3d_k2s2_bwd with g_fine = NULL.  colsum (nullable) [Cin][2] fp64 += per-channel
  * (sum, sum of squares) of dx: column 0 is the ConvTranspose bias gradient. */
 int pcrl_conv3d_k3_dgrad_unshuffled(const void* dy, const void* wd, void* dx_coarse_major,
                                     double* colsum, int N, int D, int H, int W, int Cin, int Cout,
-                                    void* stream);
+                                    int dtype, void* stream);
 /* dw_packed [27][Cout][Cin] fp32 += weight gradient (caller zeroes or keeps a running sum).
  * dy and x must have zero pad rows. */
 int pcrl_conv3d_k3_wgrad(const void* dy, const void* x, float* dw_packed, int N, int D, int H,
-                         int W, int Cin, int Cout, void* stream);
+                         int W, int Cin, int Cout, int dtype, void* stream);
 
 /* ---- Conv3d(1 -> 32) stem (down_tr64.ops.0), models/pcrlv2_model_3d.py:114 ----------------- */
 int pcrl_stem_conv_fprop(const float* x, const float* w, void* y, double* stats,
-                         int stats_per_sample, int N, int D, int H, int W, void* stream);
+                         int stats_per_sample, int N, int D, int H, int W, int dtype, void* stream);
 /* dw (32,1,3,3,3) fp32 += */
 int pcrl_stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int H, int W,
-                         void* stream);
+                         int dtype, void* stream);
 
 /* ---- ConvTranspose3d(k=2, s=2), models/pcrlv2_model_3d.py:52,64 ---------------------------- */
 /* y_fine [N][2D][2H+1][2W][Cout] bf16 = convT(x [N][D][H+1][W][Cin]) + bias (pad rows zeroed). */
 int pcrl_convT3d_k2s2_fprop(const void* x, const void* wf, const float* bias, void* y_fine, int N,
-                            int D, int H, int W, int Cin, int Cout, void* stream);
+                            int D, int H, int W, int Cin, int Cout, int dtype, void* stream);
 /* Backward.  g_fine [N][2D][2H+1][2W][Cout] bf16; scratch [N*D*(H+1)*W][8*Cout] bf16;
  * dx [N][D][H+1][W][Cin] bf16; dw_packed [(tap,Cout)][Cin] fp32 += ; dbias [Cout] fp32 += .
  * x may be NULL together with dw_packed to skip the weight gradient; g_fine may be NULL when
  * scratch already holds the coarse-major gradient (pcrl_conv3d_k3_dgrad_unshuffled). */
 int pcrl_convT3d_k2s2_bwd(const void* g_fine, const void* x, const void* wd, void* scratch,
                           void* dx, float* dw_packed, float* dbias, int N, int D, int H, int W,
-                          int Cin, int Cout, void* stream);
+                          int Cin, int Cout, int dtype, void* stream);
 
 /* ---- normalisation + activation (+ max-pool, + average-pool sums) -------------------------- */
 /* BatchNorm3d / InstanceNorm3d statistics -> scale/shift; updates running stats (BatchNorm) and
@@ -102,14 +110,15 @@ int pcrl_norm_finalize(const double* stats, double count, const float* gamma, co
  * for F.adaptive_avg_pool3d (:67). */
 int pcrl_norm_act_fwd(const void* y, const float* scale, const float* shift, const float* prelu,
                       void* a_out, void* pool_out, float* avg_sum, int per_sample, int act,
-                      int pool, int N, int D, int H, int W, int C, void* stream);
+                      int pool, int N, int D, int H, int W, int C, int dtype, void* stream);
 /* two-pass backward: pass 0 accumulates sums [G][C][3] fp64, pass 1 writes dy. */
 int pcrl_norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gavg,
                       const float* scale, const float* shift, const float* mean,
                       const float* invstd, const float* gamma, const float* prelu, double* sums,
                       void* dy, double count, int per_sample, int act, int pool, int pass, int N,
-                      int D, int H, int W, int C, void* stream);
-int pcrl_zero_pad_rows(void* t, long long planes, int H1, int row_elems, void* stream);
+                      int D, int H, int W, int C, int dtype, void* stream);
+/* zero row h'=0 of `planes` planes; row_bytes = bytes of one (w, c) row */
+int pcrl_zero_pad_rows(void* t, long long planes, int H1, long long row_bytes, void* stream);
 
 /* ---- single-channel heads ------------------------------------------------------------------ */
 /* The N=1 convolutions Conv3d(C->1,k3,p1) (deep_supervision_head.conv1, :60) and Conv3d(64->1,k1)
@@ -117,14 +126,14 @@ int pcrl_zero_pad_rows(void* t, long long planes, int H1, int row_elems, void* s
  * the 1x1x1 conv, 4 zeros) followed by a 27-point gather; backward is the mirror image.
  * w3 (1,C,3,3,3), w1 (1,C,1,1,1) or NULL -> wext [32][C] bf16, wextT [C][32] bf16. */
 int pcrl_head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C,
-                           void* stream);
+                           int dtype, void* stream);
 /* tT [32][rows] fp32 (rows = N*D*(H+1)*W) -> y1 (+ y0) [N][D][H][W] fp32; stats [G][2] fp64 +=
  * (sum, sum of squares) of y1 for the 1-channel norm that follows. */
 int pcrl_head_gather(const float* tT, const float* b3, const float* b1, float* y1, float* y0,
                      double* stats, int stats_per_sample, int N, int D, int H, int W, void* stream);
 /* dT [rows][32] bf16: dT[u][tap] = dy1[u - tap], dT[u][27] = dy0[u] (dy0 may be NULL). */
 int pcrl_head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W,
-                      void* stream);
+                      int dtype, void* stream);
 /* BatchNorm3d(1)/InstanceNorm3d(1) + Sigmoid of the head (:12,27) on fp32 [G][vol]. */
 int pcrl_chan1_sigmoid_fwd(const float* y, const float* scale, const float* shift, float* mask,
                            int per_sample, int G, long long vol, void* stream);
@@ -134,15 +143,15 @@ int pcrl_chan1_sigmoid_bwd(const float* y, const float* mask, const float* dmask
                            void* stream);
 /* x [N][D][H][W] fp32 -> X27 [rows][32] bf16, X27[u][tap] = x[u + tap]: im2col of the 1-channel
  * network input; the stem weight gradient is then pcrl_gemm_tn(dY, X27). */
-int pcrl_im2col27(const float* x, void* out, int N, int D, int H, int W, void* stream);
+int pcrl_im2col27(const float* x, void* out, int N, int D, int H, int W, int dtype, void* stream);
 
-/* ---- plain tensor-core GEMMs (bf16 in, fp32 accumulate) ------------------------------------ */
+/* ---- plain tensor-core GEMMs (bf16 or fp32/tf32 in, fp32 accumulate) ------------------------------------ */
 /* C[rows][cols] = A[rows][K] * B[cols][K]^T (+ bias[col]); ldc in elements.  out_fp32: 0 = bf16,
  * 1 = fp32, 2 = fp32 transposed (C^T[cols][rows], ldc = rows). */
 int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
-                 int cols, int ldc, int out_fp32, void* stream);
+                 int cols, int ldc, int out_fp32, int dtype, void* stream);
 /* C[P][Q] (fp32) += A[rows][P]^T * B[rows][Q] */
-int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q,
+int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, int dtype,
                  void* stream);
 
 /* ---- optimizer: torch.optim.SGD(momentum, weight_decay), train_3d.py:48-51,151 ------------- */

@@ -23,31 +23,31 @@ _D = ctypes.c_double
 # name -> argtypes, mirroring include/pcrl_b200.h (the header is the source of truth; the
 # "not gpu" test-suite checks that every symbol declared there is exported and listed here).
 SIGNATURES = {
-    "pcrl_pack_conv3_weights": [_P, _P, _P, _I, _I, _P],
+    "pcrl_pack_conv3_weights": [_P, _P, _P, _I, _I, _I, _P],
     "pcrl_unpack_conv3_wgrad": [_P, _P, _I, _I, _P],
-    "pcrl_pack_convT_weights": [_P, _P, _P, _I, _I, _P],
+    "pcrl_pack_convT_weights": [_P, _P, _P, _I, _I, _I, _P],
     "pcrl_unpack_convT_wgrad": [_P, _P, _I, _I, _P],
-    "pcrl_conv3d_k3_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "pcrl_conv3d_k3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "pcrl_conv3d_k3_dgrad_unshuffled": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "pcrl_conv3d_k3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "pcrl_stem_conv_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "pcrl_stem_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
-    "pcrl_convT3d_k2s2_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "pcrl_convT3d_k2s2_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_conv3d_k3_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_conv3d_k3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_conv3d_k3_dgrad_unshuffled": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_conv3d_k3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_stem_conv_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_stem_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_convT3d_k2s2_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_convT3d_k2s2_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pcrl_norm_finalize": [_P, _D, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _P],
-    "pcrl_norm_act_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_norm_act_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "pcrl_norm_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I,
-                          _I, _I, _I, _I, _I, _P],
-    "pcrl_zero_pad_rows": [_P, _L, _I, _I, _P],
-    "pcrl_head_pack_weights": [_P, _P, _P, _P, _I, _P],
+                          _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_zero_pad_rows": [_P, _L, _I, _L, _P],
+    "pcrl_head_pack_weights": [_P, _P, _P, _P, _I, _I, _P],
     "pcrl_head_gather": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "pcrl_head_scatter": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "pcrl_head_scatter": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pcrl_chan1_sigmoid_fwd": [_P, _P, _P, _P, _I, _I, _L, _P],
     "pcrl_chan1_sigmoid_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _L, _P],
-    "pcrl_im2col27": [_P, _P, _I, _I, _I, _I, _P],
-    "pcrl_gemm_nt": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
-    "pcrl_gemm_tn": [_P, _P, _P, _L, _I, _I, _P],
+    "pcrl_im2col27": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_gemm_nt": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P],
+    "pcrl_gemm_tn": [_P, _P, _P, _L, _I, _I, _I, _P],
     "pcrl_sgd_flat": [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _P],
 }
 

@@ -22,25 +22,25 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 // launchers defined in igemm_kmajor.cu / igemm_mnmajor.cu / streaming.cu / heads.cu
-int conv3d_k3_igemm(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, cudaStream_t, int);
-int gemm_nt_igemm(const void*, const void*, void*, const float*, long long, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int conv3d_k3_wgrad_igemm(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
-int gemm_tn_igemm(const void*, const void*, float*, long long, int, int, cudaStream_t);
-int pack_conv3_weights(const float*, void*, void*, int, int, cudaStream_t);
+int conv3d_k3_igemm(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, cudaStream_t, int, int);
+int gemm_nt_igemm(const void*, const void*, void*, const float*, long long, int, int, int, int, int, int, int, int, int, cudaStream_t, int);
+int conv3d_k3_wgrad_igemm(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t, int);
+int gemm_tn_igemm(const void*, const void*, float*, long long, int, int, cudaStream_t, int);
+int pack_conv3_weights(const float*, void*, void*, int, int, int, cudaStream_t);
 int unpack_conv3_wgrad(const float*, float*, int, int, cudaStream_t);
-int pack_convT_weights(const float*, void*, void*, int, int, cudaStream_t);
+int pack_convT_weights(const float*, void*, void*, int, int, int, cudaStream_t);
 int unpack_convT_wgrad(const float*, float*, int, int, cudaStream_t);
-int stem_conv_fprop(const float*, const float*, void*, double*, int, int, int, int, int, cudaStream_t);
-int stem_conv_wgrad(const void*, const float*, float*, int, int, int, int, cudaStream_t);
+int stem_conv_fprop(const float*, const float*, void*, double*, int, int, int, int, int, int, cudaStream_t);
+int stem_conv_wgrad(const void*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int norm_finalize(const double*, double, const float*, const float*, const float*, float*, float*, long long*, float, float, float*, float*, float*, float*, int, int, cudaStream_t);
-int norm_act_fwd(const void*, const float*, const float*, const float*, void*, void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
-int norm_act_bwd(const void*, const void*, const void*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, double*, void*, double, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int zero_pad_rows(void*, long long, int, int, cudaStream_t);
-int convT_unshuffle(const void*, void*, float*, int, int, int, int, int, cudaStream_t);
-int head_pack_weights(const float*, const float*, void*, void*, int, cudaStream_t);
+int norm_act_fwd(const void*, const float*, const float*, const float*, void*, void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int norm_act_bwd(const void*, const void*, const void*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, double*, void*, double, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int zero_pad_rows(void*, long long, int, long long, cudaStream_t);
+int convT_unshuffle(const void*, void*, float*, int, int, int, int, int, int, cudaStream_t);
+int head_pack_weights(const float*, const float*, void*, void*, int, int, cudaStream_t);
 int head_gather(const float*, const float*, const float*, float*, float*, double*, int, int, int, int, int, cudaStream_t);
-int head_scatter(const float*, const float*, void*, int, int, int, int, cudaStream_t);
-int im2col27(const float*, void*, int, int, int, int, cudaStream_t);
+int head_scatter(const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
+int im2col27(const float*, void*, int, int, int, int, int, cudaStream_t);
 int chan1_sigmoid_fwd(const float*, const float*, const float*, float*, int, int, long long, cudaStream_t);
 int chan1_sigmoid_bwd(const float*, const float*, const float*, const float*, const float*, const float*, double*, float*, double, int, int, int, long long, cudaStream_t);
 int sgd_flat(float*, const float*, float*, const long long*, const int*, const int*, int, float, float, float, float, cudaStream_t);
@@ -54,19 +54,21 @@ using namespace pcrl;
 extern "C" {
 
 const char* pcrl_last_error(void) { return last_error_buf(); }
-int pcrl_version(void) { return 100; }
+int pcrl_version(void) { return 101; }
+static inline int esz(int dtype) { return dtype == PCRL_DTYPE_F32 ? 4 : 2; }
+#define CHECK_DTYPE(d) PCRL_REQUIRE((d) == PCRL_DTYPE_BF16 || (d) == PCRL_DTYPE_F32, "%s: unknown dtype %d", __func__, (d))
 
-int pcrl_pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, void* stream) {
-  NONNULL(w); NONNULL(wf);
-  return pack_conv3_weights(w, wf, wd, Cout, Cin, ST(stream));
+int pcrl_pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int dtype, void* stream) {
+  NONNULL(w); NONNULL(wf); CHECK_DTYPE(dtype);
+  return pack_conv3_weights(w, wf, wd, Cout, Cin, dtype, ST(stream));
 }
 int pcrl_unpack_conv3_wgrad(const float* gpk, float* g, int Cout, int Cin, void* stream) {
   NONNULL(gpk); NONNULL(g);
   return unpack_conv3_wgrad(gpk, g, Cout, Cin, ST(stream));
 }
-int pcrl_pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, void* stream) {
-  NONNULL(w); NONNULL(wf); NONNULL(wd);
-  return pack_convT_weights(w, wf, wd, Cin, Cout, ST(stream));
+int pcrl_pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, int dtype, void* stream) {
+  NONNULL(w); NONNULL(wf); NONNULL(wd); CHECK_DTYPE(dtype);
+  return pack_convT_weights(w, wf, wd, Cin, Cout, dtype, ST(stream));
 }
 int pcrl_unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, void* stream) {
   NONNULL(gpk); NONNULL(g);
@@ -74,70 +76,71 @@ int pcrl_unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, void*
 }
 
 int pcrl_conv3d_k3_fprop(const void* x, const void* wf, void* y, double* stats, int stats_per_sample,
-                         int out_fp32, int N, int D, int H, int W, int Cin, int Cout, void* stream) {
-  NONNULL(x); NONNULL(wf); NONNULL(y);
-  return conv3d_k3_igemm(x, wf, y, stats, stats_per_sample, out_fp32, N, D, H, W, Cin, Cout, ST(stream), 0);
+                         int out_fp32, int N, int D, int H, int W, int Cin, int Cout, int dtype, void* stream) {
+  NONNULL(x); NONNULL(wf); NONNULL(y); CHECK_DTYPE(dtype);
+  return conv3d_k3_igemm(x, wf, y, stats, stats_per_sample, out_fp32, N, D, H, W, Cin, Cout, ST(stream), 0, dtype);
 }
 int pcrl_conv3d_k3_dgrad(const void* dy, const void* wd, void* dx, int N, int D, int H, int W,
-                         int Cin, int Cout, void* stream) {
-  NONNULL(dy); NONNULL(wd); NONNULL(dx);
+                         int Cin, int Cout, int dtype, void* stream) {
+  NONNULL(dy); NONNULL(wd); NONNULL(dx); CHECK_DTYPE(dtype);
   // the data gradient is a 3x3x3 convolution of dy (Cout channels) with the mirrored, transposed
   // filter: same kernel with the channel roles swapped
-  return conv3d_k3_igemm(dy, wd, dx, nullptr, 0, 0, N, D, H, W, Cout, Cin, ST(stream), 0);
+  return conv3d_k3_igemm(dy, wd, dx, nullptr, 0, 0, N, D, H, W, Cout, Cin, ST(stream), 0, dtype);
 }
 int pcrl_conv3d_k3_dgrad_unshuffled(const void* dy, const void* wd, void* dx_coarse_major, double* colsum,
-                                    int N, int D, int H, int W, int Cin, int Cout, void* stream) {
-  NONNULL(dy); NONNULL(wd); NONNULL(dx_coarse_major);
-  int rc = conv3d_k3_igemm(dy, wd, dx_coarse_major, colsum, 0, 0, N, D, H, W, Cout, Cin, ST(stream), 1);
+                                    int N, int D, int H, int W, int Cin, int Cout, int dtype, void* stream) {
+  NONNULL(dy); NONNULL(wd); NONNULL(dx_coarse_major); CHECK_DTYPE(dtype);
+  int rc = conv3d_k3_igemm(dy, wd, dx_coarse_major, colsum, 0, 0, N, D, H, W, Cout, Cin, ST(stream), 1, dtype);
   if (rc) return rc;
   // pad rows (coarse h' = 0) of the coarse-major tensor feed the ConvTranspose GEMMs: zero them
-  return zero_pad_rows(dx_coarse_major, (long long)N * (D / 2), H / 2 + 1, (W / 2) * 8 * Cin, ST(stream));
+  return zero_pad_rows(dx_coarse_major, (long long)N * (D / 2), H / 2 + 1,
+                       (long long)(W / 2) * 8 * Cin * esz(dtype), ST(stream));
 }
 int pcrl_conv3d_k3_wgrad(const void* dy, const void* x, float* dw_packed, int N, int D, int H, int W,
-                         int Cin, int Cout, void* stream) {
-  NONNULL(dy); NONNULL(x); NONNULL(dw_packed);
-  return conv3d_k3_wgrad_igemm(dy, x, dw_packed, N, D, H, W, Cin, Cout, ST(stream));
+                         int Cin, int Cout, int dtype, void* stream) {
+  NONNULL(dy); NONNULL(x); NONNULL(dw_packed); CHECK_DTYPE(dtype);
+  return conv3d_k3_wgrad_igemm(dy, x, dw_packed, N, D, H, W, Cin, Cout, ST(stream), dtype);
 }
 
 int pcrl_stem_conv_fprop(const float* x, const float* w, void* y, double* stats, int stats_per_sample,
-                         int N, int D, int H, int W, void* stream) {
-  NONNULL(x); NONNULL(w); NONNULL(y);
-  return stem_conv_fprop(x, w, y, stats, stats_per_sample, N, D, H, W, ST(stream));
+                         int N, int D, int H, int W, int dtype, void* stream) {
+  NONNULL(x); NONNULL(w); NONNULL(y); CHECK_DTYPE(dtype);
+  return stem_conv_fprop(x, w, y, stats, stats_per_sample, N, D, H, W, dtype, ST(stream));
 }
 int pcrl_stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int H, int W,
-                         void* stream) {
-  NONNULL(dy); NONNULL(x); NONNULL(dw);
-  return stem_conv_wgrad(dy, x, dw, N, D, H, W, ST(stream));
+                         int dtype, void* stream) {
+  NONNULL(dy); NONNULL(x); NONNULL(dw); CHECK_DTYPE(dtype);
+  return stem_conv_wgrad(dy, x, dw, N, D, H, W, dtype, ST(stream));
 }
 
 int pcrl_convT3d_k2s2_fprop(const void* x, const void* wf, const float* bias, void* y_fine, int N,
-                            int D, int H, int W, int Cin, int Cout, void* stream) {
-  NONNULL(x); NONNULL(wf); NONNULL(y_fine);
+                            int D, int H, int W, int Cin, int Cout, int dtype, void* stream) {
+  NONNULL(x); NONNULL(wf); NONNULL(y_fine); CHECK_DTYPE(dtype);
   const long long rows = (long long)N * D * (H + 1) * W;
-  int rc = gemm_nt_igemm(x, wf, y_fine, bias, rows, Cin, 8 * Cout, Cout, 0, /*OUT_CONVT*/ 2, D, H, W,
-                         Cout, ST(stream));
+  int rc = gemm_nt_igemm(x, wf, y_fine, bias, rows, Cin, 8 * Cout, Cout, dtype == PCRL_DTYPE_F32, /*OUT_CONVT*/ 2,
+                         D, H, W, Cout, ST(stream), dtype);
   if (rc) return rc;
-  return zero_pad_rows(y_fine, (long long)N * 2 * D, 2 * H + 1, 2 * W * Cout, ST(stream));
+  return zero_pad_rows(y_fine, (long long)N * 2 * D, 2 * H + 1, (long long)2 * W * Cout * esz(dtype), ST(stream));
 }
 int pcrl_convT3d_k2s2_bwd(const void* g_fine, const void* x, const void* wd, void* scratch, void* dx,
                           float* dw_packed, float* dbias, int N, int D, int H, int W, int Cin,
-                          int Cout, void* stream) {
-  NONNULL(scratch);
+                          int Cout, int dtype, void* stream) {
+  NONNULL(scratch); CHECK_DTYPE(dtype);
   const long long rows = (long long)N * D * (H + 1) * W;
   int rc = PCRL_OK;
   if (g_fine) {   // otherwise `scratch` already holds the coarse-major gradient
-    rc = convT_unshuffle(g_fine, scratch, dbias, N, D, H, W, Cout, ST(stream));
+    rc = convT_unshuffle(g_fine, scratch, dbias, N, D, H, W, Cout, dtype, ST(stream));
     if (rc) return rc;
   }
   if (dx) {
     NONNULL(wd);
-    rc = gemm_nt_igemm(scratch, wd, dx, nullptr, rows, 8 * Cout, Cin, Cin, 0, /*OUT_ROWS*/ 1, 0, 0, 0, 0,
-                       ST(stream));
+    rc = gemm_nt_igemm(scratch, wd, dx, nullptr, rows, 8 * Cout, Cin, Cin, dtype == PCRL_DTYPE_F32, /*OUT_ROWS*/ 1,
+                       0, 0, 0, 0, ST(stream), dtype);
     if (rc) return rc;
   }
   if (dw_packed) {
     NONNULL(x);
-    rc = gemm_tn_igemm(scratch, x, dw_packed, rows, 8 * Cout, Cin, ST(stream));
+    rc = gemm_tn_igemm(scratch, x, dw_packed, rows, 8 * Cout, Cin, ST(stream), dtype);
     if (rc) return rc;
   }
   return PCRL_OK;
@@ -153,38 +156,38 @@ int pcrl_norm_finalize(const double* stats, double count, const float* gamma, co
 }
 int pcrl_norm_act_fwd(const void* y, const float* scale, const float* shift, const float* prelu,
                       void* a_out, void* pool_out, float* avg_sum, int per_sample, int act, int pool,
-                      int N, int D, int H, int W, int C, void* stream) {
-  NONNULL(y); NONNULL(scale); NONNULL(shift);
+                      int N, int D, int H, int W, int C, int dtype, void* stream) {
+  NONNULL(y); NONNULL(scale); NONNULL(shift); CHECK_DTYPE(dtype);
   return norm_act_fwd(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H,
-                      W, C, ST(stream));
+                      W, C, dtype, ST(stream));
 }
 int pcrl_norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gavg,
                       const float* scale, const float* shift, const float* mean, const float* invstd,
                       const float* gamma, const float* prelu, double* sums, void* dy, double count,
                       int per_sample, int act, int pool, int pass, int N, int D, int H, int W, int C,
-                      void* stream) {
-  NONNULL(y); NONNULL(scale); NONNULL(shift); NONNULL(mean); NONNULL(invstd); NONNULL(sums);
+                      int dtype, void* stream) {
+  NONNULL(y); NONNULL(scale); NONNULL(shift); NONNULL(mean); NONNULL(invstd); NONNULL(sums); CHECK_DTYPE(dtype);
   if (pass == 1) { NONNULL(dy); NONNULL(gamma); }
   return norm_act_bwd(y, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu, sums, dy, count,
-                      per_sample, act, pool, pass, N, D, H, W, C, ST(stream));
+                      per_sample, act, pool, pass, N, D, H, W, C, dtype, ST(stream));
 }
-int pcrl_zero_pad_rows(void* t, long long planes, int H1, int row_elems, void* stream) {
+int pcrl_zero_pad_rows(void* t, long long planes, int H1, long long row_bytes, void* stream) {
   NONNULL(t);
-  return zero_pad_rows(t, planes, H1, row_elems, ST(stream));
+  return zero_pad_rows(t, planes, H1, row_bytes, ST(stream));
 }
 
-int pcrl_head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C, void* stream) {
-  NONNULL(w3); NONNULL(wext); NONNULL(wextT);
-  return head_pack_weights(w3, w1, wext, wextT, C, ST(stream));
+int pcrl_head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C, int dtype, void* stream) {
+  NONNULL(w3); NONNULL(wext); NONNULL(wextT); CHECK_DTYPE(dtype);
+  return head_pack_weights(w3, w1, wext, wextT, C, dtype, ST(stream));
 }
 int pcrl_head_gather(const float* tT, const float* b3, const float* b1, float* y1, float* y0, double* stats,
                      int stats_per_sample, int N, int D, int H, int W, void* stream) {
   NONNULL(tT); NONNULL(b3); NONNULL(y1);
   return head_gather(tT, b3, b1, y1, y0, stats, stats_per_sample, N, D, H, W, ST(stream));
 }
-int pcrl_head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W, void* stream) {
-  NONNULL(dy1); NONNULL(dT);
-  return head_scatter(dy1, dy0, dT, N, D, H, W, ST(stream));
+int pcrl_head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W, int dtype, void* stream) {
+  NONNULL(dy1); NONNULL(dT); CHECK_DTYPE(dtype);
+  return head_scatter(dy1, dy0, dT, N, D, H, W, dtype, ST(stream));
 }
 int pcrl_chan1_sigmoid_fwd(const float* y, const float* scale, const float* shift, float* mask, int per_sample,
                            int G, long long vol, void* stream) {
@@ -198,20 +201,20 @@ int pcrl_chan1_sigmoid_bwd(const float* y, const float* mask, const float* dmask
   if (pass == 1) { NONNULL(dy); NONNULL(gamma); }
   return chan1_sigmoid_bwd(y, mask, dmask, mean, invstd, gamma, sums, dy, count, per_sample, pass, G, vol, ST(stream));
 }
-int pcrl_im2col27(const float* x, void* out, int N, int D, int H, int W, void* stream) {
-  NONNULL(x); NONNULL(out);
-  return im2col27(x, out, N, D, H, W, ST(stream));
+int pcrl_im2col27(const float* x, void* out, int N, int D, int H, int W, int dtype, void* stream) {
+  NONNULL(x); NONNULL(out); CHECK_DTYPE(dtype);
+  return im2col27(x, out, N, D, H, W, dtype, ST(stream));
 }
 
 int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
-                 int cols, int ldc, int out_fp32, void* stream) {
-  NONNULL(a); NONNULL(b); NONNULL(c);
+                 int cols, int ldc, int out_fp32, int dtype, void* stream) {
+  NONNULL(a); NONNULL(b); NONNULL(c); CHECK_DTYPE(dtype);
   return gemm_nt_igemm(a, b, c, bias, rows, K, cols, ldc, out_fp32 != 0, out_fp32 == 2 ? /*OUT_ROWS_T*/ 3 : /*OUT_ROWS*/ 1,
-                       0, 0, 0, 0, ST(stream));
+                       0, 0, 0, 0, ST(stream), dtype);
 }
-int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, void* stream) {
-  NONNULL(a); NONNULL(b); NONNULL(c);
-  return gemm_tn_igemm(a, b, c, rows, P, Q, ST(stream));
+int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, int dtype, void* stream) {
+  NONNULL(a); NONNULL(b); NONNULL(c); CHECK_DTYPE(dtype);
+  return gemm_tn_igemm(a, b, c, rows, P, Q, ST(stream), dtype);
 }
 
 int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf, const long long* seg_offsets,

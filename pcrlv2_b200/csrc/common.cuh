@@ -80,6 +80,17 @@ inline int encode_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const 
   return PCRL_OK;
 }
 
+// Round-to-nearest fp32 -> tf32 (10-bit mantissa).  The tensor core truncates fp32 operands to
+// tf32; storing operands already rounded makes that truncation exact, halves the operand error
+// and removes its bias.
+#ifdef __CUDACC__
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+#endif
+
 inline int num_sms() {
   static int sms = 0;
   if (!sms) {

@@ -17,19 +17,41 @@
 
 namespace pcrl {
 
+typedef __nv_bfloat16 bf16_t;
+__device__ __forceinline__ void cvt_store1(bf16_t* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void cvt_store1(float* p, float v) { *p = rna_tf32(v); }
+// store 32 consecutive values of one row
+__device__ __forceinline__ void store_row32(bf16_t* p, const float (&v)[32]) {
+  uint4* o = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint4 u;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; j++) hh[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+    o[i] = u;
+  }
+}
+__device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
+  float4* o = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    o[i] = make_float4(rna_tf32(v[4 * i]), rna_tf32(v[4 * i + 1]), rna_tf32(v[4 * i + 2]), rna_tf32(v[4 * i + 3]));
+}
+
 // w3 (1,C,3,3,3) fp32 [+ w1 (1,C,1,1,1)] -> wext [32][C] bf16 (rows = taps, row 27 = w1) and
 // wextT [C][32] bf16
+template <typename T>
 __global__ void head_pack_kernel(const float* __restrict__ w3, const float* __restrict__ w1,
-                                 __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ wextT, int C) {
+                                 T* __restrict__ wext, T* __restrict__ wextT, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 32 * C) return;
   const int tap = i / C, c = i % C;
   float v = 0.f;
   if (tap < 27) v = w3[c * 27 + tap];
   else if (tap == 27 && w1) v = w1[c];
-  const __nv_bfloat16 b = __float2bfloat16(v);
-  wext[tap * C + c] = b;
-  wextT[c * 32 + tap] = b;
+  cvt_store1(&wext[tap * C + c], v);
+  cvt_store1(&wextT[c * 32 + tap], v);
 }
 
 // tT [32][rows] fp32 (rows = N*D*(H+1)*W, H-padded order) -> y1 [N][D][H][W] (+ y0), and the
@@ -89,9 +111,10 @@ head_gather_kernel(const float* __restrict__ tT, const float* __restrict__ b3, c
 }
 
 // dT [rows][32] bf16: dT[u][tap] = dy1[u - tap] (0 outside / on pad rows), dT[u][27] = dy0[u]
+template <typename T>
 __global__ void __launch_bounds__(256)
 head_scatter_kernel(const float* __restrict__ dy1, const float* __restrict__ dy0,
-                    __nv_bfloat16* __restrict__ dT, int N, int D, int H, int W) {
+                    T* __restrict__ dT, int N, int D, int H, int W) {
   const long long rows = (long long)N * D * (H + 1) * W;
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
        r += (long long)gridDim.x * blockDim.x) {
@@ -121,22 +144,15 @@ head_scatter_kernel(const float* __restrict__ dy1, const float* __restrict__ dy0
       }
       if (dy0) v[27] = __ldg(&dy0[(((size_t)n * D + d) * H + h) * W + w]);
     }
-    uint4* o = reinterpret_cast<uint4*>(dT + (size_t)r * 32);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      uint4 u;
-      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; j++) hh[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-      o[i] = u;
-    }
+    store_row32(dT + (size_t)r * 32, v);
   }
 }
 
 // x [N][D][H][W] fp32 (C = 1) -> X27 [rows][32] bf16 in H-padded row order:
 // X27[u][tap] = x[u + tap] (0 outside, pad rows all zero).  Feeds the stem weight gradient GEMM.
+template <typename T>
 __global__ void __launch_bounds__(256)
-im2col27_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int D, int H, int W) {
+im2col27_kernel(const float* __restrict__ x, T* __restrict__ out, int N, int D, int H, int W) {
   const long long rows = (long long)N * D * (H + 1) * W;
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
        r += (long long)gridDim.x * blockDim.x) {
@@ -165,15 +181,7 @@ im2col27_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, in
         }
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(out + (size_t)r * 32);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      uint4 u;
-      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; j++) hh[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-      o[i] = u;
-    }
+    store_row32(out + (size_t)r * 32, v);
   }
 }
 
@@ -284,8 +292,9 @@ static inline unsigned blocks_for(long long items, int per_block, int cap) {
   return (unsigned)b;
 }
 
-int head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C, cudaStream_t s) {
-  head_pack_kernel<<<(32 * C + 255) / 256, 256, 0, s>>>(w3, w1, (__nv_bfloat16*)wext, (__nv_bfloat16*)wextT, C);
+int head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C, int dtype, cudaStream_t s) {
+  if (dtype == PCRL_DTYPE_F32) head_pack_kernel<float><<<(32 * C + 255) / 256, 256, 0, s>>>(w3, w1, (float*)wext, (float*)wextT, C);
+  else head_pack_kernel<bf16_t><<<(32 * C + 255) / 256, 256, 0, s>>>(w3, w1, (bf16_t*)wext, (bf16_t*)wextT, C);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -298,15 +307,17 @@ int head_gather(const float* tT, const float* b3, const float* b1, float* y1, fl
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
-int head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W, cudaStream_t s) {
+int head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W, int dtype, cudaStream_t s) {
   const long long rows = (long long)N * D * (H + 1) * W;
-  head_scatter_kernel<<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(dy1, dy0, (__nv_bfloat16*)dT, N, D, H, W);
+  if (dtype == PCRL_DTYPE_F32) head_scatter_kernel<float><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(dy1, dy0, (float*)dT, N, D, H, W);
+  else head_scatter_kernel<bf16_t><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(dy1, dy0, (bf16_t*)dT, N, D, H, W);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
-int im2col27(const float* x, void* out, int N, int D, int H, int W, cudaStream_t s) {
+int im2col27(const float* x, void* out, int N, int D, int H, int W, int dtype, cudaStream_t s) {
   const long long rows = (long long)N * D * (H + 1) * W;
-  im2col27_kernel<<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(x, (__nv_bfloat16*)out, N, D, H, W);
+  if (dtype == PCRL_DTYPE_F32) im2col27_kernel<float><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(x, (float*)out, N, D, H, W);
+  else im2col27_kernel<bf16_t><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(x, (bf16_t*)out, N, D, H, W);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

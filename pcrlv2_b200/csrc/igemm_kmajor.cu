@@ -41,6 +41,7 @@ struct IgemmParams {
   // tiling
   int m_cta, mt, P, nc, kc, row_bytes, kblocks, tpg;
   int slab_bytes, b_bytes, sa, sb, nbuf, tmem_cols;
+  int tf32;                   // operands are fp32 in memory, MMA kind::tf32 (K = 8 per instruction)
   int tiles_per_group, groups, col_chunks, nsamples;
   long long total_tiles;
   int seg_len;                // rows of one segment that belong to this tile family
@@ -52,6 +53,12 @@ struct IgemmParams {
   const float* bias;
   double* stats;
 };
+
+__device__ __forceinline__ void umma_any(int tf32, uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc,
+                                         uint32_t acc) {
+  if (tf32) umma_tf32(d, ad, bd, idesc, acc);
+  else umma_bf16(d, ad, bd, idesc, acc);
+}
 
 __device__ __forceinline__ int floordiv(int a, int b) {
   int q = a / b;
@@ -181,7 +188,8 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     const uint32_t layout = (p.row_bytes == 128) ? LAYOUT_SW128 : LAYOUT_SW64;
     const uint64_t desc_hi = make_smem_desc(0, 16, 8 * p.row_bytes, layout);
     const int ksteps = p.row_bytes / 32;
-    const uint32_t idesc_nc = make_idesc(1, 128, (uint32_t)p.nc, 0, 0);
+    const uint32_t fmt = p.tf32 ? 2u : 1u;
+    const uint32_t idesc_nc = make_idesc(fmt, 128, (uint32_t)p.nc, 0, 0);
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
       const TileCoord tc = tile_coord(p, tile);
@@ -202,8 +210,8 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
           }
           // the block of output plane q+1 is touched for the first time by this slab
           const bool has_new = (kb == 0) && (p.mode != IG_CONV || q + 1 <= p.P - 1);
-          const uint32_t idesc_all = make_idesc(1, 128, (uint32_t)(cnt * p.nc), 0, 0);
-          const uint32_t idesc_old = make_idesc(1, 128, (uint32_t)((cnt > 1 ? cnt - 1 : 1) * p.nc), 0, 0);
+          const uint32_t idesc_all = make_idesc(fmt, 128, (uint32_t)(cnt * p.nc), 0, 0);
+          const uint32_t idesc_old = make_idesc(fmt, 128, (uint32_t)((cnt > 1 ? cnt - 1 : 1) * p.nc), 0, 0);
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_base = smem_u32(a_s + (size_t)sa * p.slab_bytes);
           for (int j = 0; j < p.tpg; j++) {
@@ -222,13 +230,13 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
                 int ks = 0;
                 if (first) {
                   // split: old blocks accumulate, the new block (last of the range) is overwritten
-                  if (cnt > 1) umma_bf16(d_addr, ad0, bd0, idesc_old, 1u);
+                  if (cnt > 1) umma_any(p.tf32, d_addr, ad0, bd0, idesc_old, 1u);
                   const uint32_t boff = (uint32_t)((cnt - 1) * p.nc) * p.row_bytes;
-                  umma_bf16(d_addr + (uint32_t)((cnt - 1) * p.nc), ad0, bd0 + (boff >> 4), idesc_nc, 0u);
+                  umma_any(p.tf32, d_addr + (uint32_t)((cnt - 1) * p.nc), ad0, bd0 + (boff >> 4), idesc_nc, 0u);
                   ks = 1;
                 }
                 for (; ks < ksteps; ks++)
-                  umma_bf16(d_addr, ad0 + 2 * ks, bd0 + 2 * ks, idesc_all, 1u);
+                  umma_any(p.tf32, d_addr, ad0 + 2 * ks, bd0 + 2 * ks, idesc_all, 1u);
               }
               umma_commit(&b_empty[sb]);
             }
@@ -335,6 +343,11 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
                 for (int i = 0; i < 32; i++) o[(size_t)(co0 + c + i) * p.ldc] = y[i];
               }
             } else if (p.out_fp32) {
+              if (p.out_mode == OUT_CONVT || p.out_mode == OUT_UNSHUFFLE) {
+                // these outputs are tensor-core operands of the next kernel: store tf32-rounded
+#pragma unroll
+                for (int i = 0; i < 32; i++) y[i] = rna_tf32(y[i]);
+              }
               if (valid) {
                 float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c);
 #pragma unroll
@@ -454,13 +467,20 @@ static int finish_and_launch(IgemmLaunch& L, cudaStream_t stream) {
 }
 
 // B operand maps: packed weights viewed as (K, cols, taps) bf16, boxes (kc, nc, cnt), cnt = 1..3
+static inline CUtensorMapDataType tma_dtype(int tf32) {
+  return tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+static inline CUtensorMapSwizzle tma_swizzle(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+}
+
 static int make_b_maps(IgemmLaunch& L, const void* w, int K, int cols, int taps) {
+  const uint64_t elt = L.p.tf32 ? 4 : 2;
   for (int cnt = 1; cnt <= 3; cnt++) {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)cols, (uint64_t)taps};
-    uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)K * cols * 2};
+    uint64_t str[2] = {(uint64_t)K * elt, (uint64_t)K * cols * elt};
     uint32_t box[3] = {(uint32_t)L.p.kc, (uint32_t)L.p.nc, (uint32_t)(cnt <= taps ? cnt : 1)};
-    int rc = encode_map(&L.tb[cnt - 1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w, dims, str, box,
-                        L.p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    int rc = encode_map(&L.tb[cnt - 1], tma_dtype(L.p.tf32), 3, w, dims, str, box, tma_swizzle(L.p.row_bytes));
     if (rc) return rc;
   }
   return PCRL_OK;
@@ -472,8 +492,14 @@ static int make_b_maps(IgemmLaunch& L, const void* w, int K, int cols, int taps)
 //   stats (optional): [Cout][2] (or [N][Cout][2]) fp64, ACCUMULATED (caller zeroes)
 int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int stats_per_sample,
                     int out_fp32, int N, int D, int H, int W, int Cin, int Cout,
-                    cudaStream_t stream, int unshuffle) {
-  PCRL_REQUIRE(Cin == 32 || Cin % 64 == 0, "conv3d_k3: Cin=%d must be 32 or a multiple of 64", Cin);
+                    cudaStream_t stream, int unshuffle, int dtype) {
+  const int tf32 = dtype == PCRL_DTYPE_F32;
+  if (tf32) {
+    PCRL_REQUIRE(Cin % 32 == 0, "conv3d_k3 (fp32): Cin=%d must be a multiple of 32", Cin);
+    out_fp32 = 1;
+  } else {
+    PCRL_REQUIRE(Cin == 32 || Cin % 64 == 0, "conv3d_k3: Cin=%d must be 32 or a multiple of 64", Cin);
+  }
   PCRL_REQUIRE(Cout % 32 == 0, "conv3d_k3: Cout=%d must be a multiple of 32", Cout);
   PCRL_REQUIRE(W + 1 <= 256 && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_k3: bad dims");
   IgemmLaunch L;
@@ -481,8 +507,10 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
   IgemmParams& p = L.p;
   p.mode = IG_CONV;
   p.W = W; p.Wp = W + 1; p.H1 = H + 1; p.D = D; p.MR = D * (H + 1); p.PL = p.H1 * p.Wp;
-  p.kc = (Cin == 32) ? 32 : 64;
-  p.row_bytes = p.kc * 2;
+  p.tf32 = tf32;
+  const int elt = tf32 ? 4 : 2;
+  p.kc = tf32 ? 32 : ((Cin == 32) ? 32 : 64);
+  p.row_bytes = p.kc * elt;
   p.kblocks = Cin / p.kc;
   p.tpg = 9;
   p.nc = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
@@ -519,16 +547,15 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
   p.slab_bytes = ((p.nh_box * p.Wp * p.row_bytes + 1023) / 1024) * 1024;
   p.out_mode = unshuffle ? OUT_UNSHUFFLE : OUT_FLAT; p.out_fp32 = out_fp32; p.ldc = Cout; p.cout_total = Cout;
   if (unshuffle) {
-    PCRL_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && !out_fp32, "conv3d_k3: unshuffle needs even dims, bf16");
+    PCRL_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "conv3d_k3: the coarse-major (unshuffled) output needs even dims");
     p.ct_D = D / 2; p.ct_H = H / 2; p.ct_W = W / 2;
   }
   p.has_stats = stats != nullptr; p.stats_per_sample = stats_per_sample;
   p.out = y; p.stats = stats;
   uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)p.MR, (uint64_t)N};
-  uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)p.MR * W * Cin * 2};
+  uint64_t str[3] = {(uint64_t)Cin * elt, (uint64_t)W * Cin * elt, (uint64_t)p.MR * W * Cin * elt};
   uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.Wp, (uint32_t)p.nh_box, 1};
-  int rc = encode_map(&L.ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, str, box,
-                      p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+  int rc = encode_map(&L.ta, tma_dtype(tf32), 4, x, dims, str, box, tma_swizzle(p.row_bytes));
   if (rc) return rc;
   rc = make_b_maps(L, w, Cin, Cout, 27);
   if (rc) return rc;
@@ -540,15 +567,23 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
 // (tap, cout) columns of a ConvTranspose3d(k=2,s=2) to the fine H-padded NDHWC tensor.
 int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
                   int cols, int ldc, int out_fp32, int out_mode, int ct_D, int ct_H, int ct_W,
-                  int ct_cout, cudaStream_t stream) {
-  PCRL_REQUIRE(K % 64 == 0 || K == 32, "gemm_nt: K=%d must be 32 or a multiple of 64", K);
+                  int ct_cout, cudaStream_t stream, int dtype) {
+  const int tf32 = dtype == PCRL_DTYPE_F32;
+  if (tf32) {
+    PCRL_REQUIRE(K % 32 == 0, "gemm_nt (fp32): K=%d must be a multiple of 32", K);
+    out_fp32 = 1;
+  } else {
+    PCRL_REQUIRE(K % 64 == 0 || K == 32, "gemm_nt: K=%d must be 32 or a multiple of 64", K);
+  }
   PCRL_REQUIRE(cols % 32 == 0, "gemm_nt: cols=%d must be a multiple of 32", cols);
   PCRL_REQUIRE(rows < (1LL << 31), "gemm_nt: too many rows");
   IgemmLaunch L;
   memset(&L.p, 0, sizeof(L.p));
   IgemmParams& p = L.p;
   p.mode = IG_PLAIN;
-  p.kc = (K == 32) ? 32 : 64; p.row_bytes = p.kc * 2; p.kblocks = K / p.kc; p.tpg = 1; p.P = 1;
+  p.tf32 = tf32;
+  const int elt = tf32 ? 4 : 2;
+  p.kc = tf32 ? 32 : ((K == 32) ? 32 : 64); p.row_bytes = p.kc * elt; p.kblocks = K / p.kc; p.tpg = 1; p.P = 1;
   p.nc = (cols % 128 == 0) ? 128 : (cols % 64 == 0 ? 64 : 32);
   if (out_mode == OUT_CONVT) {
     PCRL_REQUIRE(ct_cout % p.nc == 0, "convT: Cout=%d must be a multiple of %d", ct_cout, p.nc);
@@ -566,10 +601,9 @@ int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long
   p.ct_D = ct_D; p.ct_H = ct_H; p.ct_W = ct_W;
   p.has_bias = bias != nullptr; p.bias = bias; p.out = c;
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
-  uint64_t str[1] = {(uint64_t)K * 2};
+  uint64_t str[1] = {(uint64_t)K * elt};
   uint32_t box[2] = {(uint32_t)p.kc, 128};
-  int rc = encode_map(&L.ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, dims, str, box,
-                      p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+  int rc = encode_map(&L.ta, tma_dtype(tf32), 2, a, dims, str, box, tma_swizzle(p.row_bytes));
   if (rc) return rc;
   rc = make_b_maps(L, b, K, cols, 1);
   if (rc) return rc;

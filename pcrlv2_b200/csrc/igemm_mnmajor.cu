@@ -19,6 +19,12 @@
 
 namespace pcrl {
 
+__device__ __forceinline__ void umma_any(int tf32, uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc,
+                                         uint32_t acc) {
+  if (tf32) umma_tf32(d, ad, bd, idesc, acc);
+  else umma_bf16(d, ad, bd, idesc, acc);
+}
+
 enum { WG_CONV = 0, WG_PLAIN = 1 };
 
 struct WgradParams {
@@ -35,6 +41,8 @@ struct WgradParams {
   int b_box_rows;                        // rows written by the X TMA box
   int ntaps;                             // taps per CTA (3 in CONV, 1 in PLAIN)
   int stages, tmem_cols;
+  int tf32, krows;                       // fp32 operands / kind::tf32; reduction rows per MMA (16 or 8)
+  int chunk_ch;                          // channels per 128-byte chunk row (64 bf16 / 32 fp32)
   int stack_dx;                          // CONV: one MMA of N = 3*nc covers the three dx taps
   int m_chunks_total;                    // Cout / mc
   int cout, cin;                         // leading dims of dW: [tap][cout][cin]
@@ -104,16 +112,16 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
           const int mr0 = (s % p.stages_per_sample) * p.nrows;
           for (int c = 0; c < p.a_chunks; c++)
             tma_load_4d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st],
-                        mchunk * p.mc + c * 64, -1, mr0, n);
+                        mchunk * p.mc + c * p.chunk_ch, -1, mr0, n);
           for (int c = 0; c < p.b_chunks; c++)
             tma_load_4d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st],
-                        nchunk * p.nc + c * 64, -1, mr0 + dzo * p.H1 + dyo - 1, n);
+                        nchunk * p.nc + c * p.chunk_ch, -1, mr0 + dzo * p.H1 + dyo - 1, n);
         } else {
           const int r0 = s * p.nrows;
           for (int c = 0; c < p.a_chunks; c++)
-            tma_load_2d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st], mchunk * p.mc + c * 64, r0);
+            tma_load_2d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st], mchunk * p.mc + c * p.chunk_ch, r0);
           for (int c = 0; c < p.b_chunks; c++)
-            tma_load_2d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st], nchunk * p.nc + c * 64, r0);
+            tma_load_2d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st], nchunk * p.nc + c * p.chunk_ch, r0);
         }
       }
       __syncwarp();
@@ -121,15 +129,18 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     }
   } else if (warp == 1) {
     int st = 0, ph = 0;
-    const uint32_t idesc = make_idesc(1, (uint32_t)p.mc, (uint32_t)p.nc, 1, 1);
-    const uint64_t a_hi = make_smem_desc(0, p.a_chunk_bytes, 8 * p.a_row_bytes,
-                                         p.a_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
-    const uint64_t b_hi = make_smem_desc(0, p.b_chunk_bytes, 8 * p.b_row_bytes,
-                                         p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
-    const uint32_t a_step = (uint32_t)(16 * p.a_row_bytes) >> 4, b_step = (uint32_t)(16 * p.b_row_bytes) >> 4;
-    const uint32_t idesc_stack = make_idesc(1, (uint32_t)p.mc, (uint32_t)(3 * p.nc), 1, 1);
-    const uint64_t b_stack_hi = make_smem_desc(0, p.b_row_bytes, 8 * p.b_row_bytes,
-                                               p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
+    const uint32_t fmt = p.tf32 ? 2u : 1u;
+    const uint32_t idesc = make_idesc(fmt, (uint32_t)p.mc, (uint32_t)p.nc, 1, 1);
+    // MN-major layouts: 16-bit operands use the 128B/64B swizzle (K atom = 8 rows); fp32 (tf32)
+    // operands need the 32-byte-atom variant (K atom = 4 rows) -- profiles/r01_umma_probe.md
+    const uint32_t a_lay = p.tf32 ? LAYOUT_SW128_B32 : (p.a_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
+    const uint32_t b_lay = p.tf32 ? LAYOUT_SW128_B32 : (p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
+    const uint32_t a_sbo = p.tf32 ? 512u : 8u * p.a_row_bytes, b_sbo = p.tf32 ? 512u : 8u * p.b_row_bytes;
+    const uint64_t a_hi = make_smem_desc(0, p.a_chunk_bytes, a_sbo, a_lay);
+    const uint64_t b_hi = make_smem_desc(0, p.b_chunk_bytes, b_sbo, b_lay);
+    const uint32_t a_step = (uint32_t)(p.krows * p.a_row_bytes) >> 4, b_step = (uint32_t)(p.krows * p.b_row_bytes) >> 4;
+    const uint32_t idesc_stack = make_idesc(fmt, (uint32_t)p.mc, (uint32_t)(3 * p.nc), 1, 1);
+    const uint64_t b_stack_hi = make_smem_desc(0, p.b_row_bytes, b_sbo, b_lay);
     uint32_t accumulate = 0;
     for (int s = s_begin; s < s_end; s++) {
       mbar_wait(&full[st], ph);
@@ -143,11 +154,11 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
           // slab row, so a single MMA fills the three accumulators (N = 96 / 192 instead of 3 x 32 / 64)
           uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
           uint64_t bd = b_stack_hi | (uint64_t)(((b_base + (uint32_t)(p.Wp - 1) * p.b_row_bytes) >> 4) & 0x3FFF);
-          umma_bf16(tmem, ad, bd, idesc_stack, accumulate);
+          umma_any(p.tf32, tmem, ad, bd, idesc_stack, accumulate);
           for (int ks = 1; ks < p.ksteps; ks++) {
             ad += a_step;
             bd += b_step;
-            umma_bf16(tmem, ad, bd, idesc_stack, 1u);
+            umma_any(p.tf32, tmem, ad, bd, idesc_stack, 1u);
           }
         } else {
           for (int t = 0; t < p.ntaps; t++) {
@@ -155,11 +166,11 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
             uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
             uint64_t bd = b_hi | (uint64_t)(((b_base + (uint32_t)b_row0 * p.b_row_bytes) >> 4) & 0x3FFF);
             const uint32_t d = tmem + t * p.nc;
-            umma_bf16(d, ad, bd, idesc, accumulate);
+            umma_any(p.tf32, d, ad, bd, idesc, accumulate);
             for (int ks = 1; ks < p.ksteps; ks++) {
               ad += a_step;
               bd += b_step;
-              umma_bf16(d, ad, bd, idesc, 1u);
+              umma_any(p.tf32, d, ad, bd, idesc, 1u);
             }
           }
         }
@@ -231,28 +242,35 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // dW[27][Cout][Cin] (fp32) += conv3d_k3 weight gradient.
 //   dy: [N][D][H+1][W][Cout] bf16 (pad rows zero), x: [N][D][H+1][W][Cin] bf16 (pad rows zero)
 int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D, int H, int W,
-                          int Cin, int Cout, cudaStream_t stream) {
+                          int Cin, int Cout, cudaStream_t stream, int dtype) {
+  const int tf32 = dtype == PCRL_DTYPE_F32;
   PCRL_REQUIRE(Cout % 64 == 0, "conv3d_k3_wgrad: Cout=%d must be a multiple of 64", Cout);
   PCRL_REQUIRE(Cin == 32 || Cin % 64 == 0, "conv3d_k3_wgrad: Cin=%d must be 32 or a multiple of 64", Cin);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.mode = WG_CONV;
+  p.tf32 = tf32;
+  const int elt = tf32 ? 4 : 2;
+  p.krows = 32 / elt;
+  p.chunk_ch = 128 / elt;
   p.W = W; p.Wp = W + 1; p.H1 = H + 1; p.MR = D * (H + 1); p.nsamples = N;
-  // merged rows per stage: aim at ~128..160 reduction rows
-  p.nrows = (128 + p.Wp - 1) / p.Wp;
+  // merged rows per stage: aim at ~128..160 reduction rows (half of that for fp32 operands)
+  const int target = tf32 ? 64 : 128;
+  p.nrows = (target + p.Wp - 1) / p.Wp;
   if (p.nrows > p.MR) p.nrows = p.MR;
   if (p.nrows + 2 > 256) return fail(PCRL_ERR_UNSUPPORTED, "conv3d_k3_wgrad: W too small");
   p.kr = p.nrows * p.Wp;
-  p.ksteps = (p.kr + 15) / 16;
+  p.ksteps = (p.kr + p.krows - 1) / p.krows;
   p.stages_per_sample = (p.MR + p.nrows - 1) / p.nrows;
   p.total_stages = p.stages_per_sample * N;
   p.mc = (Cout % 128 == 0) ? 128 : 64;
   p.nc = (Cin % 128 == 0) ? 128 : (Cin % 64 == 0 ? 64 : 32);
-  p.a_row_bytes = 128; p.a_chunks = p.mc / 64;
-  p.b_row_bytes = (p.nc == 32) ? 64 : 128; p.b_chunks = (p.nc == 32) ? 1 : p.nc / 64;
-  p.a_chunk_bytes = round_up(p.ksteps * 16 * p.a_row_bytes, 1024);
+  p.a_row_bytes = 128; p.a_chunks = p.mc / p.chunk_ch;
+  if (!tf32 && p.nc == 32) { p.b_row_bytes = 64; p.b_chunks = 1; }
+  else { p.b_row_bytes = 128; p.b_chunks = p.nc / p.chunk_ch; }
+  p.a_chunk_bytes = round_up(p.ksteps * p.krows * p.a_row_bytes, 1024);
   p.b_box_rows = (p.nrows + 2) * p.Wp;
-  const int b_rows_needed = p.ksteps * 16 + p.Wp + 2;
+  const int b_rows_needed = p.ksteps * p.krows + p.Wp + 2;
   p.b_chunk_bytes = round_up((b_rows_needed > p.b_box_rows ? b_rows_needed : p.b_box_rows) * p.b_row_bytes, 1024);
   p.ntaps = 3;
   p.stack_dx = (p.b_chunks == 1 && !getenv("PCRL_WGRAD_NOSTACK")) ? 1 : 0;
@@ -268,17 +286,19 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)p.MR, (uint64_t)N};
-    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)p.MR * W * Cout * 2};
-    uint32_t box[4] = {64, (uint32_t)p.Wp, (uint32_t)p.nrows, 1};
-    int rc = encode_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint64_t str[3] = {(uint64_t)Cout * elt, (uint64_t)W * Cout * elt, (uint64_t)p.MR * W * Cout * elt};
+    uint32_t box[4] = {(uint32_t)p.chunk_ch, (uint32_t)p.Wp, (uint32_t)p.nrows, 1};
+    int rc = encode_map(&ta, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, str, box,
+                        tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)p.MR, (uint64_t)N};
-    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)p.MR * W * Cin * 2};
-    uint32_t box[4] = {(uint32_t)(p.nc == 32 ? 32 : 64), (uint32_t)p.Wp, (uint32_t)(p.nrows + 2), 1};
-    int rc = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, str, box,
-                        p.nc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    uint64_t str[3] = {(uint64_t)Cin * elt, (uint64_t)W * Cin * elt, (uint64_t)p.MR * W * Cin * elt};
+    uint32_t box[4] = {(uint32_t)(p.b_row_bytes / elt), (uint32_t)p.Wp, (uint32_t)(p.nrows + 2), 1};
+    int rc = encode_map(&tb, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, str, box,
+                        tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                             : (p.b_row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
     if (rc) return rc;
   }
   dim3 grid((unsigned)kchunks, 9, (unsigned)((Cout / p.mc) * (Cin / p.nc)));
@@ -287,20 +307,26 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
 
 // dW[P][Q] (fp32, leading dimension Q) += A[rows][P]^T * B[rows][Q]; A, B bf16 row-major.
 int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P, int Q,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int dtype) {
+  const int tf32 = dtype == PCRL_DTYPE_F32;
   PCRL_REQUIRE(P % 64 == 0 && (Q % 64 == 0 || Q == 32), "gemm_tn: P=%d (multiple of 64), Q=%d (32 or multiple of 64)", P, Q);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.mode = WG_PLAIN;
-  p.nrows = 128; p.kr = 128; p.ksteps = 8;
-  p.total_stages = (int)((rows + 127) / 128);
+  p.tf32 = tf32;
+  const int elt = tf32 ? 4 : 2;
+  p.krows = 32 / elt;
+  p.chunk_ch = 128 / elt;
+  p.nrows = tf32 ? 64 : 128; p.kr = p.nrows; p.ksteps = p.nrows / p.krows;
+  p.total_stages = (int)((rows + p.nrows - 1) / p.nrows);
   p.stages_per_sample = p.total_stages;
   p.mc = (P % 128 == 0) ? 128 : 64;
   p.nc = (Q % 128 == 0) ? 128 : (Q % 64 == 0 ? 64 : 32);
-  p.a_row_bytes = 128; p.b_row_bytes = (p.nc == 32) ? 64 : 128;
-  p.a_chunks = p.mc / 64; p.b_chunks = (p.nc == 32) ? 1 : p.nc / 64;
-  p.a_chunk_bytes = 128 * 128; p.b_chunk_bytes = 128 * p.b_row_bytes;
-  p.b_box_rows = 128;
+  p.a_row_bytes = 128; p.a_chunks = p.mc / p.chunk_ch;
+  if (!tf32 && p.nc == 32) { p.b_row_bytes = 64; p.b_chunks = 1; }
+  else { p.b_row_bytes = 128; p.b_chunks = p.nc / p.chunk_ch; }
+  p.a_chunk_bytes = p.nrows * 128; p.b_chunk_bytes = p.nrows * p.b_row_bytes;
+  p.b_box_rows = p.nrows;
   p.ntaps = 1;
   p.m_chunks_total = P / p.mc;
   p.cout = P; p.cin = Q; p.dw = dw; p.rows_total = rows;
@@ -313,17 +339,19 @@ int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P
   CUtensorMap ta, tb;
   {
     uint64_t dims[2] = {(uint64_t)P, (uint64_t)rows};
-    uint64_t str[1] = {(uint64_t)P * 2};
-    uint32_t box[2] = {64, 128};
-    int rc = encode_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint64_t str[1] = {(uint64_t)P * elt};
+    uint32_t box[2] = {(uint32_t)p.chunk_ch, (uint32_t)p.nrows};
+    int rc = encode_map(&ta, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, dims, str, box,
+                        tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)Q, (uint64_t)rows};
-    uint64_t str[1] = {(uint64_t)Q * 2};
-    uint32_t box[2] = {(uint32_t)(p.nc == 32 ? 32 : 64), 128};
-    int rc = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, dims, str, box,
-                        p.nc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    uint64_t str[1] = {(uint64_t)Q * elt};
+    uint32_t box[2] = {(uint32_t)(p.b_row_bytes / elt), (uint32_t)p.nrows};
+    int rc = encode_map(&tb, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, dims, str, box,
+                        tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                             : (p.b_row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
     if (rc) return rc;
   }
   dim3 grid((unsigned)kchunks, 1, (unsigned)((P / p.mc) * (Q / p.nc)));

@@ -191,7 +191,9 @@ __device__ __forceinline__ void tmem_ld_wait() {
 
 // ------------------------------------------------------------- descriptors
 // Swizzle / layout-type codes of the sm_100 shared-memory matrix descriptor (bits 61..63).
-enum : uint32_t { LAYOUT_NONE = 0, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_SW32 = 6 };
+// LAYOUT_SW128_B32: 128-byte swizzle with 32-byte atoms -- the layout MN-major 32-bit (tf32) operands
+// need (TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; K atom = 4 rows, SBO = 512).
+enum : uint32_t { LAYOUT_NONE = 0, LAYOUT_SW128_B32 = 1, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_SW32 = 6 };
 
 // 64-bit shared-memory matrix descriptor (sm_100 "version 1").
 //   bits  0..13 start address >> 4        bits 16..29 leading byte offset >> 4

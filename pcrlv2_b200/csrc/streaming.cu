@@ -12,11 +12,25 @@ namespace pcrl {
 
 enum { ACT_RELU = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_SIGMOID = 3, ACT_NONE = 4 };
 
-struct bf16x8 {
-  uint4 u;
-};
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+// ---- 8-channel vector access, templated on the storage type (bf16: 16 bytes, fp32: 32 bytes)
+typedef __nv_bfloat16 bf16_t;
+template <typename T> struct V8;
+template <> struct V8<bf16_t> { uint4 a; };
+template <> struct V8<float> { uint4 a, b; };
+
+__device__ __forceinline__ V8<bf16_t> ld8(const bf16_t* p) {
+  V8<bf16_t> v;
+  v.a = *reinterpret_cast<const uint4*>(p);
+  return v;
+}
+__device__ __forceinline__ V8<float> ld8(const float* p) {
+  V8<float> v;
+  v.a = reinterpret_cast<const uint4*>(p)[0];
+  v.b = reinterpret_cast<const uint4*>(p)[1];
+  return v;
+}
+__device__ __forceinline__ void up8(const V8<bf16_t>& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v.a);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     float2 t = __bfloat1622float2(h[i]);
@@ -24,13 +38,41 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[2 * i + 1] = t.y;
   }
 }
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+__device__ __forceinline__ void up8(const V8<float>& v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.a.x); f[1] = __uint_as_float(v.a.y); f[2] = __uint_as_float(v.a.z); f[3] = __uint_as_float(v.a.w);
+  f[4] = __uint_as_float(v.b.x); f[5] = __uint_as_float(v.b.y); f[6] = __uint_as_float(v.b.z); f[7] = __uint_as_float(v.b.w);
+}
+__device__ __forceinline__ void st8(bf16_t* p, const float (&f)[8]) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return u;
+  *reinterpret_cast<uint4*>(p) = u;
 }
+__device__ __forceinline__ void st8(float* p, const float (&f)[8]) {
+  // fp32 activations are tensor-core (tf32) operands of the next kernel: store them tf32-rounded
+  reinterpret_cast<float4*>(p)[0] = make_float4(rna_tf32(f[0]), rna_tf32(f[1]), rna_tf32(f[2]), rna_tf32(f[3]));
+  reinterpret_cast<float4*>(p)[1] = make_float4(rna_tf32(f[4]), rna_tf32(f[5]), rna_tf32(f[6]), rna_tf32(f[7]));
+}
+__device__ __forceinline__ void z8(bf16_t* p) { *reinterpret_cast<uint4*>(p) = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void z8(float* p) {
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(0, 0, 0, 0);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(0, 0, 0, 0);
+}
+// round through the storage type: statistics / sums are taken over the values that are stored
+__device__ __forceinline__ void rnd8(bf16_t, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) f[i] = __bfloat162float(__float2bfloat16(f[i]));
+}
+__device__ __forceinline__ void rnd8(float, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) f[i] = rna_tf32(f[i]);
+}
+__device__ __forceinline__ void cvt_store(bf16_t* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void cvt_store(float* p, float v) { *p = rna_tf32(v); }
+__device__ __forceinline__ float to_f(bf16_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(float v) { return v; }
+
 __device__ __forceinline__ float act_fwd(float z, int act, float slope) {
   switch (act) {
     case ACT_RELU: return fmaxf(z, 0.f);
@@ -56,8 +98,9 @@ __device__ __forceinline__ float act_bwd(float z, int act, float slope) {
 //   wf [9 (ky,kx)][3 (kz = 2,1,0)][Cout][Cin] bf16   forward
 //   wd [9][3][Cin][Cout] bf16, taps mirrored          data gradient
 // (the kz-innermost order lets one TMA box fetch the filters of up to three stacked output planes)
-__global__ void pack_conv3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
-                                  __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
+template <typename T>
+__global__ void pack_conv3_kernel(const float* __restrict__ w, T* __restrict__ wf,
+                                  T* __restrict__ wd, int Cout, int Cin) {
   const long long total = (long long)Cout * Cin * 27;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -65,12 +108,12 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, __nv_bfloat16* __
     const long long r = i / 27;
     const int ci = (int)(r % Cin), co = (int)(r / Cin);
     const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
-    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    const float v = w[i];
     const int tf = (ky * 3 + kx) * 3 + (2 - kz);
-    wf[((size_t)tf * Cout + co) * Cin + ci] = v;
+    cvt_store(&wf[((size_t)tf * Cout + co) * Cin + ci], v);
     if (wd) {
       const int td = ((2 - ky) * 3 + (2 - kx)) * 3 + kz;
-      wd[((size_t)td * Cin + ci) * Cout + co] = v;
+      cvt_store(&wd[((size_t)td * Cin + ci) * Cout + co], v);
     }
   }
 }
@@ -87,17 +130,18 @@ __global__ void unpack_conv3_wgrad_kernel(const float* __restrict__ gpk, float* 
   }
 }
 // w [Cin][Cout][8] fp32 -> wf [(t,co)][Cin] bf16 (forward B operand) and wd [Cin][(t,co)] bf16
-__global__ void pack_convT_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
-                                  __nv_bfloat16* __restrict__ wd, int Cin, int Cout) {
+template <typename T>
+__global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ wf,
+                                  T* __restrict__ wd, int Cin, int Cout) {
   const long long total = (long long)Cin * Cout * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % 8);
     const long long r = i / 8;
     const int co = (int)(r % Cout), ci = (int)(r / Cout);
-    const __nv_bfloat16 v = __float2bfloat16(w[i]);
-    wf[((size_t)t * Cout + co) * Cin + ci] = v;
-    wd[(size_t)ci * (8 * Cout) + (size_t)t * Cout + co] = v;
+    const float v = w[i];
+    cvt_store(&wf[((size_t)t * Cout + co) * Cin + ci], v);
+    cvt_store(&wd[(size_t)ci * (8 * Cout) + (size_t)t * Cout + co], v);
   }
 }
 // gpk [(t,co)][Cin] fp32 -> g [Cin][Cout][8]
@@ -116,9 +160,10 @@ __global__ void unpack_convT_wgrad_kernel(const float* __restrict__ gpk, float* 
 // ------------------------------------------------------------------------------ stem conv, Cin = 1
 // x [N][D][H][W] fp32 (C = 1, so NCDHW == NDHWC), w [32][27] fp32, y H-padded bf16 [N][D][H+1][W][32].
 // One thread per output voxel, 32 output channels in registers; statistics as in the igemm epilogue.
+template <typename T>
 __global__ void __launch_bounds__(128)
 stem_conv_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                       __nv_bfloat16* __restrict__ y, double* __restrict__ stats,
+                       T* __restrict__ y, double* __restrict__ stats,
                        int stats_per_sample, int N, int D, int H, int W) {
   __shared__ float ws[27][32];
   __shared__ float st[2][32];
@@ -163,18 +208,16 @@ stem_conv_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
       }
     }
     // store (pad rows get zeros)
-    uint4* o = reinterpret_cast<uint4*>(y + ((size_t)n * slots + slot) * 32);
+    T* o = y + ((size_t)n * slots + slot) * 32;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       float f[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) f[j] = acc[8 * i + j];
-      const uint4 u = pack8(f);
-      o[i] = u;
-      float r[8];
-      unpack8(u, r);
+      rnd8(T(), f);
+      st8(o + 8 * i, f);
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[8 * i + j] = r[j];  // statistics over the stored values
+      for (int j = 0; j < 8; j++) acc[8 * i + j] = f[j];  // statistics over the stored values
     }
   }
   if (stats) {
@@ -204,8 +247,9 @@ stem_conv_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
 }
 
 // dw[32][27] += sum_v dy[v][co] * x[v + tap]; lane = output channel, one warp per run of voxels.
+template <typename T>
 __global__ void __launch_bounds__(256)
-stem_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+stem_conv_wgrad_kernel(const T* __restrict__ dy, const float* __restrict__ x,
                        float* __restrict__ dw, int N, int D, int H, int W, int vox_per_warp) {
   __shared__ float red[27][32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) red[i / 32][i % 32] = 0.f;
@@ -222,8 +266,7 @@ stem_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __rest
     const int h = (int)((v / W) % H);
     const int d = (int)((v / ((long long)W * H)) % D);
     const int n = (int)(v / ((long long)W * H * D));
-    const float g = __bfloat162float(
-        dy[((((size_t)n * D + d) * (H + 1) + h + 1) * W + wq) * 32 + lane]);
+    const float g = to_f(dy[((((size_t)n * D + d) * (H + 1) + h + 1) * W + wq) * 32 + lane]);
     const float* xs = x + (size_t)n * D * H * W;
 #pragma unroll
     for (int kz = 0; kz < 3; kz++) {
@@ -295,10 +338,11 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, double co
 // channels (16 bytes) of one column of the row and keeps that channel group for the whole kernel,
 // so the only integer division in the loop is the pad-row test.  RELU is specialised at compile
 // time (ACT = PCRL_ACT_RELU), every other activation takes the generic path (ACT = -1).
+template <typename T>
 struct NormActFwdParams {
-  const __nv_bfloat16* y;
+  const T* y;
   const float* scale; const float* shift; const float* prelu;
-  __nv_bfloat16* a_out; __nv_bfloat16* pool_out; float* avg_sum;
+  T* a_out; T* pool_out; float* avg_sum;
   int per_sample, act, N, D, H, W, C;
 };
 
@@ -329,8 +373,8 @@ __device__ __forceinline__ float act_d(float z, int act, float slope) {
   return act_bwd(z, act, slope);
 }
 
-template <bool POOL, int ACT>
-__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParams p) {
+template <typename T, bool POOL, int ACT>
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParams<T> p) {
   extern __shared__ float red[];  // [blockDim.x][8] when avg_sum
   const int n = blockIdx.y;
   const int C8 = p.C >> 3;
@@ -355,7 +399,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
   const size_t row_elems = (size_t)p.W * p.C;            // elements of one fine row
   for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < R; row0 += gridDim.x * m.rows_per_iter * U) {
     if (!POOL) {
-      uint4 yv[U];
+      V8<T> yv[U];
       int kind[U];
       size_t off[U];
 #pragma unroll
@@ -365,25 +409,23 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
         if (lane_ok && row < R) {
           off[u] = ((size_t)n * R + row) * row_elems + (size_t)m.w * p.C + m.c8 * 8;
           kind[u] = (row % H1) == 0 ? 1 : 2;
-          if (kind[u] == 2) yv[u] = *reinterpret_cast<const uint4*>(p.y + off[u]);
+          if (kind[u] == 2) yv[u] = ld8(p.y + off[u]);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (kind[u] == 1) {
-          if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off[u]) = make_uint4(0, 0, 0, 0);
+          if (p.a_out) z8(p.a_out + off[u]);
         } else if (kind[u] == 2) {
           float v[8];
-          unpack8(yv[u], v);
+          up8(yv[u], v);
 #pragma unroll
           for (int q = 0; q < 8; q++) v[q] = act_f<ACT>(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
-          const uint4 o = pack8(v);
-          if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off[u]) = o;
+          rnd8(T(), v);  // average the stored (rounded) activations
+          if (p.a_out) st8(p.a_out + off[u], v);
           if (p.avg_sum) {
-            float r[8];
-            unpack8(o, r);  // average the stored (rounded) activations
 #pragma unroll
-            for (int q = 0; q < 8; q++) asum[q] += r[q];
+            for (int q = 0; q < 8; q++) asum[q] += v[q];
           }
         }
       }
@@ -393,20 +435,19 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
       const int hp = row % (ch + 1), d = row / (ch + 1);
       const size_t pooled_off = (((size_t)n * R + row) * cw + m.w) * p.C + m.c8 * 8;
       if (hp == 0) {  // pad rows of the outputs
-        if (p.pool_out) *reinterpret_cast<uint4*>(p.pool_out + pooled_off) = make_uint4(0, 0, 0, 0);
+        if (p.pool_out) z8(p.pool_out + pooled_off);
         if (p.a_out)
           for (int i = 0; i < 2; i++)
             for (int k = 0; k < 2; k++)
-              *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8) =
-                  make_uint4(0, 0, 0, 0);
+              z8(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
         continue;
       }
       const int h = hp - 1;
-      uint4 yv[8];
+      V8<T> yv[8];
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
-        yv[pos] = *reinterpret_cast<const uint4*>(
+        yv[pos] = ld8(
             p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
       }
       float mx[8];
@@ -416,16 +457,16 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
         float v[8];
-        unpack8(yv[pos], v);
+        up8(yv[pos], v);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           v[q] = act_f<ACT>(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
           mx[q] = fmaxf(mx[q], v[q]);
         }
         if (p.a_out)
-          *reinterpret_cast<uint4*>(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8) = pack8(v);
+          st8(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8, v);
       }
-      if (p.pool_out) *reinterpret_cast<uint4*>(p.pool_out + pooled_off) = pack8(mx);
+      if (p.pool_out) st8(p.pool_out + pooled_off, mx);
     }
   }
   if (p.avg_sum) {
@@ -455,18 +496,19 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
 //   gavg: optional [N][C] fp32 gradient wrt the global average pool; adds gavg/(D*H*W).
 // pass 1 accumulates per (group, channel): sum dz, sum dz*xhat (and sum dA*min(z,0) for PReLU);
 // pass 2 writes dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), pad rows zero.
+template <typename T>
 struct NormActBwdParams {
-  const __nv_bfloat16* y; const __nv_bfloat16* g1; const __nv_bfloat16* g2; const float* gavg;
+  const T* y; const T* g1; const T* g2; const float* gavg;
   const float* scale; const float* shift; const float* mean; const float* invstd;
   const float* gamma; const float* prelu;
   double* sums;      // [G][C][3]
-  __nv_bfloat16* dy; // pass 2
+  T* dy; // pass 2
   double count;      // elements per (group, channel)
   int per_sample, act, N, D, H, W, C;
 };
 
-template <bool POOL, bool APPLY, int ACT>
-__global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParams p) {
+template <typename T, bool POOL, bool APPLY, int ACT>
+__global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParams<T> p) {
   extern __shared__ float red[];  // pass 1: [blockDim.x][24]
   const int n = blockIdx.y;
   const int C8 = p.C >> 3;
@@ -504,7 +546,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
   const size_t row_elems = (size_t)p.W * p.C;
   for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < R; row0 += gridDim.x * m.rows_per_iter * U) {
     if (!POOL) {
-      uint4 yq[U], g1q[U], g2q[U];
+      V8<T> yq[U], g1q[U], g2q[U];
       int kind[U];
       size_t off[U];
 #pragma unroll
@@ -515,21 +557,21 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
           off[u] = ((size_t)n * R + row) * row_elems + (size_t)m.w * p.C + m.c8 * 8;
           kind[u] = (row % H1) == 0 ? 1 : 2;
           if (kind[u] == 2) {
-            yq[u] = *reinterpret_cast<const uint4*>(p.y + off[u]);
-            if (p.g1) g1q[u] = *reinterpret_cast<const uint4*>(p.g1 + off[u]);
-            if (p.g2) g2q[u] = *reinterpret_cast<const uint4*>(p.g2 + off[u]);
+            yq[u] = ld8(p.y + off[u]);
+            if (p.g1) g1q[u] = ld8(p.g1 + off[u]);
+            if (p.g2) g2q[u] = ld8(p.g2 + off[u]);
           }
         }
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (kind[u] == 1) {
-          if (APPLY) *reinterpret_cast<uint4*>(p.dy + off[u]) = make_uint4(0, 0, 0, 0);
+          if (APPLY) z8(p.dy + off[u]);
         } else if (kind[u] == 2) {
           float yv[8], g1v[8], g2v[8], out[8];
-          unpack8(yq[u], yv);
-          if (p.g1) unpack8(g1q[u], g1v);
-          if (p.g2) unpack8(g2q[u], g2v);
+          up8(yq[u], yv);
+          if (p.g1) up8(g1q[u], g1v);
+          if (p.g2) up8(g2q[u], g2v);
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const float z = fmaf(yv[q], sc[q], sh[q]);
@@ -545,7 +587,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
               if (ACT != ACT_RELU) a2[q] += da * fminf(z, 0.f);
             }
           }
-          if (APPLY) *reinterpret_cast<uint4*>(p.dy + off[u]) = pack8(out);
+          if (APPLY) st8(p.dy + off[u], out);
         }
       }
     } else {
@@ -556,18 +598,17 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
         if (APPLY)
           for (int i = 0; i < 2; i++)
             for (int k = 0; k < 2; k++)
-              *reinterpret_cast<uint4*>(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8) =
-                  make_uint4(0, 0, 0, 0);
+              z8(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
         continue;
       }
       const int h = hp - 1;
       float gp[8];
-      unpack8(*reinterpret_cast<const uint4*>(p.g1 + (((size_t)n * R + row) * cw + m.w) * p.C + m.c8 * 8), gp);
-      uint4 yq[8];
+      up8(ld8(p.g1 + (((size_t)n * R + row) * cw + m.w) * p.C + m.c8 * 8), gp);
+      V8<T> yq[8];
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
-        yq[pos] = *reinterpret_cast<const uint4*>(
+        yq[pos] = ld8(
             p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
       }
       int arg[8];
@@ -577,7 +618,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         float yv[8];
-        unpack8(yq[pos], yv);
+        up8(yq[pos], yv);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           // same fp32 values and scan order as the forward pass: the first maximum wins
@@ -590,8 +631,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
         const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8;
         float yv[8], g2v[8], out[8];
-        unpack8(yq[pos], yv);
-        if (p.g2) unpack8(*reinterpret_cast<const uint4*>(p.g2 + off), g2v);
+        up8(yq[pos], yv);
+        if (p.g2) up8(ld8(p.g2 + off), g2v);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const float z = fmaf(yv[q], sc[q], sh[q]);
@@ -606,7 +647,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
             if (ACT != ACT_RELU) a2[q] += da * fminf(z, 0.f);
           }
         }
-        if (APPLY) *reinterpret_cast<uint4*>(p.dy + off) = pack8(out);
+        if (APPLY) st8(p.dy + off, out);
       }
     }
   }
@@ -634,23 +675,22 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
 }
 
 // ------------------------------------------------------------------------------ misc
-// zero the pad row (h' = 0) of every plane of an H-padded tensor with `row_elems` = W*C elements
-__global__ void zero_pad_rows_kernel(__nv_bfloat16* __restrict__ t, long long planes, int H1,
-                                     int row_elems) {
-  const int per = row_elems / 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < planes * per;
+// zero the pad row (h' = 0) of every plane of an H-padded tensor; row_vecs = 16-byte vectors per row
+__global__ void zero_pad_rows_kernel(uint4* __restrict__ t, long long planes, int H1, int row_vecs) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < planes * row_vecs;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long pl = i / per;
-    const int e = (int)(i % per);
-    reinterpret_cast<uint4*>(t + (size_t)pl * H1 * row_elems)[e] = make_uint4(0, 0, 0, 0);
+    const long long pl = i / row_vecs;
+    const int e = (int)(i % row_vecs);
+    t[(size_t)pl * H1 * row_vecs + e] = make_uint4(0, 0, 0, 0);
   }
 }
 
 // ConvTranspose backward re-layout: fine gradient [N][2D][2H+1][2W][C] bf16 -> coarse-major
 // [N*D*(H+1)*W][8*C] bf16 (rows follow the coarse H-padded order, pad rows zero), plus the bias
 // gradient dbias[C] += sum over all fine voxels.
+template <typename T>
 __global__ void __launch_bounds__(256)
-convT_unshuffle_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ out,
+convT_unshuffle_kernel(const T* __restrict__ g, T* __restrict__ out,
                        float* __restrict__ dbias, int N, int D, int H, int W, int C) {
   extern __shared__ float red[];  // [blockDim.x][8]
   const int C8 = C >> 3;
@@ -668,17 +708,17 @@ convT_unshuffle_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __res
     const int hp = (int)((r / W) % (H + 1));
     const int d = (int)((r / ((long long)W * (H + 1))) % D);
     const long long n = r / ((long long)W * (H + 1) * D);
-    uint4 v = make_uint4(0, 0, 0, 0);
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) f[q] = 0.f;
     if (hp >= 1) {
       const int i = t >> 2, j = (t >> 1) & 1, k = t & 1;
       const size_t off = ((((size_t)n * 2 * D + 2 * d + i) * (2 * H + 1) + 2 * (hp - 1) + j + 1) * (2 * W) + 2 * w + k) * C + c8 * 8;
-      v = *reinterpret_cast<const uint4*>(g + off);
-      float f[8];
-      unpack8(v, f);
+      up8(ld8(g + off), f);
 #pragma unroll
       for (int q = 0; q < 8; q++) bs[q] += f[q];
     }
-    *reinterpret_cast<uint4*>(out + ((size_t)r * 8 + t) * C + c8 * 8) = v;
+    st8(out + ((size_t)r * 8 + t) * C + c8 * 8, f);
   }
   if (dbias) {
 #pragma unroll
@@ -711,9 +751,15 @@ static inline int block_for_c8(int C8) {
   return b;
 }
 
-int pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s) {
+// dtype: PCRL_DTYPE_BF16 (0) or PCRL_DTYPE_F32 (1) = storage type of activations / packed operands
+#define PCRL_BY_DTYPE(dtype, EXPR_BF16, EXPR_F32) \
+  do { if ((dtype) == PCRL_DTYPE_F32) { EXPR_F32; } else { EXPR_BF16; } } while (0)
+
+int pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int dtype, cudaStream_t s) {
   const long long total = (long long)Cout * Cin * 27;
-  pack_conv3_kernel<<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin);
+  PCRL_BY_DTYPE(dtype,
+    (pack_conv3_kernel<bf16_t><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (bf16_t*)wf, (bf16_t*)wd, Cout, Cin)),
+    (pack_conv3_kernel<float><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (float*)wf, (float*)wd, Cout, Cin)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -723,9 +769,11 @@ int unpack_conv3_wgrad(const float* gpk, float* g, int Cout, int Cin, cudaStream
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
-int pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, cudaStream_t s) {
+int pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, int dtype, cudaStream_t s) {
   const long long total = (long long)Cin * Cout * 8;
-  pack_convT_kernel<<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cin, Cout);
+  PCRL_BY_DTYPE(dtype,
+    (pack_convT_kernel<bf16_t><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (bf16_t*)wf, (bf16_t*)wd, Cin, Cout)),
+    (pack_convT_kernel<float><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (float*)wf, (float*)wd, Cin, Cout)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -737,14 +785,16 @@ int unpack_convT_wgrad(const float* gpk, float* g, int Cin, int Cout, cudaStream
 }
 
 int stem_conv_fprop(const float* x, const float* w, void* y, double* stats, int stats_per_sample,
-                    int N, int D, int H, int W, cudaStream_t s) {
+                    int N, int D, int H, int W, int dtype, cudaStream_t s) {
   const int slots = D * (H + 1) * W;
   dim3 grid((slots + 127) / 128, N);
-  stem_conv_fprop_kernel<<<grid, 128, 0, s>>>(x, w, (__nv_bfloat16*)y, stats, stats_per_sample, N, D, H, W);
+  PCRL_BY_DTYPE(dtype,
+    (stem_conv_fprop_kernel<bf16_t><<<grid, 128, 0, s>>>(x, w, (bf16_t*)y, stats, stats_per_sample, N, D, H, W)),
+    (stem_conv_fprop_kernel<float><<<grid, 128, 0, s>>>(x, w, (float*)y, stats, stats_per_sample, N, D, H, W)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
-int stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int H, int W,
+int stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int H, int W, int dtype,
                     cudaStream_t s) {
   const long long total = (long long)N * D * H * W;
   const int warps = num_sms() * 16;
@@ -752,7 +802,9 @@ int stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int
   if (vpw < 1) vpw = 1;
   const long long nwarps = (total + vpw - 1) / vpw;
   const int blocks = (int)((nwarps + 7) / 8);
-  stem_conv_wgrad_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)dy, x, dw, N, D, H, W, vpw);
+  PCRL_BY_DTYPE(dtype,
+    (stem_conv_wgrad_kernel<bf16_t><<<blocks, 256, 0, s>>>((const bf16_t*)dy, x, dw, N, D, H, W, vpw)),
+    (stem_conv_wgrad_kernel<float><<<blocks, 256, 0, s>>>((const float*)dy, x, dw, N, D, H, W, vpw)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -768,16 +820,13 @@ int norm_finalize(const double* stats, double count, const float* gamma, const f
   return PCRL_OK;
 }
 
-int norm_act_fwd(const void* y, const float* scale, const float* shift, const float* prelu,
-                 void* a_out, void* pool_out, float* avg_sum, int per_sample, int act, int pool,
-                 int N, int D, int H, int W, int C, cudaStream_t s) {
-  PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_fwd: C=%d must be 8 * 2^k", C);
-  PCRL_REQUIRE(!pool || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "norm_act_fwd: pooling needs even dims");
-  PCRL_REQUIRE(!(pool && avg_sum), "norm_act_fwd: avg_sum with pool is not supported");
+template <typename T>
+static int norm_act_fwd_t(const void* y, const float* scale, const float* shift, const float* prelu,
+                          void* a_out, void* pool_out, float* avg_sum, int per_sample, int act, int pool,
+                          int N, int D, int H, int W, int C, cudaStream_t s) {
   const int cw = pool ? W / 2 : W;
-  PCRL_REQUIRE(cw * (C / 8) <= 256, "norm_act_fwd: row of %d x %d channels is too wide", cw, C);
-  NormActFwdParams p{(const __nv_bfloat16*)y, scale, shift, prelu, (__nv_bfloat16*)a_out,
-                     (__nv_bfloat16*)pool_out, avg_sum, per_sample, act, N, D, H, W, C};
+  NormActFwdParams<T> p{(const T*)y, scale, shift, prelu, (T*)a_out, (T*)pool_out, avg_sum,
+                        per_sample, act, N, D, H, W, C};
   const int items = cw * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
   const int R = pool ? (D / 2) * (H / 2 + 1) : D * (H + 1);
   int bx = (R + rpi * U - 1) / (rpi * U);
@@ -788,29 +837,37 @@ int norm_act_fwd(const void* y, const float* scale, const float* shift, const fl
   const size_t smem = avg_sum ? (size_t)256 * 8 * 4 : 0;
   const bool relu = act == ACT_RELU;
   if (pool) {
-    if (relu) norm_act_fwd_kernel<true, ACT_RELU><<<grid, 256, smem, s>>>(p);
-    else norm_act_fwd_kernel<true, -1><<<grid, 256, smem, s>>>(p);
+    if (relu) norm_act_fwd_kernel<T, true, ACT_RELU><<<grid, 256, smem, s>>>(p);
+    else norm_act_fwd_kernel<T, true, -1><<<grid, 256, smem, s>>>(p);
   } else {
-    if (relu) norm_act_fwd_kernel<false, ACT_RELU><<<grid, 256, smem, s>>>(p);
-    else norm_act_fwd_kernel<false, -1><<<grid, 256, smem, s>>>(p);
+    if (relu) norm_act_fwd_kernel<T, false, ACT_RELU><<<grid, 256, smem, s>>>(p);
+    else norm_act_fwd_kernel<T, false, -1><<<grid, 256, smem, s>>>(p);
   }
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
 
-// pass = 0: reduce into sums [G][C][3] (caller zeroes), pass = 1: apply (writes dy)
-int norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gavg,
-                 const float* scale, const float* shift, const float* mean, const float* invstd,
-                 const float* gamma, const float* prelu, double* sums, void* dy, double count,
-                 int per_sample, int act, int pool, int pass, int N, int D, int H, int W, int C,
-                 cudaStream_t s) {
-  PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_bwd: C=%d must be 8 * 2^k", C);
-  PCRL_REQUIRE(!pool || g1, "norm_act_bwd: pooled backward needs g1");
+int norm_act_fwd(const void* y, const float* scale, const float* shift, const float* prelu,
+                 void* a_out, void* pool_out, float* avg_sum, int per_sample, int act, int pool,
+                 int N, int D, int H, int W, int C, int dtype, cudaStream_t s) {
+  PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_fwd: C=%d must be 8 * 2^k", C);
+  PCRL_REQUIRE(!pool || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "norm_act_fwd: pooling needs even dims");
+  PCRL_REQUIRE(!(pool && avg_sum), "norm_act_fwd: avg_sum with pool is not supported");
+  PCRL_REQUIRE((pool ? W / 2 : W) * (C / 8) <= 256, "norm_act_fwd: row of %d x %d channels is too wide", W, C);
+  if (dtype == PCRL_DTYPE_F32)
+    return norm_act_fwd_t<float>(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H, W, C, s);
+  return norm_act_fwd_t<bf16_t>(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H, W, C, s);
+}
+
+template <typename T>
+static int norm_act_bwd_t(const void* y, const void* g1, const void* g2, const float* gavg,
+                          const float* scale, const float* shift, const float* mean, const float* invstd,
+                          const float* gamma, const float* prelu, double* sums, void* dy, double count,
+                          int per_sample, int act, int pool, int pass, int N, int D, int H, int W, int C,
+                          cudaStream_t s) {
   const int cw = pool ? W / 2 : W;
-  PCRL_REQUIRE(cw * (C / 8) <= 256, "norm_act_bwd: row of %d x %d channels is too wide", cw, C);
-  NormActBwdParams p{(const __nv_bfloat16*)y, (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, gavg,
-                     scale, shift, mean, invstd, gamma, prelu, sums, (__nv_bfloat16*)dy, count,
-                     per_sample, act, N, D, H, W, C};
+  NormActBwdParams<T> p{(const T*)y, (const T*)g1, (const T*)g2, gavg, scale, shift, mean, invstd, gamma,
+                        prelu, sums, (T*)dy, count, per_sample, act, N, D, H, W, C};
   const int items = cw * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
   const int R = pool ? (D / 2) * (H / 2 + 1) : D * (H + 1);
   int bx = (R + rpi * U - 1) / (rpi * U);
@@ -819,10 +876,10 @@ int norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gav
   if (bx < 1) bx = 1;
   dim3 grid(bx, N);
   const bool relu = act == ACT_RELU;
-#define PCRL_LAUNCH_BWD(POOLV, APPLYV, SMEM)                                              \
-  do {                                                                                    \
-    if (relu) norm_act_bwd_kernel<POOLV, APPLYV, ACT_RELU><<<grid, 256, SMEM, s>>>(p);    \
-    else norm_act_bwd_kernel<POOLV, APPLYV, -1><<<grid, 256, SMEM, s>>>(p);               \
+#define PCRL_LAUNCH_BWD(POOLV, APPLYV, SMEM)                                                 \
+  do {                                                                                       \
+    if (relu) norm_act_bwd_kernel<T, POOLV, APPLYV, ACT_RELU><<<grid, 256, SMEM, s>>>(p);    \
+    else norm_act_bwd_kernel<T, POOLV, APPLYV, -1><<<grid, 256, SMEM, s>>>(p);               \
   } while (0)
   if (pass == 0) {
     const size_t smem = (size_t)256 * 24 * 4;
@@ -837,20 +894,41 @@ int norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gav
   return PCRL_OK;
 }
 
-int zero_pad_rows(void* t, long long planes, int H1, int row_elems, cudaStream_t s) {
-  PCRL_REQUIRE(row_elems % 8 == 0, "zero_pad_rows: row_elems=%d must be a multiple of 8", row_elems);
-  zero_pad_rows_kernel<<<grid_for(planes * (row_elems / 8), 256, 8192), 256, 0, s>>>((__nv_bfloat16*)t, planes, H1, row_elems);
+// pass = 0: reduce into sums [G][C][3] (caller zeroes), pass = 1: apply (writes dy)
+int norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gavg,
+                 const float* scale, const float* shift, const float* mean, const float* invstd,
+                 const float* gamma, const float* prelu, double* sums, void* dy, double count,
+                 int per_sample, int act, int pool, int pass, int N, int D, int H, int W, int C,
+                 int dtype, cudaStream_t s) {
+  PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_bwd: C=%d must be 8 * 2^k", C);
+  PCRL_REQUIRE(!pool || g1, "norm_act_bwd: pooled backward needs g1");
+  PCRL_REQUIRE((pool ? W / 2 : W) * (C / 8) <= 256, "norm_act_bwd: row of %d x %d channels is too wide", W, C);
+  if (dtype == PCRL_DTYPE_F32)
+    return norm_act_bwd_t<float>(y, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu, sums, dy, count,
+                                 per_sample, act, pool, pass, N, D, H, W, C, s);
+  return norm_act_bwd_t<bf16_t>(y, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu, sums, dy, count,
+                                per_sample, act, pool, pass, N, D, H, W, C, s);
+}
+
+// row_bytes = bytes of one (w, c) row of the H-padded tensor
+int zero_pad_rows(void* t, long long planes, int H1, long long row_bytes, cudaStream_t s) {
+  PCRL_REQUIRE(row_bytes % 16 == 0, "zero_pad_rows: row of %lld bytes must be a multiple of 16", row_bytes);
+  const int row_vecs = (int)(row_bytes / 16);
+  zero_pad_rows_kernel<<<grid_for(planes * row_vecs, 256, 8192), 256, 0, s>>>((uint4*)t, planes, H1, row_vecs);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
 
-int convT_unshuffle(const void* g, void* out, float* dbias, int N, int D, int H, int W, int C,
+int convT_unshuffle(const void* g, void* out, float* dbias, int N, int D, int H, int W, int C, int dtype,
                     cudaStream_t s) {
   PCRL_REQUIRE(C % 8 == 0, "convT_unshuffle: C=%d must be a multiple of 8", C);
   const int C8 = C / 8, block = block_for_c8(C8);
   const long long items = (long long)N * D * (H + 1) * W * 8 * C8;
   const int blocks = grid_for((items + 3) / 4, block, 1 << 20);
-  convT_unshuffle_kernel<<<blocks, block, dbias ? (size_t)block * 8 * 4 : 0, s>>>((const __nv_bfloat16*)g, (__nv_bfloat16*)out, dbias, N, D, H, W, C);
+  const size_t smem = dbias ? (size_t)block * 8 * 4 : 0;
+  PCRL_BY_DTYPE(dtype,
+    (convT_unshuffle_kernel<bf16_t><<<blocks, block, smem, s>>>((const bf16_t*)g, (bf16_t*)out, dbias, N, D, H, W, C)),
+    (convT_unshuffle_kernel<float><<<blocks, block, smem, s>>>((const float*)g, (float*)out, dbias, N, D, H, W, C)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

@@ -13,12 +13,22 @@ from . import _lib
 
 ACT = {"relu": 0, "prelu": 1, "elu": 2, "sigmoid": 3, "none": 4}
 BF16 = torch.bfloat16
+F32 = torch.float32
+# storage types of activations / tensor-core operands (include/pcrl_b200.h: PCRL_DTYPE_*)
+DTYPE_CODE = {torch.bfloat16: 0, torch.float32: 1}
 
 
-def pad_ndhwc(x: torch.Tensor) -> torch.Tensor:
-    """(N,C,D,H,W) float -> [N,D,H+1,W,C] bf16 with the zero pad row."""
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return DTYPE_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f"activations must be bf16 or fp32, got {t.dtype}")
+
+
+def pad_ndhwc(x: torch.Tensor, dtype=BF16) -> torch.Tensor:
+    """(N,C,D,H,W) float -> [N,D,H+1,W,C] (bf16 by default) with the zero pad row."""
     n, c, d, h, w = x.shape
-    out = torch.zeros((n, d, h + 1, w, c), dtype=BF16, device=x.device)
+    out = torch.zeros((n, d, h + 1, w, c), dtype=dtype, device=x.device)
     out[:, :, 1:] = x.permute(0, 2, 3, 4, 1)
     return out
 
@@ -41,13 +51,13 @@ def _chk(t: torch.Tensor, dtype=None):
 
 
 # ------------------------------------------------------------------------------ weights
-def pack_conv3_weights(w: torch.Tensor, need_dgrad: bool = True):
-    """(Cout,Cin,3,3,3) fp32 -> (wf [27,Cout,Cin] bf16, wd [27,Cin,Cout] bf16 or None)."""
+def pack_conv3_weights(w: torch.Tensor, need_dgrad: bool = True, dtype=BF16):
+    """(Cout,Cin,3,3,3) fp32 -> (wf [27,Cout,Cin], wd [27,Cin,Cout] or None) in ``dtype``."""
     _chk(w, torch.float32)
     cout, cin = w.shape[0], w.shape[1]
-    wf = torch.empty((27, cout, cin), dtype=BF16, device=w.device)
-    wd = torch.empty((27, cin, cout), dtype=BF16, device=w.device) if need_dgrad else None
-    _lib.call("pcrl_pack_conv3_weights", w, wf, wd, cout, cin)
+    wf = torch.empty((27, cout, cin), dtype=dtype, device=w.device)
+    wd = torch.empty((27, cin, cout), dtype=dtype, device=w.device) if need_dgrad else None
+    _lib.call("pcrl_pack_conv3_weights", w, wf, wd, cout, cin, DTYPE_CODE[dtype])
     return wf, wd
 
 
@@ -59,13 +69,13 @@ def unpack_conv3_wgrad(gpk: torch.Tensor) -> torch.Tensor:
     return g
 
 
-def pack_convT_weights(w: torch.Tensor):
-    """(Cin,Cout,2,2,2) fp32 -> (wf [8*Cout,Cin] bf16, wd [Cin,8*Cout] bf16)."""
+def pack_convT_weights(w: torch.Tensor, dtype=BF16):
+    """(Cin,Cout,2,2,2) fp32 -> (wf [8*Cout,Cin], wd [Cin,8*Cout]) in ``dtype``."""
     _chk(w, torch.float32)
     cin, cout = w.shape[0], w.shape[1]
-    wf = torch.empty((8 * cout, cin), dtype=BF16, device=w.device)
-    wd = torch.empty((cin, 8 * cout), dtype=BF16, device=w.device)
-    _lib.call("pcrl_pack_convT_weights", w, wf, wd, cin, cout)
+    wf = torch.empty((8 * cout, cin), dtype=dtype, device=w.device)
+    wd = torch.empty((cin, 8 * cout), dtype=dtype, device=w.device)
+    _lib.call("pcrl_pack_convT_weights", w, wf, wd, cin, cout, DTYPE_CODE[dtype])
     return wf, wd
 
 
@@ -78,39 +88,39 @@ def unpack_convT_wgrad(gpk: torch.Tensor, cin: int, cout: int) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------ 3x3x3 conv
 def conv3d_k3_fprop(xp, wf, stats=None, per_sample=False, out_fp32=False):
-    _chk(xp, BF16), _chk(wf, BF16)
+    _chk(xp), _chk(wf, xp.dtype)
     n, d, h, w, cin = dims_of(xp)
     cout = wf.shape[1]
     assert wf.shape == (27, cout, cin)
-    y = torch.empty((n, d, h + 1, w, cout), dtype=torch.float32 if out_fp32 else BF16,
+    y = torch.empty((n, d, h + 1, w, cout), dtype=torch.float32 if out_fp32 else xp.dtype,
                     device=xp.device)
     if stats is not None:
         _chk(stats, torch.float64)
     _lib.call("pcrl_conv3d_k3_fprop", xp, wf, y, stats, int(per_sample), int(out_fp32), n, d, h, w,
-              cin, cout)
+              cin, cout, _dt(xp))
     return y
 
 
 def conv3d_k3_dgrad(dyp, wd):
-    _chk(dyp, BF16), _chk(wd, BF16)
+    _chk(dyp), _chk(wd, dyp.dtype)
     n, d, h, w, cout = dims_of(dyp)
     cin = wd.shape[1]
     assert wd.shape == (27, cin, cout)
-    dx = torch.empty((n, d, h + 1, w, cin), dtype=BF16, device=dyp.device)
-    _lib.call("pcrl_conv3d_k3_dgrad", dyp, wd, dx, n, d, h, w, cin, cout)
+    dx = torch.empty((n, d, h + 1, w, cin), dtype=dyp.dtype, device=dyp.device)
+    _lib.call("pcrl_conv3d_k3_dgrad", dyp, wd, dx, n, d, h, w, cin, cout, _dt(dyp))
     return dx
 
 
 def conv3d_k3_dgrad_unshuffled(dyp, wd):
     """Data gradient written coarse-major for the ConvTranspose that produced the conv input.
     Returns (scratch [N*(D/2)*(H/2+1)*(W/2), 8*Cin] bf16, colsum [Cin,2] fp64)."""
-    _chk(dyp, BF16), _chk(wd, BF16)
+    _chk(dyp), _chk(wd, dyp.dtype)
     n, d, h, w, cout = dims_of(dyp)
     cin = wd.shape[1]
     rows = n * (d // 2) * (h // 2 + 1) * (w // 2)
-    scratch = torch.empty((rows, 8 * cin), dtype=BF16, device=dyp.device)
+    scratch = torch.empty((rows, 8 * cin), dtype=dyp.dtype, device=dyp.device)
     colsum = torch.zeros((cin, 2), dtype=torch.float64, device=dyp.device)
-    _lib.call("pcrl_conv3d_k3_dgrad_unshuffled", dyp, wd, scratch, colsum, n, d, h, w, cin, cout)
+    _lib.call("pcrl_conv3d_k3_dgrad_unshuffled", dyp, wd, scratch, colsum, n, d, h, w, cin, cout, _dt(dyp))
     return scratch, colsum
 
 
@@ -118,65 +128,65 @@ def convT_bwd_from_scratch(scratch, xp, wd, need_dx=True):
     """ConvTranspose3d(k2,s2) gradient GEMMs on an already coarse-major output gradient."""
     n, d, h, w, cin = dims_of(xp)
     cout = scratch.shape[1] // 8
-    dx = torch.empty((n, d, h + 1, w, cin), dtype=BF16, device=xp.device) if need_dx else None
+    dx = torch.empty((n, d, h + 1, w, cin), dtype=xp.dtype, device=xp.device) if need_dx else None
     dw = torch.zeros((8 * cout, cin), dtype=torch.float32, device=xp.device)
-    _lib.call("pcrl_convT3d_k2s2_bwd", None, xp, wd, scratch, dx, dw, None, n, d, h, w, cin, cout)
+    _lib.call("pcrl_convT3d_k2s2_bwd", None, xp, wd, scratch, dx, dw, None, n, d, h, w, cin, cout, _dt(xp))
     return dx, dw
 
 
 def conv3d_k3_wgrad(dyp, xp, out=None):
     """Returns / accumulates into the packed gradient [27,Cout,Cin] fp32."""
-    _chk(dyp, BF16), _chk(xp, BF16)
+    _chk(dyp), _chk(xp, dyp.dtype)
     n, d, h, w, cout = dims_of(dyp)
     cin = xp.shape[-1]
     if out is None:
         out = torch.zeros((27, cout, cin), dtype=torch.float32, device=xp.device)
-    _lib.call("pcrl_conv3d_k3_wgrad", dyp, xp, out, n, d, h, w, cin, cout)
+    _lib.call("pcrl_conv3d_k3_wgrad", dyp, xp, out, n, d, h, w, cin, cout, _dt(dyp))
     return out
 
 
 # ------------------------------------------------------------------------------ stem
-def stem_conv_fprop(x, w, stats=None, per_sample=False):
-    """x (N,1,D,H,W) fp32, w (32,1,3,3,3) fp32 -> H-padded bf16 [N,D,H+1,W,32]."""
+def stem_conv_fprop(x, w, stats=None, per_sample=False, dtype=BF16):
+    """x (N,1,D,H,W) fp32, w (32,1,3,3,3) fp32 -> H-padded [N,D,H+1,W,32] in ``dtype``."""
     _chk(x, torch.float32), _chk(w, torch.float32)
     n, _, d, h, wd_ = x.shape
     assert w.shape[0] == 32 and w.shape[1] == 1
-    y = torch.empty((n, d, h + 1, wd_, 32), dtype=BF16, device=x.device)
-    _lib.call("pcrl_stem_conv_fprop", x, w, y, stats, int(per_sample), n, d, h, wd_)
+    y = torch.empty((n, d, h + 1, wd_, 32), dtype=dtype, device=x.device)
+    _lib.call("pcrl_stem_conv_fprop", x, w, y, stats, int(per_sample), n, d, h, wd_, DTYPE_CODE[dtype])
     return y
 
 
 def stem_conv_wgrad(dyp, x):
-    _chk(dyp, BF16), _chk(x, torch.float32)
+    _chk(dyp), _chk(x, torch.float32)
     n, _, d, h, w = x.shape
     dw = torch.zeros((32, 1, 3, 3, 3), dtype=torch.float32, device=x.device)
-    _lib.call("pcrl_stem_conv_wgrad", dyp, x, dw, n, d, h, w)
+    _lib.call("pcrl_stem_conv_wgrad", dyp, x, dw, n, d, h, w, _dt(dyp))
     return dw
 
 
 # ------------------------------------------------------------------------------ ConvTranspose
 def convT_fprop(xp, wf, bias):
-    _chk(xp, BF16), _chk(wf, BF16)
+    _chk(xp), _chk(wf, xp.dtype)
     n, d, h, w, cin = dims_of(xp)
     cout = wf.shape[0] // 8
-    y = torch.empty((n, 2 * d, 2 * h + 1, 2 * w, cout), dtype=BF16, device=xp.device)
-    _lib.call("pcrl_convT3d_k2s2_fprop", xp, wf, bias, y, n, d, h, w, cin, cout)
+    y = torch.empty((n, 2 * d, 2 * h + 1, 2 * w, cout), dtype=xp.dtype, device=xp.device)
+    _lib.call("pcrl_convT3d_k2s2_fprop", xp, wf, bias, y, n, d, h, w, cin, cout, _dt(xp))
     return y
 
 
 def convT_bwd(gp, xp, wd, need_dx=True, need_dw=True):
     """gp: gradient wrt the fine output.  Returns (dx padded bf16, dw_packed fp32, dbias fp32)."""
-    _chk(gp, BF16)
+    _chk(gp)
     n, d2, h2, w2, cout = dims_of(gp)
     d, h, w = d2 // 2, h2 // 2, w2 // 2
     cin = wd.shape[0]
     rows = n * d * (h + 1) * w
-    scratch = torch.empty((rows, 8 * cout), dtype=BF16, device=gp.device)
-    dx = torch.empty((n, d, h + 1, w, cin), dtype=BF16, device=gp.device) if need_dx else None
+    scratch = torch.empty((rows, 8 * cout), dtype=gp.dtype, device=gp.device)
+    dx = torch.empty((n, d, h + 1, w, cin), dtype=gp.dtype, device=gp.device) if need_dx else None
     dw = torch.zeros((8 * cout, cin), dtype=torch.float32, device=gp.device) if need_dw else None
     db = torch.zeros((cout,), dtype=torch.float32, device=gp.device)
     _lib.call("pcrl_convT3d_k2s2_bwd", gp, xp if need_dw else None, wd, scratch, dx, dw, db,
-              n, d, h, w, cin, cout)
+              n, d, h, w, cin, cout, _dt(gp))
     return dx, dw, db
 
 
@@ -196,21 +206,21 @@ def norm_finalize(stats, count, gamma, beta, conv_bias=None, running_mean=None, 
 
 def norm_act_fwd(yp, scale, shift, act="relu", prelu=None, want_full=True, want_pool=False,
                  want_avg=False, per_sample=False):
-    _chk(yp, BF16)
+    _chk(yp)
     n, d, h, w, c = dims_of(yp)
     a = torch.empty_like(yp) if want_full else None
-    pool = (torch.empty((n, d // 2, h // 2 + 1, w // 2, c), dtype=BF16, device=yp.device)
+    pool = (torch.empty((n, d // 2, h // 2 + 1, w // 2, c), dtype=yp.dtype, device=yp.device)
             if want_pool else None)
     avg = torch.zeros((n, c), dtype=torch.float32, device=yp.device) if want_avg else None
     _lib.call("pcrl_norm_act_fwd", yp, scale, shift, prelu, a, pool, avg, int(per_sample), ACT[act],
-              int(want_pool), n, d, h, w, c)
+              int(want_pool), n, d, h, w, c, _dt(yp))
     return a, pool, avg
 
 
 def norm_act_bwd(yp, g1, g2, gavg, scale, shift, mean, invstd, gamma, act="relu", prelu=None,
                  pool=False, per_sample=False):
     """Returns (dy padded bf16, sums [G,C,3] fp64 = (dbeta, dgamma, dprelu partial))."""
-    _chk(yp, BF16)
+    _chk(yp)
     n, d, h, w, c = dims_of(yp)
     g = scale.shape[0]
     sums = torch.zeros((g, c, 3), dtype=torch.float64, device=yp.device)
@@ -218,29 +228,29 @@ def norm_act_bwd(yp, g1, g2, gavg, scale, shift, mean, invstd, gamma, act="relu"
     dy = torch.empty_like(yp)
     for p in (0, 1):
         _lib.call("pcrl_norm_act_bwd", yp, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu,
-                  sums, dy, count, int(per_sample), ACT[act], int(pool), p, n, d, h, w, c)
+                  sums, dy, count, int(per_sample), ACT[act], int(pool), p, n, d, h, w, c, _dt(yp))
     return dy, sums
 
 
 # ------------------------------------------------------------------------------ heads
-def head_pack_weights(w3, w1=None):
-    """(1,C,3,3,3) [+ (1,C,1,1,1)] fp32 -> (wext [32,C] bf16, wextT [C,32] bf16)."""
+def head_pack_weights(w3, w1=None, dtype=BF16):
+    """(1,C,3,3,3) [+ (1,C,1,1,1)] fp32 -> (wext [32,C], wextT [C,32]) in ``dtype``."""
     c = w3.shape[1]
-    wext = torch.empty((32, c), dtype=BF16, device=w3.device)
-    wext_t = torch.empty((c, 32), dtype=BF16, device=w3.device)
+    wext = torch.empty((32, c), dtype=dtype, device=w3.device)
+    wext_t = torch.empty((c, 32), dtype=dtype, device=w3.device)
     _lib.call("pcrl_head_pack_weights", w3.contiguous(), None if w1 is None else w1.contiguous(),
-              wext, wext_t, c)
+              wext, wext_t, c, DTYPE_CODE[dtype])
     return wext, wext_t
 
 
 def head_fwd(ap, wext, b3, b1=None, stats=None, per_sample=False):
     """1-channel head convolutions of an H-padded activation: T = A * wext^T on the tensor cores,
     then the 27-point gather.  Returns (y1 (N,1,D,H,W) fp32, y0 or None)."""
-    _chk(ap, BF16), _chk(wext, BF16)
+    _chk(ap), _chk(wext, ap.dtype)
     n, d, h, w, c = dims_of(ap)
     rows = n * d * (h + 1) * w
     t_t = torch.empty((32, rows), dtype=torch.float32, device=ap.device)
-    _lib.call("pcrl_gemm_nt", ap, wext, t_t, None, rows, c, 32, rows, 2)
+    _lib.call("pcrl_gemm_nt", ap, wext, t_t, None, rows, c, 32, rows, 2, _dt(ap))
     y1 = torch.empty((n, 1, d, h, w), dtype=torch.float32, device=ap.device)
     y0 = torch.empty_like(y1) if b1 is not None else None
     _lib.call("pcrl_head_gather", t_t, b3, b1, y1, y0, stats, int(per_sample), n, d, h, w)
@@ -251,12 +261,12 @@ def head_bwd(ap, dy1, dy0, wext_t):
     """Returns (dA H-padded bf16, dwext [C,32] fp32: columns 0..26 = d w3 (tap order), 27 = d w1)."""
     n, d, h, w, c = dims_of(ap)
     rows = n * d * (h + 1) * w
-    d_t = torch.empty((rows, 32), dtype=BF16, device=ap.device)
-    _lib.call("pcrl_head_scatter", dy1, dy0, d_t, n, d, h, w)
-    da = torch.empty((n, d, h + 1, w, c), dtype=BF16, device=ap.device)
-    _lib.call("pcrl_gemm_nt", d_t, wext_t, da, None, rows, 32, c, c, 0)
+    d_t = torch.empty((rows, 32), dtype=ap.dtype, device=ap.device)
+    _lib.call("pcrl_head_scatter", dy1, dy0, d_t, n, d, h, w, _dt(ap))
+    da = torch.empty((n, d, h + 1, w, c), dtype=ap.dtype, device=ap.device)
+    _lib.call("pcrl_gemm_nt", d_t, wext_t, da, None, rows, 32, c, c, _dt(ap), _dt(ap))
     dwext = torch.zeros((c, 32), dtype=torch.float32, device=ap.device)
-    _lib.call("pcrl_gemm_tn", ap, d_t, dwext, rows, c, 32)
+    _lib.call("pcrl_gemm_tn", ap, d_t, dwext, rows, c, 32, _dt(ap))
     return da, dwext
 
 
@@ -287,38 +297,39 @@ def stem_conv_wgrad_gemm(dyp, x):
     """Stem weight gradient on the tensor cores: im2col of the 1-channel input to [rows,32]
     (27 taps), rows paired into 64-wide operands, dW = sum of the diagonal 32x32 blocks of
     gemm_tn(dY, X27)."""
-    _chk(dyp, BF16), _chk(x, torch.float32)
+    _chk(dyp), _chk(x, torch.float32)
     n, _, d, h, w = x.shape
     rows = n * d * (h + 1) * w
-    x27 = torch.empty((rows, 32), dtype=BF16, device=x.device)
-    _lib.call("pcrl_im2col27", x, x27, n, d, h, w)
+    x27 = torch.empty((rows, 32), dtype=dyp.dtype, device=x.device)
+    _lib.call("pcrl_im2col27", x, x27, n, d, h, w, _dt(dyp))
     out = torch.zeros((64, 64), dtype=torch.float32, device=x.device)
-    _lib.call("pcrl_gemm_tn", dyp, x27, out, rows // 2, 64, 64)
+    _lib.call("pcrl_gemm_tn", dyp, x27, out, rows // 2, 64, 64, _dt(dyp))
     dw = out[:32, :32] + out[32:, 32:]
     return dw[:, :27].reshape(32, 1, 3, 3, 3).contiguous()
 
 
 # ------------------------------------------------------------------------------ GEMMs / SGD
 def gemm_nt(a, b, bias=None, out_fp32=True):
-    _chk(a, BF16), _chk(b, BF16)
+    _chk(a), _chk(b, a.dtype)
     rows, k = a.shape
     cols = b.shape[0]
     if out_fp32 == "transposed":
         c = torch.empty((cols, rows), dtype=torch.float32, device=a.device)
-        _lib.call("pcrl_gemm_nt", a, b, c, bias, rows, k, cols, rows, 2)
+        _lib.call("pcrl_gemm_nt", a, b, c, bias, rows, k, cols, rows, 2, _dt(a))
         return c
+    out_fp32 = bool(out_fp32) or a.dtype == torch.float32
     c = torch.empty((rows, cols), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
-    _lib.call("pcrl_gemm_nt", a, b, c, bias, rows, k, cols, cols, int(out_fp32))
+    _lib.call("pcrl_gemm_nt", a, b, c, bias, rows, k, cols, cols, int(out_fp32), _dt(a))
     return c
 
 
 def gemm_tn(a, b, out=None):
-    _chk(a, BF16), _chk(b, BF16)
+    _chk(a), _chk(b, a.dtype)
     rows, p = a.shape
     q = b.shape[1]
     if out is None:
         out = torch.zeros((p, q), dtype=torch.float32, device=a.device)
-    _lib.call("pcrl_gemm_tn", a, b, out, rows, p, q)
+    _lib.call("pcrl_gemm_tn", a, b, out, rows, p, q, _dt(a))
     return out
 
 

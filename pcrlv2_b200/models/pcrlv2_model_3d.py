@@ -36,17 +36,18 @@ def bump_param_epoch():
     _PARAM_EPOCH[0] += 1
 
 
-def _packed(module, kind):
-    """bf16 tensor-core layouts of a conv weight, cached until the parameter changes."""
+def _packed(module, kind, dtype=torch.bfloat16):
+    """Tensor-core operand layouts of a conv weight in the activation storage type, cached until
+    the parameter changes."""
     w = module.weight
-    key = (w._version, _PARAM_EPOCH[0], w.data_ptr())
+    key = (w._version, _PARAM_EPOCH[0], w.data_ptr(), dtype)
     cache = getattr(module, "_pcrl_packed", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():
             if kind == "conv3":
-                pk = K.pack_conv3_weights(w.detach().contiguous())
+                pk = K.pack_conv3_weights(w.detach().contiguous(), dtype=dtype)
             elif kind == "convT":
-                pk = K.pack_convT_weights(w.detach().contiguous())
+                pk = K.pack_convT_weights(w.detach().contiguous(), dtype=dtype)
             elif kind == "head":    # (ds conv, final conv or None) -> wext [32,C], wextT [C,32]
                 raise ValueError("use _packed_head")
             else:
@@ -56,15 +57,15 @@ def _packed(module, kind):
     return cache[1]
 
 
-def _packed_head(ds, fin):
+def _packed_head(ds, fin, dtype=torch.bfloat16):
     """bf16 GEMM operands of the 1-channel head convolutions (deep-supervision conv [+ 1x1x1 output
     conv]), cached until either weight changes."""
-    key = (ds.weight._version, ds.weight.data_ptr(), _PARAM_EPOCH[0],
+    key = (ds.weight._version, ds.weight.data_ptr(), _PARAM_EPOCH[0], dtype,
            None if fin is None else (fin.weight._version, fin.weight.data_ptr()))
     cache = getattr(ds, "_pcrl_head", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():
-            pk = K.head_pack_weights(ds.weight.detach(), None if fin is None else fin.weight.detach())
+            pk = K.head_pack_weights(ds.weight.detach(), None if fin is None else fin.weight.detach(), dtype=dtype)
         cache = (key, pk)
         ds._pcrl_head = cache
     return cache[1]
@@ -72,7 +73,7 @@ def _packed_head(ds, fin):
 
 class _Cfg:
     """Static (non-tensor) configuration of one fused LUConv call."""
-    __slots__ = ("stem", "pool", "tail", "final", "act", "norm", "training", "conv", "bn", "ds", "fin", "up")
+    __slots__ = ("stem", "pool", "tail", "final", "act", "norm", "training", "conv", "bn", "ds", "fin", "up", "dtype")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -95,7 +96,7 @@ class _LUConvFn(torch.autograd.Function):
         use_batch_stats = cfg.training or per_sample
         x_coarse = None
         if cfg.up is not None:
-            wtf, _ = _packed(cfg.up, "convT")
+            wtf, _ = _packed(cfg.up, "convT", cfg.dtype)
             x_coarse = x
             x = K.convT_fprop(x, wtf, up_b.detach().contiguous())
         if cfg.stem:
@@ -106,9 +107,9 @@ class _LUConvFn(torch.autograd.Function):
         stats = (torch.zeros((groups, cout, 2), dtype=torch.float64, device=x.device)
                  if use_batch_stats else None)
         if cfg.stem:
-            y = K.stem_conv_fprop(x.contiguous(), weight.detach().contiguous(), stats, per_sample)
+            y = K.stem_conv_fprop(x.contiguous(), weight.detach().contiguous(), stats, per_sample, dtype=cfg.dtype)
         else:
-            wf, _ = _packed(cfg.conv, "conv3")
+            wf, _ = _packed(cfg.conv, "conv3", cfg.dtype)
             y = K.conv3d_k3_fprop(x, wf, stats, per_sample)
         if use_batch_stats:
             count = d * h * w * (1 if per_sample else n)
@@ -130,7 +131,7 @@ class _LUConvFn(torch.autograd.Function):
                                         want_pool=cfg.pool, want_avg=cfg.tail, per_sample=per_sample)
         outs = [pooled if cfg.pool else a]
         if cfg.tail:
-            wext, _ = _packed_head(cfg.ds, cfg.fin)
+            wext, _ = _packed_head(cfg.ds, cfg.fin, cfg.dtype)
             st1 = torch.zeros((groups, 1, 2), dtype=torch.float64, device=x.device)
             y1, y0 = K.head_fwd(a, wext, ds_b.detach(), fin_b.detach() if cfg.final else None,
                                 st1, per_sample)
@@ -158,7 +159,7 @@ class _LUConvFn(torch.autograd.Function):
             dy1 = g_y1.contiguous() if g_y1 is not None else torch.zeros(
                 (n, 1, d, h, w), dtype=torch.float32, device=y.device)
             dy0 = g_y0.contiguous() if (cfg.final and g_y0 is not None) else None
-            _, wext_t = _packed_head(cfg.ds, cfg.fin)
+            _, wext_t = _packed_head(cfg.ds, cfg.fin, cfg.dtype)
             g2, dwext = K.head_bwd(a, dy1, dy0, wext_t)
             if g_y1 is not None:
                 grads[6] = dwext[:, :27].reshape(1, cout, 3, 3, 3)
@@ -182,12 +183,12 @@ class _LUConvFn(torch.autograd.Function):
         if cfg.stem:
             grads[1] = K.stem_conv_wgrad_gemm(dy, x)
         else:
-            _, wd = _packed(cfg.conv, "conv3")
+            _, wd = _packed(cfg.conv, "conv3", cfg.dtype)
             grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
             if cfg.up is not None:
                 # data gradient lands coarse-major; its column sums are the ConvTranspose bias gradient
                 scratch, colsum = K.conv3d_k3_dgrad_unshuffled(dy, wd)
-                _, wtd = _packed(cfg.up, "convT")
+                _, wtd = _packed(cfg.up, "convT", cfg.dtype)
                 dxc, dwt = K.convT_bwd_from_scratch(scratch, x_coarse, wtd, need_dx=ctx.needs_input_grad[0])
                 cin_t, cout_t = cfg.up.weight.shape[0], cfg.up.weight.shape[1]
                 grads[0] = dxc
@@ -284,12 +285,12 @@ class LUConv(nn.Module):
         self.act, self.norm = act, norm
         self.in_chan, self.out_chan = in_chan, out_chan
 
-    def run(self, x, pool=False, tail=None, final=None, up=None):
-        """x: fp32 (N,1,D,H,W) for the stem, otherwise an H-padded bf16 activation.  ``up``: the
-        ConvTranspose3d module to apply to x first (UpTransition)."""
+    def run(self, x, pool=False, tail=None, final=None, up=None, dtype=torch.bfloat16):
+        """x: fp32 (N,1,D,H,W) for the stem, otherwise an H-padded activation in ``dtype``.
+        ``up``: the ConvTranspose3d module to apply to x first (UpTransition)."""
         cfg = _Cfg(stem=self.in_chan == 1, pool=pool, tail=tail is not None, final=final is not None,
                    act=self.act, norm=self.norm, training=self.training, conv=self.conv1, bn=self.bn1,
-                   ds=tail.conv1 if tail is not None else None, fin=final, up=up)
+                   ds=tail.conv1 if tail is not None else None, fin=final, up=up, dtype=dtype)
         prelu = self.activation.weight if self.act == "prelu" else None
         return _LUConvFn.apply(
             x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, prelu,
@@ -302,7 +303,7 @@ class LUConv(nn.Module):
 
     def forward(self, x):
         """Stand-alone use with the reference's NCDHW fp32 convention."""
-        inp = x.float() if self.in_chan == 1 else K.pad_ndhwc(x)
+        inp = x.float() if self.in_chan == 1 else K.pad_ndhwc(x)  # bf16 storage
         if self.in_chan != 1 and self.in_chan % 32:
             raise NotImplementedError("LUConv needs in_chan == 1 or a multiple of 32")
         return K.unpad_ndhwc(self.run(inp)[0])
@@ -323,8 +324,8 @@ class DownTransition(nn.Module):
         super().__init__()
         self.ops = _make_nConv(in_channel, depth, act, norm)
 
-    def run(self, x, pool):
-        return self.ops[1].run(self.ops[0].run(x)[0], pool=pool)[0]
+    def run(self, x, pool, dtype=torch.bfloat16):
+        return self.ops[1].run(self.ops[0].run(x, dtype=dtype)[0], pool=pool, dtype=dtype)[0]
 
 
 class UpTransition(nn.Module):
@@ -344,9 +345,9 @@ class UpTransition(nn.Module):
         self.deep_supervision_head = LUConv(channels, 1, "sigmoid", norm)
         self.norm = norm
 
-    def run(self, x, final=None):
-        h = self.ops[0].run(x, up=self.up_conv)[0]
-        outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final)
+    def run(self, x, final=None, dtype=torch.bfloat16):
+        h = self.ops[0].run(x, up=self.up_conv, dtype=dtype)[0]
+        outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final, dtype=dtype)
         a, avg, y1, st1 = outs[0], outs[1], outs[2], outs[3]
         y0 = outs[4] if final is not None else None
         x_pro = self.bn(avg)
@@ -366,8 +367,17 @@ class OutputTransition(nn.Module):
 
 
 class PCRLv23d(nn.Module):
-    def __init__(self, n_class=1, act="relu", norm="bn", in_channels=1, low_dim=128, student=False):
+    def __init__(self, n_class=1, act="relu", norm="bn", in_channels=1, low_dim=128, student=False,
+                 precision="bf16"):
+        """Same arguments as the reference (:98) plus ``precision``: the storage type of the
+        activations between kernels.  ``"bf16"`` (default): bf16 storage, bf16 tensor-core operands.
+        ``"fp32"``: fp32 storage, TF32 tensor-core operands -- what the reference itself runs on an
+        Ampere-or-newer GPU (torch's default ``cudnn.allow_tf32``).  fp32 accumulation, statistics
+        and parameters in both."""
         super().__init__()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
         if in_channels != 1:
             raise NotImplementedError("in_channels must be 1 (CT sub-volumes, the reference default)")
         self.maxpool = nn.MaxPool3d(2)
@@ -388,13 +398,14 @@ class PCRLv23d(nn.Module):
         if x.dim() != 5 or x.shape[1] != 1 or any(s % 8 for s in x.shape[2:]):
             raise ValueError("expected (B,1,D,H,W) with D,H,W multiples of 8, got %s" % (tuple(x.shape),))
         x = x.float().contiguous()
-        h = self.down_tr64.run(x, pool=True)
-        h = self.down_tr128.run(h, pool=True)
-        h = self.down_tr256.run(h, pool=True)
-        h = self.down_tr512.run(h, pool=False)
-        h, pro_256, pre_256, m256, _ = self.up_tr256.run(h)
-        h, pro_128, pre_128, m128, _ = self.up_tr128.run(h)
-        h, pro_64, pre_64, m64, y0 = self.up_tr64.run(h, final=self.out_tr.final_conv)
+        dt = torch.float32 if self.precision == "fp32" else torch.bfloat16
+        h = self.down_tr64.run(x, pool=True, dtype=dt)
+        h = self.down_tr128.run(h, pool=True, dtype=dt)
+        h = self.down_tr256.run(h, pool=True, dtype=dt)
+        h = self.down_tr512.run(h, pool=False, dtype=dt)
+        h, pro_256, pre_256, m256, _ = self.up_tr256.run(h, dtype=dt)
+        h, pro_128, pre_128, m128, _ = self.up_tr128.run(h, dtype=dt)
+        h, pro_64, pre_64, m64, y0 = self.up_tr64.run(h, final=self.out_tr.final_conv, dtype=dt)
         middle_masks = []
         if not local:
             middle_masks.append(F.interpolate(m256, scale_factor=4, mode="trilinear"))

@@ -358,3 +358,134 @@ def test_dgrad_unshuffled_feeds_convT_bwd(shape):
     assert rel(K.unpad_ndhwc(dxc), xc.grad) < 2e-2
     assert rel(K.unpack_convT_wgrad(dwt, cin, cin), wt.grad) < 2e-2
     assert rel(colsum[:, 0], bt.grad) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 storage / TF32 tensor-core operands (precision="fp32").  Inputs are made TF32-representable
+# (10-bit mantissa) so that the tensor-core products are exact and only accumulation order differs.
+def q32(t):
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+F32 = torch.float32
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3d_fp32_tf32(shape):
+    n, d, h, w, cin, cout = shape
+    torch.manual_seed(20)
+    x = q32(torch.randn(n, cin, d, h, w, device=DEV)).requires_grad_(True)
+    wt = q32(torch.randn(cout, cin, 3, 3, 3, device=DEV) / (27 * cin) ** 0.5).requires_grad_(True)
+    ref = F.conv3d(x, wt, padding=1)
+    dy = q32(torch.randn_like(ref))
+    ref.backward(dy)
+    xp = K.pad_ndhwc(x.detach(), F32)
+    wf, wd = K.pack_conv3_weights(wt.detach(), dtype=F32)
+    stats = torch.zeros(cout, 2, dtype=torch.float64, device=DEV)
+    y = K.conv3d_k3_fprop(xp, wf, stats=stats)
+    assert y.dtype == F32
+    got = K.unpad_ndhwc(y)
+    assert rel(got, ref) < TOL32
+    assert rel(stats[:, 1], (got.double() ** 2).sum(dim=(0, 2, 3, 4))) < 1e-5
+    dyp = K.pad_ndhwc(dy, F32)
+    assert rel(K.unpad_ndhwc(K.conv3d_k3_dgrad(dyp, wd)), x.grad) < TOL32
+    if cout % 64 == 0:
+        assert rel(K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dyp, xp)), wt.grad) < TOL32
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2, 2, 128, 128), (2, 8, 8, 4, 128, 128), (1, 2, 3, 5, 512, 512)])
+def test_convT_fp32(shape):
+    n, d, h, w, cin, cout = shape
+    torch.manual_seed(21)
+    x = q32(torch.randn(n, cin, d, h, w, device=DEV)).requires_grad_(True)
+    wt = q32(torch.randn(cin, cout, 2, 2, 2, device=DEV) / cin ** 0.5).requires_grad_(True)
+    b = torch.randn(cout, device=DEV, requires_grad=True)
+    ref = F.conv_transpose3d(x, wt, b, stride=2)
+    wf, wd = K.pack_convT_weights(wt.detach(), dtype=F32)
+    xp = K.pad_ndhwc(x.detach(), F32)
+    yp = K.convT_fprop(xp, wf, b.detach())
+    # outputs that feed the next tensor-core kernel are stored tf32-rounded (2^-11 relative)
+    assert rel(K.unpad_ndhwc(yp), ref) < 6e-4
+    assert yp[:, :, 0].abs().max().item() == 0
+    g = q32(torch.randn_like(ref))
+    ref.backward(g)
+    dx, dw, db = K.convT_bwd(K.pad_ndhwc(g, F32), xp, wd)
+    assert rel(K.unpad_ndhwc(dx), x.grad) < 6e-4
+    assert rel(K.unpack_convT_wgrad(dw, cin, cout), wt.grad) < TOL32
+    assert rel(db, b.grad) < TOL32
+    # fused path: conv data gradient written coarse-major
+    wc = q32(torch.randn(64, cout, 3, 3, 3, device=DEV) / (27 * cout) ** 0.5)
+    x.grad = None; wt.grad = None; b.grad = None
+    up = F.conv_transpose3d(x, wt, b, stride=2)
+    y = F.conv3d(up, wc, padding=1)
+    dy = q32(torch.randn_like(y))
+    y.backward(dy)
+    _, wcd = K.pack_conv3_weights(wc, dtype=F32)
+    scratch, colsum = K.conv3d_k3_dgrad_unshuffled(K.pad_ndhwc(dy, F32), wcd)
+    dxc, dwt = K.convT_bwd_from_scratch(scratch, xp, wd)
+    # (the intermediate gradient is not TF32-representable: one TF32 rounding of an operand)
+    assert rel(K.unpad_ndhwc(dxc), x.grad) < 2e-3
+    assert rel(K.unpack_convT_wgrad(dwt, cin, cout), wt.grad) < 2e-3
+    assert rel(colsum[:, 0], b.grad) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["full", "pool", "avg"])
+def test_norm_act_fp32(mode):
+    n, c, d, h, w = 3, 64, 4, 6, 8
+    torch.manual_seed(22)
+    y = (torch.randn(n, c, d, h, w, device=DEV) * 2 + 0.3).requires_grad_(True)
+    gamma = (torch.rand(c, device=DEV) + 0.5).requires_grad_(True)
+    beta = (torch.randn(c, device=DEV) * 0.2).requires_grad_(True)
+    yp = K.pad_ndhwc(y.detach(), F32)
+    yd = y.detach().double()
+    stats = torch.stack([yd.sum((0, 2, 3, 4)), (yd ** 2).sum((0, 2, 3, 4))], -1).reshape(1, c, 2).contiguous()
+    scale, shift, mean, invstd = K.norm_finalize(stats, n * d * h * w, gamma.detach(), beta.detach())
+    a_ref = F.relu(F.batch_norm(y, None, None, gamma, beta, True, 0.1, 1e-5))
+    a, pool, avg = K.norm_act_fwd(yp, scale, shift, "relu", None, want_full=(mode != "pool"),
+                                  want_pool=(mode == "pool"), want_avg=(mode == "avg"))
+    out_ref = F.max_pool3d(a_ref, 2) if mode == "pool" else a_ref
+    got = pool if mode == "pool" else a
+    assert got.dtype == F32 and rel(K.unpad_ndhwc(got), out_ref) < 6e-4   # stored tf32-rounded
+    assert got[:, :, 0].abs().max().item() == 0
+    g1 = torch.randn_like(out_ref)
+    loss = (out_ref * g1).sum()
+    gavg = None
+    if mode == "avg":
+        assert rel(avg / (d * h * w), a_ref.mean(dim=(2, 3, 4))) < 1e-5
+        gavg = torch.randn(n, c, device=DEV)
+        loss = loss + (a_ref.mean(dim=(2, 3, 4)) * gavg).sum()
+    loss.backward()
+    dy, sums = K.norm_act_bwd(yp, K.pad_ndhwc(g1, F32), None, gavg, scale, shift, mean, invstd,
+                              gamma.detach(), "relu", None, pool=(mode == "pool"))
+    assert rel(K.unpad_ndhwc(dy), y.grad) < 6e-4
+    assert rel(sums[..., 1].sum(0), gamma.grad) < 1e-4
+
+
+def test_heads_and_stem_fp32():
+    n, d, h, w, c = 2, 4, 6, 8, 64
+    torch.manual_seed(23)
+    a = q32(torch.randn(n, c, d, h, w, device=DEV)).requires_grad_(True)
+    w3 = q32(torch.randn(1, c, 3, 3, 3, device=DEV) / (27 * c) ** 0.5).requires_grad_(True)
+    b3 = torch.randn(1, device=DEV)
+    w1 = q32(torch.randn(1, c, 1, 1, 1, device=DEV) / c ** 0.5).requires_grad_(True)
+    b1 = torch.randn(1, device=DEV)
+    y1_ref, y0_ref = F.conv3d(a, w3, b3, padding=1), F.conv3d(a, w1, b1)
+    ap = K.pad_ndhwc(a.detach(), F32)
+    wext, wext_t = K.head_pack_weights(w3.detach(), w1.detach(), dtype=F32)
+    y1, y0 = K.head_fwd(ap, wext, b3, b1)
+    assert rel(y1, y1_ref) < TOL32 and rel(y0, y0_ref) < TOL32
+    dy1, dy0 = q32(torch.randn_like(y1_ref)), q32(torch.randn_like(y0_ref))
+    ((y1_ref * dy1).sum() + (y0_ref * dy0).sum()).backward()
+    da, dwext = K.head_bwd(ap, dy1, dy0, wext_t)
+    assert rel(K.unpad_ndhwc(da), a.grad) < 6e-4
+    assert rel(dwext[:, :27].reshape(1, c, 3, 3, 3), w3.grad) < TOL32
+    assert rel(dwext[:, 27].reshape(1, c, 1, 1, 1), w1.grad) < TOL32
+    # stem
+    x = q32(torch.randn(n, 1, 8, 8, 8, device=DEV))
+    wt = torch.randn(32, 1, 3, 3, 3, device=DEV, requires_grad=True)
+    ref = F.conv3d(x, wt, padding=1)
+    yp = K.stem_conv_fprop(x, wt.detach(), dtype=F32)
+    assert yp.dtype == F32 and rel(K.unpad_ndhwc(yp), ref) < 6e-4
+    dy = q32(torch.randn_like(ref))
+    ref.backward(dy)
+    assert rel(K.stem_conv_wgrad_gemm(K.pad_ndhwc(dy, F32), x), wt.grad) < TOL32

