@@ -44,6 +44,8 @@ struct IgemmParams {
   int tf32;                   // operands are fp32 in memory, MMA kind::tf32 (K = 8 per instruction)
   int tiles_per_group, groups, col_chunks, nsamples;
   long long total_tiles;
+  int cs;                     // CTAs per cluster sharing (multicasting) the filter tiles
+  long long tiles_per_chunk, steps_per_chunk, total_steps;
   int seg_len;                // rows of one segment that belong to this tile family
   long long rows_total;       // PLAIN: number of A rows
   // epilogue
@@ -54,9 +56,11 @@ struct IgemmParams {
   double* stats;
 };
 
-__device__ __forceinline__ void umma_any(int tf32, uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc,
-                                         uint32_t acc) {
-  if (tf32) umma_tf32(d, ad, bd, idesc, acc);
+// the operand kind is a compile-time parameter: a run-time select leaves a predicated-off
+// UTC*MMA next to every live one, which costs ~20 % of the tensor-pipe issue rate
+template <int TF32>
+__device__ __forceinline__ void umma_any(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  if (TF32) umma_tf32(d, ad, bd, idesc, acc);
   else umma_bf16(d, ad, bd, idesc, acc);
 }
 
@@ -67,24 +71,32 @@ __device__ __forceinline__ int floordiv(int a, int b) {
 
 struct TileCoord {
   int col0, n, f0, t_local;   // first output column, sample, first flat row, first row inside the segment
+  bool live;                  // false: padding step of a cluster (no tile for this CTA)
 };
-__device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, long long tile) {
+// step -> tile of this CTA.  The cs CTAs of a cluster walk the same steps; within a step they own cs
+// consecutive tiles of ONE column chunk, so they consume identical filter tiles.
+__device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, long long step, int rank) {
   TileCoord c;
+  const long long chunk = step / p.steps_per_chunk;
+  const long long lt = (step % p.steps_per_chunk) * p.cs + rank;
+  c.live = lt < p.tiles_per_chunk;
+  const long long tile = c.live ? lt : 0;
   const int t = (int)(tile % p.tiles_per_group);
   long long r = tile / p.tiles_per_group;
   const int g = (int)(r % p.groups);
   r /= p.groups;
-  c.n = (int)(r % p.nsamples);
-  c.col0 = (int)(r / p.nsamples) * p.nc;
+  c.n = (int)r;
+  c.col0 = (int)chunk * p.nc;
   c.t_local = t * p.m_cta;
   c.f0 = g * p.P * p.PL + c.t_local;
   return c;
 }
 
+template <int TF32>
 __global__ void __launch_bounds__(224, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb1,
                     const __grid_constant__ CUtensorMap tb2, const __grid_constant__ CUtensorMap tb3,
-                    const IgemmParams p) {
+                    const __grid_constant__ CUtensorMap tbs, const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_s = smem;
@@ -103,7 +115,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.sa; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.sb; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < p.sb; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], (uint32_t)p.cs); }
     for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     fence_barrier_init();
     tma_prefetch_desc(&ta);
@@ -118,6 +130,11 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const int rank = (p.cs > 1) ? (int)cluster_ctarank() : 0;
+  const long long first_step = (p.cs > 1) ? (long long)(blockIdx.x / p.cs) : (long long)blockIdx.x;
+  const long long step_stride = (p.cs > 1) ? (long long)(gridDim.x / p.cs) : (long long)gridDim.x;
+  const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+  if (p.cs > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive
   const uint32_t tmem = *tmem_slot;
   const int acc_cols = p.mt * p.P * p.nc;
   const int nslab = (p.mode == IG_CONV) ? p.P + 2 : 1;
@@ -128,8 +145,9 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     int sa = 0, pa = 0;
     const uint32_t a_tx = (p.mode == IG_CONV) ? (uint32_t)(p.nh_box * p.Wp * p.row_bytes)
                                               : (uint32_t)(p.mt * 128 * p.row_bytes);
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(p, tile);
+    for (long long step = first_step; step < p.total_steps; step += step_stride) {
+      const TileCoord tc = tile_coord(p, step, rank);
+      if (!tc.live) continue;
       int mr_first = 0;
       if (p.mode == IG_CONV) mr_first = floordiv(tc.f0 - p.Wp - 1, p.Wp);
       for (int kb = 0; kb < p.kblocks; kb++) {
@@ -156,8 +174,8 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     // =============================== TMA producer for the filter tiles: its own warp, so weight
     // prefetch runs sb tiles ahead of the MMAs independently of the slab ring
     int sb = 0, pb = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(p, tile);
+    for (long long step = first_step; step < p.total_steps; step += step_stride) {
+      const TileCoord tc = tile_coord(p, step, rank);   // col0 is common to the whole cluster
       for (int kb = 0; kb < p.kblocks; kb++) {
         for (int s = 0; s < nslab; s++) {
           const int q = s - 1;
@@ -170,11 +188,19 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
           const CUtensorMap* tb = cnt == 1 ? &tb1 : (cnt == 2 ? &tb2 : &tb3);
           const uint32_t b_tx = (uint32_t)(cnt * p.nc * p.row_bytes);
           for (int j = 0; j < p.tpg; j++) {
-            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_wait(&b_empty[sb], pb ^ 1);   // cs > 1: every CTA of the cluster released this slot
             if (elect_one()) {
               mbar_expect_tx(&b_full[sb], b_tx);
-              tma_load_3d(b_s + (size_t)sb * p.b_bytes, tb, &b_full[sb], kb * p.kc, tc.col0,
-                          j * 3 + dzr_lo);
+              if (p.cs == 1) {
+                tma_load_3d(b_s + (size_t)sb * p.b_bytes, tb, &b_full[sb], kb * p.kc, tc.col0,
+                            j * 3 + dzr_lo);
+              } else {
+                // this CTA fetches 1/cs of the rows of every dz block and multicasts them
+                const int share = p.nc / p.cs;
+                for (int z = 0; z < cnt; z++)
+                  tma_load_3d_mc(b_s + (size_t)sb * p.b_bytes + (size_t)(z * p.nc + rank * share) * p.row_bytes,
+                                 &tbs, &b_full[sb], kb * p.kc, tc.col0 + rank * share, j * 3 + dzr_lo + z, cmask);
+              }
             }
             __syncwarp();
             if (++sb == p.sb) { sb = 0; pb ^= 1; }
@@ -188,13 +214,24 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     const uint32_t layout = (p.row_bytes == 128) ? LAYOUT_SW128 : LAYOUT_SW64;
     const uint64_t desc_hi = make_smem_desc(0, 16, 8 * p.row_bytes, layout);
     const int ksteps = p.row_bytes / 32;
-    const uint32_t fmt = p.tf32 ? 2u : 1u;
+    const uint32_t fmt = TF32 ? 2u : 1u;
     const uint32_t idesc_nc = make_idesc(fmt, 128, (uint32_t)p.nc, 0, 0);
     int it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-      const TileCoord tc = tile_coord(p, tile);
+    for (long long step = first_step; step < p.total_steps; step += step_stride) {
+      const TileCoord tc = tile_coord(p, step, rank);
+      if (!tc.live) {
+        // padding step: keep the cluster's filter ring moving (consume and release every stage)
+        for (int i = 0; i < p.kblocks * nslab * p.tpg; i++) {
+          mbar_wait(&b_full[sb], pb);
+          if (elect_one()) umma_commit_mc(&b_empty[sb], cmask);
+          __syncwarp();
+          if (++sb == p.sb) { sb = 0; pb ^= 1; }
+        }
+        continue;
+      }
       const int buf = (p.nbuf == 2) ? (it & 1) : 0;
       const int use = (p.nbuf == 2) ? (it >> 1) : it;      // how often this buffer was used before
+      it++;
       mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
       tc_fence_after();
       const uint32_t acc = tmem + buf * acc_cols;
@@ -230,15 +267,16 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
                 int ks = 0;
                 if (first) {
                   // split: old blocks accumulate, the new block (last of the range) is overwritten
-                  if (cnt > 1) umma_any(p.tf32, d_addr, ad0, bd0, idesc_old, 1u);
+                  if (cnt > 1) umma_any<TF32>(d_addr, ad0, bd0, idesc_old, 1u);
                   const uint32_t boff = (uint32_t)((cnt - 1) * p.nc) * p.row_bytes;
-                  umma_any(p.tf32, d_addr + (uint32_t)((cnt - 1) * p.nc), ad0, bd0 + (boff >> 4), idesc_nc, 0u);
+                  umma_any<TF32>(d_addr + (uint32_t)((cnt - 1) * p.nc), ad0, bd0 + (boff >> 4), idesc_nc, 0u);
                   ks = 1;
                 }
                 for (; ks < ksteps; ks++)
-                  umma_any(p.tf32, d_addr, ad0 + 2 * ks, bd0 + 2 * ks, idesc_all, 1u);
+                  umma_any<TF32>(d_addr, ad0 + 2 * ks, bd0 + 2 * ks, idesc_all, 1u);
               }
-              umma_commit(&b_empty[sb]);
+              if (p.cs > 1) umma_commit_mc(&b_empty[sb], cmask);
+              else umma_commit(&b_empty[sb]);
             }
             __syncwarp();
             if (++sb == p.sb) { sb = 0; pb ^= 1; }
@@ -257,10 +295,12 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     int it = 0;
     int cur_col0 = -1, cur_n = -1;
     const int et = threadIdx.x - 64;  // 0..127
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-      const TileCoord tc = tile_coord(p, tile);
+    for (long long step = first_step; step < p.total_steps; step += step_stride) {
+      const TileCoord tc = tile_coord(p, step, rank);
+      if (!tc.live) continue;
       const int buf = (p.nbuf == 2) ? (it & 1) : 0;
       const int use = (p.nbuf == 2) ? (it >> 1) : it;
+      it++;
       if (p.has_stats && (tc.col0 != cur_col0 || (p.stats_per_sample && tc.n != cur_n))) {
         // flush the per-CTA partial statistics of the previous (column chunk, sample)
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -414,6 +454,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into its smem
   if (warp == 1) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
@@ -424,9 +465,17 @@ static int pow2_cols(int c) {
   return t;
 }
 
+static inline CUtensorMapDataType tma_dtype(int tf32) {
+  return tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+static inline CUtensorMapSwizzle tma_swizzle(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+}
+
 struct IgemmLaunch {
   IgemmParams p;
-  CUtensorMap ta, tb[3];
+  CUtensorMap ta, tb[3], tbs;
+  const void* w_ptr; int w_K, w_cols, w_taps;
 };
 
 static int finish_and_launch(IgemmLaunch& L, cudaStream_t stream) {
@@ -456,26 +505,60 @@ static int finish_and_launch(IgemmLaunch& L, cudaStream_t stream) {
                       (2 * p.sa + 2 * p.sb + 4) * 8 + 16 + 2 * p.nc * 4 + 1024;
   static bool configured = false;
   if (!configured) {
-    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel,
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  igemm_kmajor_kernel<<<(unsigned)grid, 224, smem, stream>>>(L.ta, L.tb[0], L.tb[1], L.tb[2], p);
-  PCRL_CHECK_LAUNCH();
+  // cluster of cs CTAs that walk the same steps and multicast the filter tiles to each other
+  // (cuts the dominant L2 -> shared-memory traffic of the kernel by cs)
+  p.cs = 1;
+  if (p.mode == IG_CONV) {
+    p.cs = 1;   // multicast halves L2 reads but not the bytes each SM ingests, which is the limit
+    const char* e = getenv("PCRL_IGEMM_CS");
+    if (e && atoi(e) >= 1) p.cs = atoi(e);
+    while (p.cs > 1 && ((p.nc / p.cs) % 8 != 0 || p.nc % p.cs != 0)) p.cs >>= 1;
+  }
+  p.tiles_per_chunk = (long long)p.tiles_per_group * p.groups * p.nsamples;
+  p.steps_per_chunk = (p.tiles_per_chunk + p.cs - 1) / p.cs;
+  p.total_steps = p.steps_per_chunk * p.col_chunks;
+  if (p.cs > 1) {
+    const uint64_t elt = p.tf32 ? 4 : 2;
+    uint64_t dims[3] = {(uint64_t)L.w_K, (uint64_t)L.w_cols, (uint64_t)L.w_taps};
+    uint64_t str[2] = {(uint64_t)L.w_K * elt, (uint64_t)L.w_K * L.w_cols * elt};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)(p.nc / p.cs), 1};
+    int rc = encode_map(&L.tbs, tma_dtype(p.tf32), 3, L.w_ptr, dims, str, box, tma_swizzle(p.row_bytes));
+    if (rc) return rc;
+  } else {
+    L.tbs = L.tb[0];
+  }
+  long long clusters = num_sms() / p.cs;
+  if (p.total_steps < clusters) clusters = p.total_steps;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(clusters * p.cs));
+  cfg.blockDim = dim3(224);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (p.tf32)
+    PCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<1>, L.ta, L.tb[0], L.tb[1], L.tb[2], L.tbs, p));
+  else
+    PCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<0>, L.ta, L.tb[0], L.tb[1], L.tb[2], L.tbs, p));
   return PCRL_OK;
 }
 
 // B operand maps: packed weights viewed as (K, cols, taps) bf16, boxes (kc, nc, cnt), cnt = 1..3
-static inline CUtensorMapDataType tma_dtype(int tf32) {
-  return tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-}
-static inline CUtensorMapSwizzle tma_swizzle(int row_bytes) {
-  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-}
-
 static int make_b_maps(IgemmLaunch& L, const void* w, int K, int cols, int taps) {
   const uint64_t elt = L.p.tf32 ? 4 : 2;
+  L.w_ptr = w; L.w_K = K; L.w_cols = cols; L.w_taps = taps;
   for (int cnt = 1; cnt <= 3; cnt++) {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)cols, (uint64_t)taps};
     uint64_t str[2] = {(uint64_t)K * elt, (uint64_t)K * cols * elt};
@@ -541,7 +624,6 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
   p.tiles_per_group = (p.seg_len + p.m_cta - 1) / p.m_cta;
   p.col_chunks = Cout / p.nc;
   p.nsamples = N;
-  p.total_tiles = (long long)p.tiles_per_group * p.groups * N * p.col_chunks;
   p.nh_box = (p.m_cta + 3 * p.Wp + 1 + p.Wp - 1) / p.Wp;
   if (p.nh_box > 256) return fail(PCRL_ERR_UNSUPPORTED, "conv3d_k3: W=%d too small for box", W);
   p.slab_bytes = ((p.nh_box * p.Wp * p.row_bytes + 1023) / 1024) * 1024;
@@ -595,7 +677,6 @@ int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long
   p.seg_len = 0; p.PL = 0; p.Wp = 1;
   p.tiles_per_group = (int)((rows + p.m_cta - 1) / p.m_cta);
   p.groups = 1; p.nsamples = 1; p.col_chunks = cols / p.nc;
-  p.total_tiles = (long long)p.tiles_per_group * p.col_chunks;
   p.out_mode = out_mode; p.out_fp32 = out_fp32; p.ldc = ldc;
   p.cout_total = (out_mode == OUT_CONVT) ? ct_cout : cols;
   p.ct_D = ct_D; p.ct_H = ct_H; p.ct_W = ct_W;

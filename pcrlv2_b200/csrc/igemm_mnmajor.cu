@@ -19,9 +19,9 @@
 
 namespace pcrl {
 
-__device__ __forceinline__ void umma_any(int tf32, uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc,
-                                         uint32_t acc) {
-  if (tf32) umma_tf32(d, ad, bd, idesc, acc);
+template <int TF32>
+__device__ __forceinline__ void umma_any(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  if (TF32) umma_tf32(d, ad, bd, idesc, acc);   // compile-time kind: see igemm_kmajor.cu
   else umma_bf16(d, ad, bd, idesc, acc);
 }
 
@@ -50,6 +50,7 @@ struct WgradParams {
   float* dw;
 };
 
+template <int TF32>
 __global__ void __launch_bounds__(128)
 igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb,
                      const WgradParams p) {
@@ -129,13 +130,13 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     }
   } else if (warp == 1) {
     int st = 0, ph = 0;
-    const uint32_t fmt = p.tf32 ? 2u : 1u;
+    const uint32_t fmt = TF32 ? 2u : 1u;
     const uint32_t idesc = make_idesc(fmt, (uint32_t)p.mc, (uint32_t)p.nc, 1, 1);
     // MN-major layouts: 16-bit operands use the 128B/64B swizzle (K atom = 8 rows); fp32 (tf32)
     // operands need the 32-byte-atom variant (K atom = 4 rows) -- profiles/r01_umma_probe.md
-    const uint32_t a_lay = p.tf32 ? LAYOUT_SW128_B32 : (p.a_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
-    const uint32_t b_lay = p.tf32 ? LAYOUT_SW128_B32 : (p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
-    const uint32_t a_sbo = p.tf32 ? 512u : 8u * p.a_row_bytes, b_sbo = p.tf32 ? 512u : 8u * p.b_row_bytes;
+    const uint32_t a_lay = TF32 ? LAYOUT_SW128_B32 : (p.a_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
+    const uint32_t b_lay = TF32 ? LAYOUT_SW128_B32 : (p.b_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
+    const uint32_t a_sbo = TF32 ? 512u : 8u * p.a_row_bytes, b_sbo = TF32 ? 512u : 8u * p.b_row_bytes;
     const uint64_t a_hi = make_smem_desc(0, p.a_chunk_bytes, a_sbo, a_lay);
     const uint64_t b_hi = make_smem_desc(0, p.b_chunk_bytes, b_sbo, b_lay);
     const uint32_t a_step = (uint32_t)(p.krows * p.a_row_bytes) >> 4, b_step = (uint32_t)(p.krows * p.b_row_bytes) >> 4;
@@ -154,11 +155,11 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
           // slab row, so a single MMA fills the three accumulators (N = 96 / 192 instead of 3 x 32 / 64)
           uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
           uint64_t bd = b_stack_hi | (uint64_t)(((b_base + (uint32_t)(p.Wp - 1) * p.b_row_bytes) >> 4) & 0x3FFF);
-          umma_any(p.tf32, tmem, ad, bd, idesc_stack, accumulate);
+          umma_any<TF32>(tmem, ad, bd, idesc_stack, accumulate);
           for (int ks = 1; ks < p.ksteps; ks++) {
             ad += a_step;
             bd += b_step;
-            umma_any(p.tf32, tmem, ad, bd, idesc_stack, 1u);
+            umma_any<TF32>(tmem, ad, bd, idesc_stack, 1u);
           }
         } else {
           for (int t = 0; t < p.ntaps; t++) {
@@ -166,11 +167,11 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
             uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
             uint64_t bd = b_hi | (uint64_t)(((b_base + (uint32_t)b_row0 * p.b_row_bytes) >> 4) & 0x3FFF);
             const uint32_t d = tmem + t * p.nc;
-            umma_any(p.tf32, d, ad, bd, idesc, accumulate);
+            umma_any<TF32>(d, ad, bd, idesc, accumulate);
             for (int ks = 1; ks < p.ksteps; ks++) {
               ad += a_step;
               bd += b_step;
-              umma_any(p.tf32, d, ad, bd, idesc, 1u);
+              umma_any<TF32>(d, ad, bd, idesc, 1u);
             }
           }
         }
@@ -228,11 +229,14 @@ static int launch_wgrad(WgradParams& p, const CUtensorMap& ta, const CUtensorMap
   const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
-    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel,
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  igemm_mnmajor_kernel<<<grid, 128, smem, stream>>>(ta, tb, p);
+  if (p.tf32) igemm_mnmajor_kernel<1><<<grid, 128, smem, stream>>>(ta, tb, p);
+  else igemm_mnmajor_kernel<0><<<grid, 128, smem, stream>>>(ta, tb, p);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
