@@ -252,11 +252,9 @@ def run_ours(args):
         d = per.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
         d["ms"] += a.elapsed_time(b)
         d["n"] += 1
-        if name == "pcrl_conv3d_k3_fprop":
-            _, _, n_, d_, h_, w_, ci, co = ints
-            d["flops"] += 2.0 * n_ * d_ * h_ * w_ * 27 * ci * co
-        elif name in ("pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_wgrad", "pcrl_conv3d_k3_dgrad_unshuffled"):
-            n_, d_, h_, w_, ci, co = ints
+        if name in ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_wgrad",
+                    "pcrl_conv3d_k3_dgrad_unshuffled"):
+            n_, d_, h_, w_, ci, co = ints[-7:-1]       # (..., N, D, H, W, Cin, Cout, dtype)
             d["flops"] += 2.0 * n_ * d_ * h_ * w_ * 27 * ci * co
     peaks, peak_src = measured_peaks()
     fam = ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_dgrad_unshuffled")

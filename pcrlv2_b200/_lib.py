@@ -12,7 +12,9 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcrl_b200.so")
+# PCRL_B200_LIB selects another build of the same library (e.g. the stall-accounting build of
+# tools/stall_report.py); it is still this CUDA library, never a fallback.
+LIB_PATH = os.environ.get("PCRL_B200_LIB") or os.path.join(_HERE, "libpcrl_b200.so")
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int

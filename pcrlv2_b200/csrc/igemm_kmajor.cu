@@ -64,6 +64,22 @@ __device__ __forceinline__ void umma_any(uint32_t d, uint64_t ad, uint64_t bd, u
   else umma_bf16(d, ad, bd, idesc, acc);
 }
 
+// Optional stall accounting (build with -DPCRL_TIMING; tools/bench_layers.py reads it back):
+// per CTA [0] MMA-warp loop cycles, waits on [1] a_full [2] b_full [3] acc_empty, [4] slab producer
+// on a_empty, [5] filter producer on b_empty, [6] epilogue warp 2 on acc_full, [7] its loop cycles.
+#ifdef PCRL_TIMING
+__device__ unsigned long long g_timing[1024][8];
+#define TWAIT(acc, bar, par) do { long long t0_ = clock64(); mbar_wait(bar, par); acc += clock64() - t0_; } while (0)
+#define TDECL(...) long long __VA_ARGS__
+#define TNOW() clock64()
+#define TSTORE(i, v) do { if (lane == 0) g_timing[blockIdx.x][i] = (unsigned long long)(v); } while (0)
+#else
+#define TWAIT(acc, bar, par) mbar_wait(bar, par)
+#define TDECL(...)
+#define TNOW() 0
+#define TSTORE(i, v)
+#endif
+
 __device__ __forceinline__ int floordiv(int a, int b) {
   int q = a / b;
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
@@ -143,6 +159,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     // =============================== TMA producer for the activation slabs (whole warp runs the
     // loop so that every operand stays warp-uniform; one elected lane issues)
     int sa = 0, pa = 0;
+    TDECL(tw = 0);
     const uint32_t a_tx = (p.mode == IG_CONV) ? (uint32_t)(p.nh_box * p.Wp * p.row_bytes)
                                               : (uint32_t)(p.mt * 128 * p.row_bytes);
     for (long long step = first_step; step < p.total_steps; step += step_stride) {
@@ -153,7 +170,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
       for (int kb = 0; kb < p.kblocks; kb++) {
         for (int s = 0; s < nslab; s++) {
           const int q = s - 1;
-          mbar_wait(&a_empty[sa], pa ^ 1);
+          TWAIT(tw, &a_empty[sa], pa ^ 1);
           uint8_t* dst = a_s + (size_t)sa * p.slab_bytes;
           if (elect_one()) {
             mbar_expect_tx(&a_full[sa], a_tx);
@@ -170,10 +187,12 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
         }
       }
     }
+    TSTORE(4, tw);
   } else if (warp == 6) {
     // =============================== TMA producer for the filter tiles: its own warp, so weight
     // prefetch runs sb tiles ahead of the MMAs independently of the slab ring
     int sb = 0, pb = 0;
+    TDECL(tw = 0);
     for (long long step = first_step; step < p.total_steps; step += step_stride) {
       const TileCoord tc = tile_coord(p, step, rank);   // col0 is common to the whole cluster
       for (int kb = 0; kb < p.kblocks; kb++) {
@@ -188,7 +207,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
           const CUtensorMap* tb = cnt == 1 ? &tb1 : (cnt == 2 ? &tb2 : &tb3);
           const uint32_t b_tx = (uint32_t)(cnt * p.nc * p.row_bytes);
           for (int j = 0; j < p.tpg; j++) {
-            mbar_wait(&b_empty[sb], pb ^ 1);   // cs > 1: every CTA of the cluster released this slot
+            TWAIT(tw, &b_empty[sb], pb ^ 1);   // cs > 1: every CTA of the cluster released this slot
             if (elect_one()) {
               mbar_expect_tx(&b_full[sb], b_tx);
               if (p.cs == 1) {
@@ -208,15 +227,27 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
         }
       }
     }
+    TSTORE(5, tw);
   } else if (warp == 1) {
-    // =============================== MMA issuer (whole warp loops, one elected lane issues)
+    // =============================== MMA issuer (whole warp loops, one elected lane issues).
+    // The issue thread is the critical resource: a tcgen05.mma of N <= 128 retires in 48..69 clk
+    // (tools/umma_probe lean), so everything between two MMAs has to be a handful of uniform-
+    // register adds.  Descriptors are advanced incrementally (tap -> +1 row / +Wp-2 rows), the
+    // k-step loop is straight-line code, and the rare first-touch split lives in a slow path.
     int sa = 0, pa = 0, sb = 0, pb = 0;
     const uint32_t layout = (p.row_bytes == 128) ? LAYOUT_SW128 : LAYOUT_SW64;
     const uint64_t desc_hi = make_smem_desc(0, 16, 8 * p.row_bytes, layout);
-    const int ksteps = p.row_bytes / 32;
+    const bool ks4 = p.row_bytes == 128;                  // 4 (128 B rows) or 2 (64 B rows) k-steps of 32 B
     const uint32_t fmt = TF32 ? 2u : 1u;
     const uint32_t idesc_nc = make_idesc(fmt, 128, (uint32_t)p.nc, 0, 0);
+    const uint32_t rb16 = (uint32_t)p.row_bytes >> 4;     // descriptor address units per operand row
+    const uint32_t mt16 = 128u * rb16, slab16 = (uint32_t)p.slab_bytes >> 4, bst16 = (uint32_t)p.b_bytes >> 4;
+    const uint64_t a_desc0 = desc_hi | (uint64_t)((smem_u32(a_s) >> 4) & 0x3FFF);
+    const uint64_t b_desc0 = desc_hi | (uint64_t)((smem_u32(b_s) >> 4) & 0x3FFF);
+    const uint32_t d_mt = (uint32_t)(p.P * p.nc);
+    const bool conv = p.mode == IG_CONV;
     int it = 0;
+    TDECL(twa = 0, twb = 0, twc = 0, tstart = TNOW());
     for (long long step = first_step; step < p.total_steps; step += step_stride) {
       const TileCoord tc = tile_coord(p, step, rank);
       if (!tc.live) {
@@ -232,54 +263,67 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
       const int buf = (p.nbuf == 2) ? (it & 1) : 0;
       const int use = (p.nbuf == 2) ? (it >> 1) : it;      // how often this buffer was used before
       it++;
-      mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+      TWAIT(twc, &acc_empty[buf], (use & 1) ^ 1);
       tc_fence_after();
       const uint32_t acc = tmem + buf * acc_cols;
-      int a_row_base = 0;
-      if (p.mode == IG_CONV) a_row_base = tc.f0 - floordiv(tc.f0 - p.Wp - 1, p.Wp) * p.Wp;
+      // first tap (dy,dx) = (-1,-1): rows before the tile's first row inside the slab
+      int tap0_rows = 0;
+      if (conv) tap0_rows = tc.f0 - floordiv(tc.f0 - p.Wp - 1, p.Wp) * p.Wp - p.Wp - 1;
       for (int kb = 0; kb < p.kblocks; kb++) {
         for (int s = 0; s < nslab; s++) {
           const int q = s - 1;
           int p_lo = 0, cnt = 1;
-          if (p.mode == IG_CONV) {
+          if (conv) {
             p_lo = max(0, q - 1);
             cnt = min(p.P - 1, q + 1) - p_lo + 1;
           }
           // the block of output plane q+1 is touched for the first time by this slab
-          const bool has_new = (kb == 0) && (p.mode != IG_CONV || q + 1 <= p.P - 1);
+          const bool has_new = (kb == 0) && (!conv || q + 1 <= p.P - 1);
           const uint32_t idesc_all = make_idesc(fmt, 128, (uint32_t)(cnt * p.nc), 0, 0);
-          const uint32_t idesc_old = make_idesc(fmt, 128, (uint32_t)((cnt > 1 ? cnt - 1 : 1) * p.nc), 0, 0);
-          mbar_wait(&a_full[sa], pa);
-          const uint32_t a_base = smem_u32(a_s + (size_t)sa * p.slab_bytes);
+          const uint32_t d0 = acc + (uint32_t)(p_lo * p.nc);
+          TWAIT(twa, &a_full[sa], pa);
+          uint64_t ad_tap = a_desc0 + (uint32_t)sa * slab16 + (uint32_t)tap0_rows * rb16;
+          int c3 = 0;
           for (int j = 0; j < p.tpg; j++) {
-            int row_off = 0;
-            if (p.mode == IG_CONV) row_off = a_row_base + (j / 3 - 1) * p.Wp + (j % 3 - 1);
-            mbar_wait(&b_full[sb], pb);
+            TWAIT(twb, &b_full[sb], pb);
             tc_fence_after();
-            const uint32_t b_base = smem_u32(b_s + (size_t)sb * p.b_bytes);
-            const uint64_t bd0 = desc_hi | (uint64_t)((b_base >> 4) & 0x3FFF);
-            const bool first = has_new && j == 0;
+            const uint64_t bd = b_desc0 + (uint32_t)sb * bst16;
             if (elect_one()) {
-              for (int mt = 0; mt < p.mt; mt++) {
-                const uint32_t a_addr = a_base + (uint32_t)(row_off + mt * 128) * p.row_bytes;
-                const uint64_t ad0 = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
-                const uint32_t d_addr = acc + (uint32_t)((mt * p.P + p_lo) * p.nc);
-                int ks = 0;
-                if (first) {
-                  // split: old blocks accumulate, the new block (last of the range) is overwritten
-                  if (cnt > 1) umma_any<TF32>(d_addr, ad0, bd0, idesc_old, 1u);
-                  const uint32_t boff = (uint32_t)((cnt - 1) * p.nc) * p.row_bytes;
-                  umma_any<TF32>(d_addr + (uint32_t)((cnt - 1) * p.nc), ad0, bd0 + (boff >> 4), idesc_nc, 0u);
-                  ks = 1;
+              if (has_new && j == 0) {
+                // slow path, once per (tile, slab): old blocks accumulate, the new block (last of
+                // the range) is overwritten by its first MMA
+                const uint32_t idesc_old = make_idesc(fmt, 128, (uint32_t)((cnt > 1 ? cnt - 1 : 1) * p.nc), 0, 0);
+                const uint32_t boff16 = (uint32_t)((cnt - 1) * p.nc) * rb16;
+                const int ksteps = ks4 ? 4 : 2;
+                for (int mt = 0; mt < p.mt; mt++) {
+                  const uint64_t ad = ad_tap + (uint32_t)mt * mt16;
+                  const uint32_t d = d0 + (uint32_t)mt * d_mt;
+                  if (cnt > 1) umma_any<TF32>(d, ad, bd, idesc_old, 1u);
+                  umma_any<TF32>(d + (uint32_t)((cnt - 1) * p.nc), ad, bd + boff16, idesc_nc, 0u);
+                  for (int ks = 1; ks < ksteps; ks++) umma_any<TF32>(d, ad + 2 * ks, bd + 2 * ks, idesc_all, 1u);
                 }
-                for (; ks < ksteps; ks++)
-                  umma_any<TF32>(d_addr, ad0 + 2 * ks, bd0 + 2 * ks, idesc_all, 1u);
+              } else {
+                uint64_t ad = ad_tap;
+                uint32_t d = d0;
+                for (int mt = 0; mt < p.mt; mt++) {
+                  umma_any<TF32>(d, ad, bd, idesc_all, 1u);
+                  umma_any<TF32>(d, ad + 2, bd + 2, idesc_all, 1u);
+                  if (ks4) {
+                    umma_any<TF32>(d, ad + 4, bd + 4, idesc_all, 1u);
+                    umma_any<TF32>(d, ad + 6, bd + 6, idesc_all, 1u);
+                  }
+                  ad += mt16;
+                  d += d_mt;
+                }
               }
               if (p.cs > 1) umma_commit_mc(&b_empty[sb], cmask);
               else umma_commit(&b_empty[sb]);
             }
             __syncwarp();
             if (++sb == p.sb) { sb = 0; pb ^= 1; }
+            // next tap: dx+1, or wrap to (dy+1, dx=-1)
+            if (++c3 == 3) { c3 = 0; ad_tap += (uint32_t)(p.Wp - 2) * rb16; }
+            else ad_tap += rb16;
           }
           if (elect_one()) umma_commit(&a_empty[sa]);
           __syncwarp();
@@ -289,12 +333,14 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
+    TSTORE(0, TNOW() - tstart); TSTORE(1, twa); TSTORE(2, twb); TSTORE(3, twc);
   } else if (warp >= 2 && warp <= 5) {
     // =============================== epilogue warps (warp w owns TMEM lanes 32*(w%4) .. +31)
     const int quad = warp & 3;
     int it = 0;
     int cur_col0 = -1, cur_n = -1;
     const int et = threadIdx.x - 64;  // 0..127
+    TDECL(twf = 0, tstart = TNOW());
     for (long long step = first_step; step < p.total_steps; step += step_stride) {
       const TileCoord tc = tile_coord(p, step, rank);
       if (!tc.live) continue;
@@ -317,7 +363,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
         cur_col0 = tc.col0;
         cur_n = tc.n;
       }
-      mbar_wait(&acc_full[buf], use & 1);
+      TWAIT(twf, &acc_full[buf], use & 1);
       tc_fence_after();
       const uint32_t acc = tmem + buf * acc_cols;
       const int t_idx = (p.out_mode == OUT_CONVT) ? tc.col0 / p.cout_total : 0;
@@ -451,6 +497,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
         }
       }
     }
+    if (warp == 2) { TSTORE(6, twf); TSTORE(7, TNOW() - tstart); }
   }
   tc_fence_before();
   __syncthreads();
@@ -692,3 +739,9 @@ int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long
 }
 
 }  // namespace pcrl
+
+#ifdef PCRL_TIMING
+extern "C" int pcrl_debug_timing(unsigned long long* host, int nblocks) {
+  return (int)cudaMemcpyFromSymbol(host, pcrl::g_timing, (size_t)nblocks * 8 * sizeof(unsigned long long));
+}
+#endif

@@ -426,7 +426,8 @@ def test_convT_fp32(shape):
     # (the intermediate gradient is not TF32-representable: one TF32 rounding of an operand)
     assert rel(K.unpad_ndhwc(dxc), x.grad) < 2e-3
     assert rel(K.unpack_convT_wgrad(dwt, cin, cout), wt.grad) < 2e-3
-    assert rel(colsum[:, 0], b.grad) < 1e-4
+    # column sums are taken over the stored (tf32-rounded) gradient: ~2^-12 / sqrt(terms) of its rms
+    assert rel(colsum[:, 0], b.grad) < 6e-4
 
 
 @pytest.mark.parametrize("mode", ["full", "pool", "avg"])
@@ -451,7 +452,8 @@ def test_norm_act_fp32(mode):
     loss = (out_ref * g1).sum()
     gavg = None
     if mode == "avg":
-        assert rel(avg / (d * h * w), a_ref.mean(dim=(2, 3, 4))) < 1e-5
+        # the pooled sum is over the stored (tf32-rounded) activations
+        assert rel(avg / (d * h * w), a_ref.mean(dim=(2, 3, 4))) < 2e-4
         gavg = torch.randn(n, c, device=DEV)
         loss = loss + (a_ref.mean(dim=(2, 3, 4)) * gavg).sum()
     loss.backward()

@@ -471,6 +471,212 @@ static int run_perf(PerfParams p) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Mixed probe: the MMA loop of perf_mma (N columns, mtiles x taps x 4 MMAs per round, `iters`
+// rounds) running concurrently with a bulk-copy ingest stream (`nloads` chunks of `chunk` bytes
+// per CTA through a `stages`-deep ring, read from a `gbytes`-sized global buffer).  Either side
+// can be switched off (iters = 0 / nloads = 0) to get the two isolated rates.
+struct MixParams { int n, mtiles, taps, iters, nloads, chunk, stages; long long gbytes; int same;
+                   int commit_every, tap_rows, pollers, fence_every; };
+__global__ void __launch_bounds__(192) mix_kernel(MixParams p, const uint8_t* g, float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_mma, full[16], empty[16], dummy[4], never;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  const int a_rows = 128 * p.mtiles + p.taps * p.tap_rows + 8;
+  const uint32_t op_bytes = ((a_rows * 128 + 1023) / 1024) * 1024 + p.n * 128;
+  uint8_t* ring = smem + ((op_bytes + 1023) / 1024) * 1024;
+  for (int i = threadIdx.x; i < (int)op_bytes / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_mma, 1);
+    for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 4; i++) mbar_init(&dummy[i], 1);
+    mbar_init(&never, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) {
+    if (threadIdx.x == 0) {
+      const uint32_t idesc = make_idesc(1, 128, p.n, 0, 0);
+      const uint32_t a0 = smem_u32(smem), b0 = a0 + ((a_rows * 128 + 1023) / 1024) * 1024;
+      int cnt = 0, dm = 0;
+      for (int it = 0; it < p.iters; it++)
+        for (int t = 0; t < p.taps; t++) {
+          if (p.fence_every) tc_fence_after();
+          for (int mt = 0; mt < p.mtiles; mt++) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              uint64_t ad = make_smem_desc(a0 + (mt * 128 + t * p.tap_rows) * 128 + ks * 32, 16, 1024, LAYOUT_SW128);
+              uint64_t bd = make_smem_desc(b0 + ks * 32, 16, 1024, LAYOUT_SW128);
+              umma_bf16(tmem + mt * p.n, ad, bd, idesc, 1);
+            }
+            if (p.commit_every && ++cnt == p.commit_every) { cnt = 0; umma_commit(&dummy[dm]); dm = (dm + 1) & 3; }
+          }
+        }
+      umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    if (threadIdx.x == 0) mbar_arrive(&never);
+  } else if (warp >= 1 && warp <= 3 && warp <= p.pollers) {
+    // pollers: whole warps spinning on a barrier that flips only when the MMAs are done
+    mbar_wait(&never, 0);
+  } else if (warp == 4) {
+    // loader
+    if ((threadIdx.x & 31) == 0) {
+      int s = 0, ph = 0;
+      const long long nch = p.gbytes / p.chunk;
+      long long c = p.same ? 0 : ((long long)blockIdx.x * 7919) % nch;
+      for (int i = 0; i < p.nloads; i++) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], (uint32_t)p.chunk);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(ring + (size_t)s * p.chunk)),
+            "l"(g + c * p.chunk), "r"((uint32_t)p.chunk), "r"(smem_u32(&full[s]))
+            : "memory");
+        if (++c == nch) c = 0;
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    // drain: release each stage as soon as it has landed
+    if ((threadIdx.x & 31) == 0) {
+      int s = 0, ph = 0;
+      for (int i = 0; i < p.nloads; i++) {
+        mbar_wait(&full[s], ph);
+        mbar_arrive(&empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v[32];
+    tmem_ld32(tmem, v);
+    tmem_ld_wait();
+    if (v[0] == 0x12345678u) sink[0] = 1.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static int run_mix(MixParams p) {
+  float* sink; CK(cudaMalloc(&sink, 4));
+  uint8_t* g; CK(cudaMalloc(&g, p.gbytes)); CK(cudaMemset(g, 0, p.gbytes));
+  int a_rows = 128 * p.mtiles + p.taps * p.tap_rows + 8;
+  size_t smem = ((a_rows * 128 + 1023) / 1024) * 1024 + p.n * 128 + 2048 + (size_t)p.stages * p.chunk + 1024;
+  CK(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  int khz = 0; CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    mix_kernel<<<sms, 192, smem>>>(p, g, sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    double flops = 2.0 * 128 * p.n * 16 * 4.0 * p.mtiles * p.taps * (double)p.iters * sms;
+    double bytes = (double)p.nloads * p.chunk * sms;
+    if (rep == 2)
+      printf("RESULT mix n=%d mt=%d iters=%d nloads=%d chunk=%d stages=%d gMB=%.1f same=%d ce=%d tr=%d poll=%d fence=%d : %.3f ms  %.1f TFLOP/s  %.2f TB/s  %.1f B/clk/SM@%dMHz\n",
+             p.n, p.mtiles, p.iters, p.nloads, p.chunk, p.stages, p.gbytes / 1048576.0, p.same, p.commit_every, p.tap_rows, p.pollers, p.fence_every, ms, flops / ms * 1e-9,
+             bytes / ms * 1e-9, bytes / sms / (ms * 1e-3 * khz * 1e3), khz / 1000);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Lean issue probe: descriptors precomputed, inner loops fully unrolled -- measures the floor
+// of clk per tcgen05.mma for a given N when the issuing thread does nothing else.
+template <int MT>
+__global__ void __launch_bounds__(128) lean_kernel(int n, int iters, int whole_warp, float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  const int a_rows = 128 * MT + 8;
+  for (int i = threadIdx.x; i < (a_rows + n) * 128 / 4 + 256; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(1, 128, n, 0, 0);
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + ((a_rows * 128 + 1023) / 1024) * 1024;
+    const uint64_t ad = make_smem_desc(a0, 16, 1024, LAYOUT_SW128);
+    const uint64_t bd = make_smem_desc(b0, 16, 1024, LAYOUT_SW128);
+    if (whole_warp) {
+      for (int it = 0; it < iters; it++) {
+        if (elect_one()) {
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++)
+              umma_bf16(tmem + mt * n, ad + mt * 1024 + 2 * ks, bd + 2 * ks, idesc, 1);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bar_mma);
+    } else if (threadIdx.x == 0) {
+      for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            umma_bf16(tmem + mt * n, ad + mt * 1024 + 2 * ks, bd + 2 * ks, idesc, 1);
+      }
+      umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld32(tmem, v);
+    tmem_ld_wait();
+    if (v[0] == 0x12345678u) sink[0] = 1.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static int run_lean(int n, int mt, int iters, int whole_warp) {
+  float* sink; CK(cudaMalloc(&sink, 4));
+  size_t smem = (size_t)(128 * mt + 8 + n) * 128 + 4096;
+  auto k = mt == 1 ? lean_kernel<1> : (mt == 2 ? lean_kernel<2> : lean_kernel<4>);
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  int khz = 0; CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    k<<<sms, 128, smem>>>(n, iters, whole_warp, sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    double nmma = 4.0 * mt * iters;
+    double flops = 2.0 * 128 * n * 16 * nmma * sms;
+    if (rep == 2)
+      printf("RESULT lean n=%d mt=%d iters=%d warp=%d : %.3f ms  %.1f TFLOP/s  %.1f clk/MMA@%dMHz\n", n, mt, iters,
+             whole_warp, ms, flops / ms * 1e-9, ms * 1e-3 * khz * 1e3 / nmma, khz / 1000);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage\n"); return 2; }
   std::string t = argv[1];
@@ -486,6 +692,15 @@ int main(int argc, char** argv) {
     return run_mnmajor(p);
   } else if (t == "halo") {
     return run_halo();
+  } else if (t == "lean") {
+    return run_lean(I(2, 128), I(3, 2), I(4, 4000), I(5, 0));
+  } else if (t == "mix") {
+    // mix n mtiles taps iters nloads chunk stages gMB same
+    MixParams p; p.n = I(2, 128); p.mtiles = I(3, 2); p.taps = I(4, 9); p.iters = I(5, 100); p.nloads = I(6, 1000);
+    p.chunk = I(7, 16384); p.stages = I(8, 8); p.gbytes = (long long)I(9, 64) * 1048576 / (I(9, 64) < 0 ? 1 : 1); p.same = I(10, 0);
+    if (I(9, 64) == 0) p.gbytes = 524288;
+    p.commit_every = I(11, 0); p.tap_rows = I(12, 0); p.pollers = I(13, 0); p.fence_every = I(14, 0);
+    return run_mix(p);
   } else if (t == "perf") {
     PerfParams p; p.n = I(2, 64); p.mtiles = I(3, 1); p.taps = I(4, 9); p.tap_rows = I(5, 0); p.iters = I(6, 200); p.layout = I(7, 2);
     return run_perf(p);
