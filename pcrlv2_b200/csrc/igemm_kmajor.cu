@@ -19,8 +19,13 @@
 // layers, where a single N=64 MMA only reaches ~46 % of the tensor-pipe rate.
 // Weights stream through a second TMA ring ([cnt*nc x kc] per tap).
 //
-// Warp roles (224 threads): warp 0 = slab TMA producer, warp 6 = filter TMA producer, warp 1 = MMA
-// issuer, warps 2..5 = epilogue.
+// Warp roles (256 threads): warp 0 = slab TMA producer, warp 6 = filter TMA producer, warps 1 and 7 =
+// MMA issuers, warps 2..5 = epilogue.  TWO issuers because the issuing thread is the critical
+// resource: a tcgen05.mma of N <= 128 occupies the pipe for only 51..69 clk and the pipe takes the
+// next one only from a thread that is ready to issue, so every barrier wait / commit / branch of a
+// single issuer is dead tensor time (measured: tools/umma_probe "lean" and "dual",
+// profiles/r01_issue_probe.md).  Issuer w owns the 128-row blocks mt = w, w+2, .. of the tile (its
+// own accumulator columns); while one issuer is in its per-tap bookkeeping the other one's MMAs run.
 // Accumulators live in TMEM, double-buffered when 2*mt*P*nc <= 512 columns so that the epilogue
 // of tile i (tcgen05.ld -> bias -> bf16/fp32 store, per-channel sum / sum-of-squares for the
 // following BatchNorm / InstanceNorm) overlaps the MMAs of tile i+1.
@@ -44,8 +49,8 @@ struct IgemmParams {
   int tf32;                   // operands are fp32 in memory, MMA kind::tf32 (K = 8 per instruction)
   int tiles_per_group, groups, col_chunks, nsamples;
   long long total_tiles;
-  int cs;                     // CTAs per cluster sharing (multicasting) the filter tiles
-  long long tiles_per_chunk, steps_per_chunk, total_steps;
+  int ni;                     // MMA issuer warps in use (1 or 2)
+  long long tiles_per_chunk, total_steps;
   int seg_len;                // rows of one segment that belong to this tile family
   long long rows_total;       // PLAIN: number of A rows
   // epilogue
@@ -87,16 +92,12 @@ __device__ __forceinline__ int floordiv(int a, int b) {
 
 struct TileCoord {
   int col0, n, f0, t_local;   // first output column, sample, first flat row, first row inside the segment
-  bool live;                  // false: padding step of a cluster (no tile for this CTA)
 };
-// step -> tile of this CTA.  The cs CTAs of a cluster walk the same steps; within a step they own cs
-// consecutive tiles of ONE column chunk, so they consume identical filter tiles.
-__device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, long long step, int rank) {
+// step -> tile: column chunks outermost so that CTAs running concurrently share filter tiles in L2
+__device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, long long step) {
   TileCoord c;
-  const long long chunk = step / p.steps_per_chunk;
-  const long long lt = (step % p.steps_per_chunk) * p.cs + rank;
-  c.live = lt < p.tiles_per_chunk;
-  const long long tile = c.live ? lt : 0;
+  const long long chunk = step / p.tiles_per_chunk;
+  const long long tile = step % p.tiles_per_chunk;
   const int t = (int)(tile % p.tiles_per_group);
   long long r = tile / p.tiles_per_group;
   const int g = (int)(r % p.groups);
@@ -109,10 +110,10 @@ __device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, long long 
 }
 
 template <int TF32>
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__(256, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb1,
                     const __grid_constant__ CUtensorMap tb2, const __grid_constant__ CUtensorMap tb3,
-                    const __grid_constant__ CUtensorMap tbs, const IgemmParams p) {
+                    const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_s = smem;
@@ -130,9 +131,9 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.sa; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.sb; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], (uint32_t)p.cs); }
-    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < p.sa; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], (uint32_t)p.ni); }
+    for (int i = 0; i < p.sb; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], (uint32_t)p.ni); }
+    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], (uint32_t)p.ni); mbar_init(&acc_empty[i], 128); }
     fence_barrier_init();
     tma_prefetch_desc(&ta);
     tma_prefetch_desc(&tb1);
@@ -146,11 +147,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const int rank = (p.cs > 1) ? (int)cluster_ctarank() : 0;
-  const long long first_step = (p.cs > 1) ? (long long)(blockIdx.x / p.cs) : (long long)blockIdx.x;
-  const long long step_stride = (p.cs > 1) ? (long long)(gridDim.x / p.cs) : (long long)gridDim.x;
-  const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
-  if (p.cs > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive
+  const long long first_step = (long long)blockIdx.x, step_stride = (long long)gridDim.x;
   const uint32_t tmem = *tmem_slot;
   const int acc_cols = p.mt * p.P * p.nc;
   const int nslab = (p.mode == IG_CONV) ? p.P + 2 : 1;
@@ -163,8 +160,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     const uint32_t a_tx = (p.mode == IG_CONV) ? (uint32_t)(p.nh_box * p.Wp * p.row_bytes)
                                               : (uint32_t)(p.mt * 128 * p.row_bytes);
     for (long long step = first_step; step < p.total_steps; step += step_stride) {
-      const TileCoord tc = tile_coord(p, step, rank);
-      if (!tc.live) continue;
+      const TileCoord tc = tile_coord(p, step);
       int mr_first = 0;
       if (p.mode == IG_CONV) mr_first = floordiv(tc.f0 - p.Wp - 1, p.Wp);
       for (int kb = 0; kb < p.kblocks; kb++) {
@@ -194,7 +190,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     int sb = 0, pb = 0;
     TDECL(tw = 0);
     for (long long step = first_step; step < p.total_steps; step += step_stride) {
-      const TileCoord tc = tile_coord(p, step, rank);   // col0 is common to the whole cluster
+      const TileCoord tc = tile_coord(p, step);
       for (int kb = 0; kb < p.kblocks; kb++) {
         for (int s = 0; s < nslab; s++) {
           const int q = s - 1;
@@ -207,19 +203,10 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
           const CUtensorMap* tb = cnt == 1 ? &tb1 : (cnt == 2 ? &tb2 : &tb3);
           const uint32_t b_tx = (uint32_t)(cnt * p.nc * p.row_bytes);
           for (int j = 0; j < p.tpg; j++) {
-            TWAIT(tw, &b_empty[sb], pb ^ 1);   // cs > 1: every CTA of the cluster released this slot
+            TWAIT(tw, &b_empty[sb], pb ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&b_full[sb], b_tx);
-              if (p.cs == 1) {
-                tma_load_3d(b_s + (size_t)sb * p.b_bytes, tb, &b_full[sb], kb * p.kc, tc.col0,
-                            j * 3 + dzr_lo);
-              } else {
-                // this CTA fetches 1/cs of the rows of every dz block and multicasts them
-                const int share = p.nc / p.cs;
-                for (int z = 0; z < cnt; z++)
-                  tma_load_3d_mc(b_s + (size_t)sb * p.b_bytes + (size_t)(z * p.nc + rank * share) * p.row_bytes,
-                                 &tbs, &b_full[sb], kb * p.kc, tc.col0 + rank * share, j * 3 + dzr_lo + z, cmask);
-              }
+              tma_load_3d(b_s + (size_t)sb * p.b_bytes, tb, &b_full[sb], kb * p.kc, tc.col0, j * 3 + dzr_lo);
             }
             __syncwarp();
             if (++sb == p.sb) { sb = 0; pb ^= 1; }
@@ -228,12 +215,13 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
       }
     }
     TSTORE(5, tw);
-  } else if (warp == 1) {
-    // =============================== MMA issuer (whole warp loops, one elected lane issues).
+  } else if (warp == 1 || warp == 7) {
+    // =============================== MMA issuers (whole warp loops, one elected lane issues).
     // The issue thread is the critical resource: a tcgen05.mma of N <= 128 retires in 48..69 clk
     // (tools/umma_probe lean), so everything between two MMAs has to be a handful of uniform-
     // register adds.  Descriptors are advanced incrementally (tap -> +1 row / +Wp-2 rows), the
     // k-step loop is straight-line code, and the rare first-touch split lives in a slow path.
+    const int iw = (warp == 1) ? 0 : 1;                   // this issuer owns blocks mt = iw, iw + ni, ..
     int sa = 0, pa = 0, sb = 0, pb = 0;
     const uint32_t layout = (p.row_bytes == 128) ? LAYOUT_SW128 : LAYOUT_SW64;
     const uint64_t desc_hi = make_smem_desc(0, 16, 8 * p.row_bytes, layout);
@@ -248,18 +236,8 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     const bool conv = p.mode == IG_CONV;
     int it = 0;
     TDECL(twa = 0, twb = 0, twc = 0, tstart = TNOW());
-    for (long long step = first_step; step < p.total_steps; step += step_stride) {
-      const TileCoord tc = tile_coord(p, step, rank);
-      if (!tc.live) {
-        // padding step: keep the cluster's filter ring moving (consume and release every stage)
-        for (int i = 0; i < p.kblocks * nslab * p.tpg; i++) {
-          mbar_wait(&b_full[sb], pb);
-          if (elect_one()) umma_commit_mc(&b_empty[sb], cmask);
-          __syncwarp();
-          if (++sb == p.sb) { sb = 0; pb ^= 1; }
-        }
-        continue;
-      }
+    for (long long step = first_step; step < p.total_steps && iw < p.ni; step += step_stride) {
+      const TileCoord tc = tile_coord(p, step);
       const int buf = (p.nbuf == 2) ? (it & 1) : 0;
       const int use = (p.nbuf == 2) ? (it >> 1) : it;      // how often this buffer was used before
       it++;
@@ -280,9 +258,9 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
           // the block of output plane q+1 is touched for the first time by this slab
           const bool has_new = (kb == 0) && (!conv || q + 1 <= p.P - 1);
           const uint32_t idesc_all = make_idesc(fmt, 128, (uint32_t)(cnt * p.nc), 0, 0);
-          const uint32_t d0 = acc + (uint32_t)(p_lo * p.nc);
+          const uint32_t d0 = acc + (uint32_t)(p_lo * p.nc) + (uint32_t)iw * d_mt;
           TWAIT(twa, &a_full[sa], pa);
-          uint64_t ad_tap = a_desc0 + (uint32_t)sa * slab16 + (uint32_t)tap0_rows * rb16;
+          uint64_t ad_tap = a_desc0 + (uint32_t)sa * slab16 + (uint32_t)tap0_rows * rb16 + (uint32_t)iw * mt16;
           int c3 = 0;
           for (int j = 0; j < p.tpg; j++) {
             TWAIT(twb, &b_full[sb], pb);
@@ -295,9 +273,9 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
                 const uint32_t idesc_old = make_idesc(fmt, 128, (uint32_t)((cnt > 1 ? cnt - 1 : 1) * p.nc), 0, 0);
                 const uint32_t boff16 = (uint32_t)((cnt - 1) * p.nc) * rb16;
                 const int ksteps = ks4 ? 4 : 2;
-                for (int mt = 0; mt < p.mt; mt++) {
-                  const uint64_t ad = ad_tap + (uint32_t)mt * mt16;
-                  const uint32_t d = d0 + (uint32_t)mt * d_mt;
+                for (int mt = iw; mt < p.mt; mt += p.ni) {
+                  const uint64_t ad = ad_tap + (uint32_t)(mt - iw) * mt16;
+                  const uint32_t d = d0 + (uint32_t)(mt - iw) * d_mt;
                   if (cnt > 1) umma_any<TF32>(d, ad, bd, idesc_old, 1u);
                   umma_any<TF32>(d + (uint32_t)((cnt - 1) * p.nc), ad, bd + boff16, idesc_nc, 0u);
                   for (int ks = 1; ks < ksteps; ks++) umma_any<TF32>(d, ad + 2 * ks, bd + 2 * ks, idesc_all, 1u);
@@ -305,19 +283,18 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
               } else {
                 uint64_t ad = ad_tap;
                 uint32_t d = d0;
-                for (int mt = 0; mt < p.mt; mt++) {
+                for (int mt = iw; mt < p.mt; mt += p.ni) {
                   umma_any<TF32>(d, ad, bd, idesc_all, 1u);
                   umma_any<TF32>(d, ad + 2, bd + 2, idesc_all, 1u);
                   if (ks4) {
                     umma_any<TF32>(d, ad + 4, bd + 4, idesc_all, 1u);
                     umma_any<TF32>(d, ad + 6, bd + 6, idesc_all, 1u);
                   }
-                  ad += mt16;
-                  d += d_mt;
+                  ad += (uint32_t)p.ni * mt16;
+                  d += (uint32_t)p.ni * d_mt;
                 }
               }
-              if (p.cs > 1) umma_commit_mc(&b_empty[sb], cmask);
-              else umma_commit(&b_empty[sb]);
+              umma_commit(&b_empty[sb]);
             }
             __syncwarp();
             if (++sb == p.sb) { sb = 0; pb ^= 1; }
@@ -333,7 +310,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
-    TSTORE(0, TNOW() - tstart); TSTORE(1, twa); TSTORE(2, twb); TSTORE(3, twc);
+    if (iw == 0) { TSTORE(0, TNOW() - tstart); TSTORE(1, twa); TSTORE(2, twb); TSTORE(3, twc); }
   } else if (warp >= 2 && warp <= 5) {
     // =============================== epilogue warps (warp w owns TMEM lanes 32*(w%4) .. +31)
     const int quad = warp & 3;
@@ -342,8 +319,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
     const int et = threadIdx.x - 64;  // 0..127
     TDECL(twf = 0, tstart = TNOW());
     for (long long step = first_step; step < p.total_steps; step += step_stride) {
-      const TileCoord tc = tile_coord(p, step, rank);
-      if (!tc.live) continue;
+      const TileCoord tc = tile_coord(p, step);
       const int buf = (p.nbuf == 2) ? (it & 1) : 0;
       const int use = (p.nbuf == 2) ? (it >> 1) : it;
       it++;
@@ -501,7 +477,6 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cs > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into its smem
   if (warp == 1) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
@@ -521,8 +496,7 @@ static inline CUtensorMapSwizzle tma_swizzle(int row_bytes) {
 
 struct IgemmLaunch {
   IgemmParams p;
-  CUtensorMap ta, tb[3], tbs;
-  const void* w_ptr; int w_K, w_cols, w_taps;
+  CUtensorMap ta, tb[3];
 };
 
 static int finish_and_launch(IgemmLaunch& L, cudaStream_t stream) {
@@ -558,54 +532,22 @@ static int finish_and_launch(IgemmLaunch& L, cudaStream_t stream) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  // cluster of cs CTAs that walk the same steps and multicast the filter tiles to each other
-  // (cuts the dominant L2 -> shared-memory traffic of the kernel by cs)
-  p.cs = 1;
-  if (p.mode == IG_CONV) {
-    p.cs = 1;   // multicast halves L2 reads but not the bytes each SM ingests, which is the limit
-    const char* e = getenv("PCRL_IGEMM_CS");
-    if (e && atoi(e) >= 1) p.cs = atoi(e);
-    while (p.cs > 1 && ((p.nc / p.cs) % 8 != 0 || p.nc % p.cs != 0)) p.cs >>= 1;
-  }
+  p.ni = p.mt >= 2 ? 2 : 1;
   p.tiles_per_chunk = (long long)p.tiles_per_group * p.groups * p.nsamples;
-  p.steps_per_chunk = (p.tiles_per_chunk + p.cs - 1) / p.cs;
-  p.total_steps = p.steps_per_chunk * p.col_chunks;
-  if (p.cs > 1) {
-    const uint64_t elt = p.tf32 ? 4 : 2;
-    uint64_t dims[3] = {(uint64_t)L.w_K, (uint64_t)L.w_cols, (uint64_t)L.w_taps};
-    uint64_t str[2] = {(uint64_t)L.w_K * elt, (uint64_t)L.w_K * L.w_cols * elt};
-    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)(p.nc / p.cs), 1};
-    int rc = encode_map(&L.tbs, tma_dtype(p.tf32), 3, L.w_ptr, dims, str, box, tma_swizzle(p.row_bytes));
-    if (rc) return rc;
-  } else {
-    L.tbs = L.tb[0];
-  }
-  long long clusters = num_sms() / p.cs;
-  if (p.total_steps < clusters) clusters = p.total_steps;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(clusters * p.cs));
-  cfg.blockDim = dim3(224);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)p.cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  p.total_steps = p.tiles_per_chunk * p.col_chunks;
+  long long grid = num_sms();
+  if (p.total_steps < grid) grid = p.total_steps;
   if (p.tf32)
-    PCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<1>, L.ta, L.tb[0], L.tb[1], L.tb[2], L.tbs, p));
+    igemm_kmajor_kernel<1><<<(unsigned)grid, 256, smem, stream>>>(L.ta, L.tb[0], L.tb[1], L.tb[2], p);
   else
-    PCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<0>, L.ta, L.tb[0], L.tb[1], L.tb[2], L.tbs, p));
+    igemm_kmajor_kernel<0><<<(unsigned)grid, 256, smem, stream>>>(L.ta, L.tb[0], L.tb[1], L.tb[2], p);
+  PCRL_CHECK_CUDA(cudaGetLastError());
   return PCRL_OK;
 }
 
 // B operand maps: packed weights viewed as (K, cols, taps) bf16, boxes (kc, nc, cnt), cnt = 1..3
 static int make_b_maps(IgemmLaunch& L, const void* w, int K, int cols, int taps) {
   const uint64_t elt = L.p.tf32 ? 4 : 2;
-  L.w_ptr = w; L.w_K = K; L.w_cols = cols; L.w_taps = taps;
   for (int cnt = 1; cnt <= 3; cnt++) {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)cols, (uint64_t)taps};
     uint64_t str[2] = {(uint64_t)K * elt, (uint64_t)K * cols * elt};

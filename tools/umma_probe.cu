@@ -620,15 +620,23 @@ __global__ void __launch_bounds__(128) lean_kernel(int n, int iters, int whole_w
     const uint64_t ad = make_smem_desc(a0, 16, 1024, LAYOUT_SW128);
     const uint64_t bd = make_smem_desc(b0, 16, 1024, LAYOUT_SW128);
     if (whole_warp) {
+      __shared__ uint64_t dummy[8];
+      if (threadIdx.x == 0) { for (int i = 0; i < 8; i++) mbar_init(&dummy[i], 1); fence_barrier_init(); }
+      __syncwarp();
+      int sb = 0;
       for (int it = 0; it < iters; it++) {
+        if (whole_warp & 4) mbar_wait(&dummy[(sb + 4) & 7], 1);   // parity of the phase before the first: completes at once
+        if (whole_warp & 8) tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int mt = 0; mt < MT; mt++)
 #pragma unroll
             for (int ks = 0; ks < 4; ks++)
               umma_bf16(tmem + mt * n, ad + mt * 1024 + 2 * ks, bd + 2 * ks, idesc, 1);
+          if (whole_warp & 2) umma_commit(&dummy[sb]);
         }
         __syncwarp();
+        sb = (sb + 1) & 3;
       }
       if (elect_one()) umma_commit(&bar_mma);
     } else if (threadIdx.x == 0) {
@@ -677,6 +685,84 @@ static int run_lean(int n, int mt, int iters, int whole_warp) {
   return 0;
 }
 
+// Dual-issue probe: `nw` warps each issue their own MMA stream (own accumulator columns), with the
+// same per-8-MMA overhead options as lean (flags: 2 commit, 4 wait, 8 fence, 16 prefetched wait).
+__global__ void __launch_bounds__(128) dual_kernel(int n, int iters, int flags, int nw, float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_mma[4], dummy[4][8];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  const int a_rows = 128 * 2 + 8;
+  for (int i = threadIdx.x; i < (a_rows + n) * 128 / 4 + 256; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 4; w++) { mbar_init(&bar_mma[w], 1); for (int i = 0; i < 8; i++) mbar_init(&dummy[w][i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s + warp * n;
+  if (warp < nw) {
+    const uint32_t idesc = make_idesc(1, 128, n, 0, 0);
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + ((a_rows * 128 + 1023) / 1024) * 1024;
+    const uint64_t ad = make_smem_desc(a0, 16, 1024, LAYOUT_SW128) + (warp & 1) * 1024;
+    const uint64_t bd = make_smem_desc(b0, 16, 1024, LAYOUT_SW128);
+    int sb = 0;
+    bool ready = true;
+    for (int it = 0; it < iters; it++) {
+      if (flags & 4) mbar_wait(&dummy[warp][(sb + 4) & 7], 1);
+      if (flags & 16) { if (!ready) mbar_wait(&dummy[warp][(sb + 4) & 7], 1); ready = mbar_try_wait(&dummy[warp][(sb + 5) & 7], 1); }
+      if (flags & 8) tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            umma_bf16(tmem, ad + 2 * ks, bd + 2 * ks, idesc, 1);
+        if (flags & 2) umma_commit(&dummy[warp][sb]);
+      }
+      __syncwarp();
+      sb = (sb + 1) & 3;
+    }
+    if (elect_one()) umma_commit(&bar_mma[warp]);
+    __syncwarp();
+    mbar_wait(&bar_mma[warp], 0);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld32(tmem_base_s, v);
+    tmem_ld_wait();
+    if (v[0] == 0x12345678u) sink[0] = 1.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
+static int run_dual(int n, int iters, int flags, int nw) {
+  float* sink; CK(cudaMalloc(&sink, 4));
+  size_t smem = (size_t)(128 * 2 + 8 + n) * 128 + 4096;
+  CK(cudaFuncSetAttribute(dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  int khz = 0; CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    dual_kernel<<<sms, 128, smem>>>(n, iters, flags, nw, sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    double nmma = 8.0 * iters * nw;
+    double flops = 2.0 * 128 * n * 16 * nmma * sms;
+    if (rep == 2)
+      printf("RESULT dual n=%d iters=%d flags=%d warps=%d : %.3f ms  %.1f TFLOP/s  %.1f clk/MMA@%dMHz\n", n, iters,
+             flags, nw, ms, flops / ms * 1e-9, ms * 1e-3 * khz * 1e3 / nmma, khz / 1000);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage\n"); return 2; }
   std::string t = argv[1];
@@ -692,6 +778,8 @@ int main(int argc, char** argv) {
     return run_mnmajor(p);
   } else if (t == "halo") {
     return run_halo();
+  } else if (t == "dual") {
+    return run_dual(I(2, 128), I(3, 4000), I(4, 0), I(5, 2));
   } else if (t == "lean") {
     return run_lean(I(2, 128), I(3, 2), I(4, 4000), I(5, 0));
   } else if (t == "mix") {
