@@ -108,6 +108,43 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def measure_tf32_peak(dev, seconds=1.0):
+    """cuBLAS TF32 GEMM throughput on this GPU, measured the way MEASURED_PEAKS.json measures the
+    bf16 figure (8192^3 matmul, back to back for about `seconds`: a sustained number)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters, total_ms, total_it = 10, 0.0, 0
+        while total_ms < seconds * 1e3:
+            e0.record()
+            for _ in range(iters):
+                torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            total_it += iters
+        return 2.0 * n ** 3 * total_it / (total_ms / 1e3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+WORKLOADS = {
+    "fp32": "LUNA 3D pretrain 64x64x32 + 6x16^3 local views, b={B}/GPU, fp32 storage / TF32 tensor-core "
+            "operands (configs[1]: b=32 fp32 on 1xB200; the reference's own fp32 convs run TF32 under "
+            "torch's default cudnn.allow_tf32)",
+    "bf16": "LUNA 3D pretrain 64x64x32 + 6x16^3 local views, b={B}/GPU, bf16 "
+            "(per-GPU shard of configs[2]: b=256 bf16 on 8xB200)",
+}
+
+
 # ------------------------------------------------------------------------------------ CPU arm
 def cpu_oracle_rate(bsz=2, steps=2, warmup=1):
     """Times the CPU oracle (port of the reference step) on the host cores.  Returns
@@ -140,7 +177,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LUNA 3D pretrain 64x64x32 + 6x16^3 local views, batch 2, CPU (configs[0])"},
+        "config": {"workload": WORKLOADS["fp32"].format(B=32) + " -- CPU arm: bounded sample of batch-2 steps "
+                               "(configs[0]), fp32 torch CPU ops on all host cores"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -149,35 +187,34 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+def make_batch(B, seed, pinned):
+    g = torch.Generator().manual_seed(seed)
+
+    def t(shape, uniform=False):
+        x = torch.rand(shape, generator=g) if uniform else torch.randn(shape, generator=g)
+        return x.pin_memory() if pinned else x
+    return (t((B, 1) + VOL), t((B, 1) + VOL), t((B, 1) + VOL, True), t((B, 1) + VOL, True),
+            [t((B, 1) + LOCAL) for _ in range(6)])
+
+
+def measure(args, precision, host, rank, world, dev, full):
+    """Times K device-resident steps at `precision`; with full=True also the end-to-end leg and
+    the instrumented per-kernel step.  Returns a dict (meaningful on every rank; rank 0 prints)."""
     import torch.distributed as dist
     from pcrlv2_b200 import _lib
     from pcrlv2_b200 import train_3d as T
     from pcrlv2_b200.models import PCRLv23d
 
-    rank, world, dev = T.init_distributed()
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1")
     torch.manual_seed(42)
     random.seed(42)
     B = args.batch
-    model = PCRLv23d(precision=args.precision).to(dev).train()
+    nbatches = len(host)
+    model = PCRLv23d(precision=precision).to(dev).train()
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, src=0)
     opt = T.FlatSGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
     crit, cos = torch.nn.MSELoss(), torch.nn.CosineSimilarity()
-
-    def make_batch(seed, pinned):
-        g = torch.Generator().manual_seed(seed)
-        def t(shape, uniform=False):
-            x = torch.rand(shape, generator=g) if uniform else torch.randn(shape, generator=g)
-            return x.pin_memory() if pinned else x
-        return (t((B, 1) + VOL), t((B, 1) + VOL), t((B, 1) + VOL, True), t((B, 1) + VOL, True),
-                [t((B, 1) + LOCAL) for _ in range(6)])
-
-    nbatches = 2
-    host = [make_batch(1000 * rank + i, True) for i in range(nbatches)]
     resident = [(b[0].to(dev), b[1].to(dev), b[2].to(dev), [v.to(dev) for v in b[4]]) for b in host]
 
     def device_step(i):
@@ -210,7 +247,10 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = ms.item()
-    value = world * B * args.steps / (ms_total / 1e3)
+    out = {"value": world * B * args.steps / (ms_total / 1e3), "ms_per_step": ms_total / args.steps,
+           "gpu_launches": launches, "clocks": clocks, "precision": precision}
+    if not full:
+        return out
 
     # ---- end to end through the public trainer call: host (pinned) -> device copies every step,
     # loss meters read back every step (train_pcrlv2_inner does .item() + synchronize)
@@ -231,8 +271,9 @@ def run_ours(args):
     e2e_t = torch.tensor([t1 - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * k2 / e2e_t.item()
     h2d = sum(t.numel() * 4 for t in (host[0][0], host[0][1], host[0][2])) + sum(v.numel() * 4 for v in host[0][4])
+    out["e2e"] = {"value": world * B * k2 / e2e_t.item(), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": 8, "steps": k2}
 
     # ---- per-kernel roofline: one instrumented step (events around every entry point).  Every
     # rank runs it (the step contains the gradient all-reduce); only rank 0 reports.
@@ -241,12 +282,7 @@ def run_ours(args):
     device_step(0)
     torch.cuda.synchronize()
     prof, _lib.profile[0] = _lib.profile[0], None
-    if world > 1:
-        dist.barrier()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    barrier()
     per = {}
     for name, ints, a, b in prof:
         d = per.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
@@ -256,13 +292,48 @@ def run_ours(args):
                     "pcrl_conv3d_k3_dgrad_unshuffled"):
             n_, d_, h_, w_, ci, co = ints[-7:-1]       # (..., N, D, H, W, Cin, Cout, dtype)
             d["flops"] += 2.0 * n_ * d_ * h_ * w_ * 27 * ci * co
+    out["per"] = per
+    return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from pcrlv2_b200 import train_3d as T
+
+    rank, world, dev = T.init_distributed()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1")
+    B = args.batch
+    host = [make_batch(B, 1000 * rank + i, True) for i in range(2)]
+    main_p = args.precision
+    other_p = "bf16" if main_p == "fp32" else "fp32"
+    r = measure(args, main_p, host, rank, world, dev, True)
+    torch.cuda.empty_cache()
+    also = None
+    if not args.no_also:
+        also = measure(args, other_p, host, rank, world, dev, False)
+        torch.cuda.empty_cache()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    per = r["per"]
     peaks, peak_src = measured_peaks()
+    if main_p == "bf16":
+        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        peak_src += ", sustained bf16"
+    else:
+        peak = measure_tf32_peak(dev)
+        peak_src = "measured live in this run: cuBLAS TF32 8192^3 GEMM back to back for 1 s (sustained)"
     fam = ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_dgrad_unshuffled")
     kmajor_ms = sum(per[k]["ms"] for k in fam if k in per)
     kmajor_fl = sum(per[k]["flops"] for k in fam if k in per)
     n_kmajor = sum(per[k]["n"] for k in fam if k in per)
     achieved = kmajor_fl / (kmajor_ms / 1e3) / 1e12 if kmajor_ms > 0 else 0.0
-    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    conv_fam = fam + ("pcrl_conv3d_k3_wgrad",)
+    conv_ms = sum(per[k]["ms"] for k in conv_fam if k in per)
+    conv_fl = sum(per[k]["flops"] for k in conv_fam if k in per)
     step_ms_prof = sum(d["ms"] for d in per.values())
     breakdown = {k.replace("pcrl_", ""): {"ms": round(v["ms"], 3), "n": v["n"],
                                           **({"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)} if v["flops"] else {})}
@@ -274,15 +345,13 @@ def run_ours(args):
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     fl = flops_per_sample()
+    value = r["value"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "tf32",
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if main_p == "bf16" else "tf32",
         "data": "synthetic",
-        "config": {"workload": (f"LUNA 3D pretrain 64x64x32 + 6x16^3 local views, b={B}/GPU, bf16 "
-                                f"(per-GPU shard of configs[2]: b=256 bf16 on 8xB200)") if args.precision == "bf16" else
-                               (f"LUNA 3D pretrain 64x64x32 + 6x16^3 local views, b={B}, fp32 storage / TF32 tensor-core "
-                                f"operands (configs[1]: b=32 fp32 on 1xB200)"),
+        "config": {"workload": WORKLOADS[main_p].format(B=B),
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "activation working set per step is tens of GB >> 126 MB L2; two input batches alternate",
                    "algorithmic_gflop_per_sample": round(fl / 1e9, 2)},
@@ -292,14 +361,21 @@ def run_ours(args):
                      "kernel": "igemm_kmajor_kernel (3x3x3 conv forward + data gradient)",
                      "launches": n_kmajor, "kernel_ms_per_step": kmajor_ms,
                      "share_of_step": kmajor_ms / step_ms_prof if step_ms_prof else None,
-                     "peak_source": peak_src + ", sustained bf16"},
+                     "all_conv3_kernels": {"achieved": conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms else None,
+                                           "frac": conv_fl / (conv_ms / 1e3) / 1e12 / peak if conv_ms and peak else None,
+                                           "ms_per_step": conv_ms},
+                     "peak_source": peak_src},
         "kernel_breakdown_ms": breakdown,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                "steps": k2},
-        "gpu_launches": launches,
-        "clocks": clocks,
+        "e2e": r["e2e"],
+        "gpu_launches": r["gpu_launches"],
+        "clocks": r["clocks"],
     }
+    if also is not None:
+        line["also"] = {"dtype": "bf16" if other_p == "bf16" else "tf32",
+                        "workload": WORKLOADS[other_p].format(B=B), "value": also["value"], "unit": UNIT,
+                        "ms_per_step": also["ms_per_step"], "overall_tflops": also["value"] * fl / 1e12,
+                        "clocks": also["clocks"]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -313,8 +389,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
-                    help="activation storage / tensor-core operand type (fp32 = TF32 MMAs: configs[1])")
+    ap.add_argument("--precision", default="fp32", choices=["bf16", "fp32"],
+                    help="activation storage / tensor-core operand type of the headline measurement "
+                         "(fp32 = fp32 storage + TF32 MMAs: configs[1]; bf16: configs[2] shard)")
+    ap.add_argument("--no-also", action="store_true",
+                    help="skip the device-resident measurement at the other precision ('also' key)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -7,6 +7,7 @@ from pcrlv2_b200 import kernels as K
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 only = sys.argv[2] if len(sys.argv) > 2 else ""
+DT = torch.float32 if os.environ.get("PCRL_PREC", "bf16") == "fp32" else torch.bfloat16   # fp32 = TF32 MMAs
 LAYERS = [("down_tr64.ops.1", 32, 64, 1), ("down_tr128.ops.0", 64, 64, 2), ("down_tr128.ops.1", 64, 128, 2),
           ("down_tr256.ops.0", 128, 128, 4), ("down_tr256.ops.1", 128, 256, 4), ("down_tr512.ops.0", 256, 256, 8),
           ("down_tr512.ops.1", 256, 512, 8), ("up_tr256.ops.0", 512, 256, 4), ("up_tr256.ops.1", 256, 256, 4),
@@ -23,10 +24,10 @@ tot = {"fprop": 0, "dgrad": 0, "wgrad": 0}; totf = 0
 for name, cin, cout, s in LAYERS:
     if only and only not in name: continue
     d, h, w = 64 // s, 64 // s, 32 // s
-    x = torch.randn(B, d, h + 1, w, cin, device="cuda").to(torch.bfloat16); x[:, :, 0] = 0
-    dy = torch.randn(B, d, h + 1, w, cout, device="cuda").to(torch.bfloat16); dy[:, :, 0] = 0
+    x = torch.randn(B, d, h + 1, w, cin, device="cuda").to(DT); x[:, :, 0] = 0
+    dy = torch.randn(B, d, h + 1, w, cout, device="cuda").to(DT); dy[:, :, 0] = 0
     wt = torch.randn(cout, cin, 3, 3, 3, device="cuda") * 0.02
-    wf, wd = K.pack_conv3_weights(wt)
+    wf, wd = K.pack_conv3_weights(wt, dtype=DT)
     stats = torch.zeros(1, cout, 2, dtype=torch.float64, device="cuda")
     gpk = torch.zeros(27, cout, cin, device="cuda")
     fl = 2.0 * B * d * h * w * 27 * cin * cout
