@@ -320,12 +320,26 @@ def run_ours(args):
 
     per = r["per"]
     peaks, peak_src = measured_peaks()
+    bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    extra = {}
     if main_p == "bf16":
-        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        peak = bf16_peak
         peak_src += ", sustained bf16"
     else:
-        peak = measure_tf32_peak(dev)
-        peak_src = "measured live in this run: cuBLAS TF32 8192^3 GEMM back to back for 1 s (sustained)"
+        # kind::tf32 runs on the same tcgen05 datapath at K = 8 instead of 16 per instruction: its
+        # hardware rate is half the bf16 rate.  cuBLAS's TF32 GEMM is measured live beside it (it sits
+        # below that figure on this pool); the larger of the two is the denominator.
+        cublas_tf32 = measure_tf32_peak(dev)
+        peak = max(0.5 * bf16_peak, cublas_tf32)
+        peak_src = ("max(half of the sustained bf16 peak [" + peak_src + "], cuBLAS TF32 8192^3 GEMM measured "
+                    "live in this run for 1 s)")
+        extra = {"cublas_tf32_tflops_live": cublas_tf32, "half_bf16_sustained_tflops": 0.5 * bf16_peak}
+    # DRAM bytes of the dominant kernel's largest launch (up_tr64.ops.0 forward at b=32) from the
+    # committed ncu --set full capture: equal to its algorithmic bytes (read x once, write y once)
+    traffic = {"bf16": 1.0910e9 + 0.5056e9, "fp32": 2.1829e9 + 1.0389e9}[main_p]
+    traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of this kernel "
+                    "(up_tr64.ops.0 forward, b=32; algorithmic bytes %.3f GB), profiles/r01b_ncu_tensor_kernels.md"
+                    % ({"bf16": 1.640, "fp32": 3.279}[main_p]))
     fam = ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_dgrad_unshuffled")
     kmajor_ms = sum(per[k]["ms"] for k in fam if k in per)
     kmajor_fl = sum(per[k]["flops"] for k in fam if k in per)
@@ -357,7 +371,8 @@ def run_ours(args):
                    "algorithmic_gflop_per_sample": round(fl / 1e9, 2)},
         "overall_tflops": value * fl / 1e12,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "traffic_note": traffic_note, **extra,
                      "kernel": "igemm_kmajor_kernel (3x3x3 conv forward + data gradient)",
                      "launches": n_kmajor, "kernel_ms_per_step": kmajor_ms,
                      "share_of_step": kmajor_ms / step_ms_prof if step_ms_prof else None,

@@ -279,21 +279,40 @@ def test_fp32_forward_vs_oracle():
 
 
 def test_fp32_restoration_gradients():
-    """Same test as the bf16 one with TF32 operands: the drift floor drops by the mantissa ratio."""
+    """Same test as the bf16 one with TF32 operands.  The floor is what TF32 operand rounding costs
+    the reference's own arithmetic (oracle/tf32_emulation.py: 0.12 at the stem, where the CUDA path
+    measures 0.13; BatchNorm-backward cancellation amplifies the 2^-11 rounding layer by layer).
+    Asserted per tensor: err(CUDA, fp32) <= 1.35 * err(emulation, fp32) + 0.01, absolute bound 0.2."""
+    from oracle import tf32_emulation as emu
     m, sd0 = build("bn", precision="fp32")
     x1, _, gt, _ = orc.synthetic_batch(2, seed=42)
-    sd = orc.clone_state(sd0)
-    keys = [k for k in sd if orc.is_param(k)]
-    for k in keys:
-        sd[k].requires_grad_(True)
-    o_out, _, o_masks = orc.forward(sd, x1, False, True)
-    o_loss = torch.nn.functional.mse_loss(o_out, gt) + torch.nn.functional.mse_loss(o_masks[0], gt)
-    og = dict(zip(keys, torch.autograd.grad(o_loss, [sd[k] for k in keys], allow_unused=True)))
+    grads = {}
+    for tag, fwd in (("fp32", lambda sd: orc.forward(sd, x1, False, True)), ("emu", lambda sd: emu.forward(sd, x1))):
+        sd = orc.clone_state(sd0)
+        keys = [k for k in sd if orc.is_param(k)]
+        for k in keys:
+            sd[k].requires_grad_(True)
+        o_out, _, o_masks = fwd(sd)
+        o_loss = torch.nn.functional.mse_loss(o_out, gt) + torch.nn.functional.mse_loss(o_masks[0], gt)
+        grads[tag] = dict(zip(keys, torch.autograd.grad(o_loss, [sd[k] for k in keys], allow_unused=True)))
+        grads[tag + "_loss"] = o_loss.item()
+    og = grads["fp32"]
     out, _, masks = m(x1.cuda())
     loss = torch.nn.functional.mse_loss(out, gt.cuda()) + torch.nn.functional.mse_loss(masks[0], gt.cuda())
     loss.backward()
-    log(f"[fp32 mse-grad] loss {loss.item():.7f} vs {o_loss.item():.7f}")
-    assert abs(loss.item() - o_loss.item()) < 1e-5
+    log(f"[fp32 mse-grad] loss {loss.item():.7f} vs {grads['fp32_loss']:.7f} (tf32 emulation {grads['emu_loss']:.7f})")
+    assert abs(loss.item() - grads["fp32_loss"]) < 1e-5
     worst = _grad_table(m, og, "fp32 mse-grad")
     log(f"[fp32 mse-grad] worst significant gradient rel-L2 {worst:.3e}")
     assert worst < 0.2   # 0.13 at the stem (bf16 storage: 0.45)
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in og.values() if g is not None)).item()
+    worst_ratio = 0.0
+    for name, p in m.named_parameters():
+        gf, ge = og[name], grads["emu"][name]
+        if gf is None or gf.double().norm().item() / total < 1e-4:
+            continue
+        e_cuda, e_emu = rl2(p.grad, gf), rl2(ge, gf)
+        worst_ratio = max(worst_ratio, e_cuda / (e_emu + 0.01))
+        log(f"[fp32 mse-grad] {name:50s} cuda-vs-fp32 {e_cuda:.3e}  tf32-emulation-vs-fp32 {e_emu:.3e}")
+        assert e_cuda <= 1.35 * e_emu + 0.01, (name, e_cuda, e_emu)
+    log(f"[fp32 mse-grad] worst ratio to the TF32-operand floor {worst_ratio:.2f}")

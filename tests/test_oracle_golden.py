@@ -117,3 +117,24 @@ def test_known_answers():
     orc.sgd_step(sd, {"w": torch.tensor([0.5, 0.5])}, bufs, lr=0.1, momentum=0.9, weight_decay=0.1)
     assert torch.allclose(bufs["w"], 0.9 * torch.tensor([0.6, 0.3]) + torch.tensor([0.5 + 0.094, 0.5 - 0.203]))
     assert abs(orc.lr_at(120, 1e-3, 240) - 5e-4) < 1e-12
+
+
+def test_tf32_emulation_rounding_and_drift():
+    """oracle/tf32_emulation.py: cvt.rna.tf32 known answers, and the forward drift TF32 operands
+    cost the reference's arithmetic (the floor the fp32-storage CUDA mode is held to)."""
+    from oracle import tf32_emulation as emu
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -11 + 2 ** -12, -1.0 - 2 ** -11, 3.14159, 0.0, -0.0])
+    want = [1.0, 1.0 + 2 ** -10, 1.0 + 2 ** -10, -1.0 - 2 ** -10, 3.140625, 0.0, -0.0]
+    assert emu.rna_tf32(x).tolist() == want
+    r = emu.rna_tf32(torch.randn(4096))
+    assert torch.equal(emu.rna_tf32(r), r)                       # idempotent
+    assert (r.view(torch.int32) & 0x1FFF).abs().max().item() == 0  # 13 low mantissa bits clear
+    sd = orc.init_state(0)
+    x1, _, _, _ = orc.synthetic_batch(2, seed=42, vol=(32, 32, 16))
+    with torch.no_grad():
+        a, _, ma = orc.forward(orc.clone_state(sd), x1, False, True)
+        b, _, mb = emu.forward(sd, x1)
+    err = ((a - b).norm() / a.norm()).item()
+    assert 1e-5 < err < 5e-3, err
+    for u, v in zip(ma, mb):
+        assert ((u - v).norm() / u.norm()).item() < 1e-2
