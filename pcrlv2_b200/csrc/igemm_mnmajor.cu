@@ -11,13 +11,18 @@
 // taps from one X slab (row-shifted views), K-stages are `nrows` merged rows of one sample in the
 // flat index space of common.cuh; tails of the stage buffers are zero so the K loop can run in
 // whole 16-row steps.
+// No halo rows are loaded for the dx taps: slab row 0 of every merged row is the virtual zero column
+// (TMA out-of-bounds fill), so the dY view starts at slab row 1 and pairs dY row k+1 with X rows
+// k+0 / k+1 / k+2 (dx = -1 / 0 / +1); the only X row outside the box that meets a non-zero dY row is
+// the virtual column of the NEXT merged row, i.e. zero -- which is what the never-written tail holds.
 // PAIR mode (Cout chunk of 64): an M = 64 MMA occupies the tensor pipe as long as an M = 128 one, so
 // a CTA owns TWO (dz, dy) groups instead of one: the second half of the M = 128 operand is the same
 // dY chunk loaded `delta` merged rows earlier (dY[f - delta] * X[f + off_a] = tap off_a + delta), the X
 // slab is shared.  The nine groups become five CTA groups (the last one alone; its upper half is
 // not stored), i.e. 1.8x fewer tensor-pipe cycles on the 64-channel layers.
-// Grid order: the (dz, dy) groups are blockIdx.x, the reduction split is blockIdx.y, so CTAs that
-// run at the same time read the SAME K-stages (L2 hits instead of nine DRAM passes over X and dY).
+// Grid order: blockIdx.x = (dz,dy) group fastest, then the (Cout, Cin) chunk pair; blockIdx.y = the
+// reduction split.  CTAs that run at the same time therefore read the SAME K-stages (L2 hits instead
+// of nine DRAM passes over X and dY).
 // Reference: autograd of nn.Conv3d / nn.ConvTranspose3d / nn.Linear weights reached from
 // train_3d.py:148 (loss.backward()).
 #include "common.cuh"
@@ -53,6 +58,7 @@ struct WgradParams {
   int stack_dx;                          // CONV: one MMA of N = 3*nc covers the three dx taps
   int m_chunks_total;                    // Cout / mch
   int pair;                              // CONV: two (dz,dy) groups per CTA stacked along M (see header)
+  int ngroups;                           // CTA groups over (dz,dy): 9, 5 in PAIR mode, 1 in PLAIN mode
   int mch;                               // dW rows (output channels) per m-chunk: mc, or 64 in PAIR mode
   int cout, cin;                         // leading dims of dW: [tap][cout][cin]
   long long rows_total;
@@ -77,9 +83,10 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunk = blockIdx.y;
   // (dz,dy) group(s) of this CTA in CONV mode: ga for M rows 0..63 (all rows without PAIR), gb for 64..127
-  const int ga = p.pair ? 2 * (int)blockIdx.x : (int)blockIdx.x;
+  const int gidx = (int)blockIdx.x % p.ngroups, mn = (int)blockIdx.x / p.ngroups;
+  const int ga = p.pair ? 2 * gidx : gidx;
   const int gb = p.pair ? min(ga + 1, 8) : ga;
-  const int mchunk = blockIdx.z % p.m_chunks_total, nchunk = blockIdx.z / p.m_chunks_total;
+  const int mchunk = mn % p.m_chunks_total, nchunk = mn / p.m_chunks_total;
   const int dzo = ga / 3 - 1, dyo = ga % 3 - 1;
   const int delta = (gb / 3 - ga / 3) * p.H1 + (gb % 3 - ga % 3);   // merged rows the second dY view lags
 
@@ -131,7 +138,7 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
           }
           for (int c = 0; c < p.b_chunks; c++)
             tma_load_4d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st],
-                        nchunk * p.nc + c * p.chunk_ch, -1, mr0 + dzo * p.H1 + dyo - 1, n);
+                        nchunk * p.nc + c * p.chunk_ch, -1, mr0 + dzo * p.H1 + dyo, n);
         } else {
           const int r0 = s * p.nrows;
           for (int c = 0; c < p.a_chunks; c++)
@@ -161,15 +168,17 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     for (int s = s_begin; s < s_end; s++) {
       mbar_wait(&full[st], ph);
       tc_fence_after();
-      const uint32_t a_base = smem_u32(smem + (size_t)st * stage_bytes);
-      const uint32_t b_base = a_base + a_stage_bytes;
+      const uint32_t a_slab = smem_u32(smem + (size_t)st * stage_bytes);
+      const uint32_t b_base = a_slab + a_stage_bytes;
+      // CONV: the dY view starts one row into the slab (see header)
+      const uint32_t a_base = a_slab + (p.mode == WG_CONV ? (uint32_t)p.a_row_bytes : 0u);
       if (elect_one()) {
         if (p.stack_dx) {
           // the three dx taps are the same X slab shifted by one row each: with a single channel
           // chunk per tap they form ONE MN-major operand of N = 3*nc whose chunk stride (LBO) is one
           // slab row, so a single MMA fills the three accumulators (N = 96 / 192 instead of 3 x 32 / 64)
           uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
-          uint64_t bd = b_stack_hi | (uint64_t)(((b_base + (uint32_t)(p.Wp - 1) * p.b_row_bytes) >> 4) & 0x3FFF);
+          uint64_t bd = b_stack_hi | (uint64_t)((b_base >> 4) & 0x3FFF);
           umma_any<TF32>(tmem, ad, bd, idesc_stack, accumulate);
           for (int ks = 1; ks < p.ksteps; ks++) {
             ad += a_step;
@@ -178,7 +187,7 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
           }
         } else {
           for (int t = 0; t < p.ntaps; t++) {
-            const int b_row0 = (p.mode == WG_CONV) ? (p.Wp + (t - 1)) : 0;
+            const int b_row0 = (p.mode == WG_CONV) ? t : 0;
             uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
             uint64_t bd = b_hi | (uint64_t)(((b_base + (uint32_t)b_row0 * p.b_row_bytes) >> 4) & 0x3FFF);
             const uint32_t d = tmem + t * p.nc;
@@ -277,36 +286,51 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   p.krows = 32 / elt;
   p.chunk_ch = 128 / elt;
   p.W = W; p.Wp = W + 1; p.H1 = H + 1; p.MR = D * (H + 1); p.nsamples = N;
-  // merged rows per stage: aim at ~128..160 reduction rows (half of that for fp32 operands)
-  const int target = tf32 ? 64 : 128;
-  p.nrows = (target + p.Wp - 1) / p.Wp;
-  if (p.nrows > p.MR) p.nrows = p.MR;
-  if (p.nrows + 2 > 256) return fail(PCRL_ERR_UNSUPPORTED, "conv3d_k3_wgrad: W too small");
-  p.kr = p.nrows * p.Wp;
-  p.ksteps = (p.kr + p.krows - 1) / p.krows;
   p.pair = (Cout % 128 != 0 && !getenv("PCRL_WGRAD_NOPAIR")) ? 1 : 0;
-  // PAIR: the second dY view lags by up to H1 - 2 merged rows (groups (dz=-1,dy=+1) | (dz=0,dy=-1)),
-  // so the reduction range is extended by that much (rows outside the sample are TMA zero fill)
-  const int k_extra = p.pair ? (p.H1 - 2 > 1 ? p.H1 - 2 : 1) : 0;
-  p.stages_per_sample = (p.MR + k_extra + p.nrows - 1) / p.nrows;
-  p.total_stages = p.stages_per_sample * N;
   p.mc = (Cout % 128 == 0 || p.pair) ? 128 : 64;
   p.mch = p.pair ? 64 : p.mc;
   p.nc = (Cin % 128 == 0) ? 128 : (Cin % 64 == 0 ? 64 : 32);
   p.a_row_bytes = 128; p.a_chunks = p.mc / p.chunk_ch;
   if (!tf32 && p.nc == 32) { p.b_row_bytes = 64; p.b_chunks = 1; }
   else { p.b_row_bytes = 128; p.b_chunks = p.nc / p.chunk_ch; }
-  p.a_chunk_bytes = round_up(p.ksteps * p.krows * p.a_row_bytes, 1024);
-  p.b_box_rows = (p.nrows + 2) * p.Wp;
-  const int b_rows_needed = p.ksteps * p.krows + p.Wp + 2;
-  p.b_chunk_bytes = round_up((b_rows_needed > p.b_box_rows ? b_rows_needed : p.b_box_rows) * p.b_row_bytes, 1024);
+  // merged rows per stage: start from ~128 reduction rows (64 for fp32 operands) and shrink until
+  // three stages fit in shared memory (latency hiding needs the depth more than the stage size);
+  // if even one merged row per stage does not allow three, take the largest two-stage tiling
+  const int target = tf32 ? 64 : 128;
+  int nrows0 = (target + p.Wp - 1) / p.Wp;
+  if (nrows0 > p.MR) nrows0 = p.MR;
+  if (nrows0 > 256) return fail(PCRL_ERR_UNSUPPORTED, "conv3d_k3_wgrad: W too small");
+  if (const char* e = getenv("PCRL_WGRAD_NROWS")) { if (atoi(e) > 0 && atoi(e) <= p.MR) nrows0 = atoi(e); }
+  int chosen = 0;
+  for (int want = 3; want >= 2 && !chosen; want--) {
+    for (int nr = nrows0; nr >= 1; nr--) {
+      const int ks = (nr * p.Wp + p.krows - 1) / p.krows;
+      const int ab = round_up((ks * p.krows + 1) * p.a_row_bytes, 1024);
+      const int bb = round_up((ks * p.krows + 3) * p.b_row_bytes, 1024);
+      const bool padded_ok = want == 2 || 100 * ks * p.krows <= 115 * nr * p.Wp;   // <= 15 % zero rows
+      if (padded_ok && (size_t)want * (p.a_chunks * ab + p.b_chunks * bb) <= 200 * 1024) { chosen = nr; break; }
+      if (want == 3 && 2 * nr <= nrows0) break;       // do not shrink the stage below half the target
+    }
+  }
+  if (!chosen) return fail(PCRL_ERR_ARG, "conv3d_k3_wgrad: no stage tiling fits shared memory");
+  p.nrows = chosen;
+  p.kr = p.nrows * p.Wp;
+  p.ksteps = (p.kr + p.krows - 1) / p.krows;
+  // PAIR: the second dY view lags by up to H1 - 2 merged rows (groups (dz=-1,dy=+1) | (dz=0,dy=-1)),
+  // so the reduction range is extended by that much (rows outside the sample are TMA zero fill)
+  const int k_extra = p.pair ? (p.H1 - 2 > 1 ? p.H1 - 2 : 1) : 0;
+  p.stages_per_sample = (p.MR + k_extra + p.nrows - 1) / p.nrows;
+  p.total_stages = p.stages_per_sample * N;
+  p.a_chunk_bytes = round_up((p.ksteps * p.krows + 1) * p.a_row_bytes, 1024);
+  p.b_box_rows = p.nrows * p.Wp;
+  p.b_chunk_bytes = round_up((p.ksteps * p.krows + 3) * p.b_row_bytes, 1024);
   p.ntaps = 3;
   p.stack_dx = (p.b_chunks == 1 && !getenv("PCRL_WGRAD_NOSTACK")) ? 1 : 0;
   p.m_chunks_total = Cout / p.mch;
   p.cout = Cout; p.cin = Cin; p.dw = dw;
   // split the reduction so that the grid has a few waves
-  const int ngroups = p.pair ? 5 : 9;
-  const int other = ngroups * (Cout / p.mch) * (Cin / p.nc);
+  p.ngroups = p.pair ? 5 : 9;
+  const int other = p.ngroups * (Cout / p.mch) * (Cin / p.nc);
   int kchunks = (4 * num_sms() + other - 1) / other;
   if (kchunks > p.total_stages) kchunks = p.total_stages;
   if (kchunks < 1) kchunks = 1;
@@ -324,13 +348,13 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)p.MR, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cin * elt, (uint64_t)W * Cin * elt, (uint64_t)p.MR * W * Cin * elt};
-    uint32_t box[4] = {(uint32_t)(p.b_row_bytes / elt), (uint32_t)p.Wp, (uint32_t)(p.nrows + 2), 1};
+    uint32_t box[4] = {(uint32_t)(p.b_row_bytes / elt), (uint32_t)p.Wp, (uint32_t)p.nrows, 1};
     int rc = encode_map(&tb, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, str, box,
                         tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                              : (p.b_row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
     if (rc) return rc;
   }
-  dim3 grid((unsigned)ngroups, (unsigned)kchunks, (unsigned)((Cout / p.mch) * (Cin / p.nc)));
+  dim3 grid((unsigned)other, (unsigned)kchunks, 1);
   return launch_wgrad(p, ta, tb, grid, stream);
 }
 
@@ -359,6 +383,7 @@ int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P
   p.ntaps = 1;
   p.m_chunks_total = P / p.mc;
   p.mch = p.mc;
+  p.ngroups = 1;
   p.cout = P; p.cin = Q; p.dw = dw; p.rows_total = rows;
   const int other = (P / p.mc) * (Q / p.nc);
   int kchunks = (2 * num_sms() + other - 1) / other;
@@ -384,7 +409,7 @@ int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P
                              : (p.b_row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
     if (rc) return rc;
   }
-  dim3 grid(1, (unsigned)kchunks, (unsigned)((P / p.mc) * (Q / p.nc)));
+  dim3 grid((unsigned)other, (unsigned)kchunks, 1);
   return launch_wgrad(p, ta, tb, grid, stream);
 }
 
