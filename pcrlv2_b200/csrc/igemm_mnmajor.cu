@@ -53,6 +53,8 @@ struct WgradParams {
   int b_box_rows;                        // rows written by the X TMA box
   int ntaps;                             // taps per CTA (3 in CONV, 1 in PLAIN)
   int stages, tmem_cols;
+  int rot_stages;                        // CONV: stage rotation per dz plane (see the producer)
+  int nacc;                              // accumulator sets (1 or 2) that k-steps alternate between
   int tf32, krows;                       // fp32 operands / kind::tf32; reduction rows per MMA (16 or 8)
   int chunk_ch;                          // channels per 128-byte chunk row (64 bf16 / 32 fp32)
   int stack_dx;                          // CONV: one MMA of N = 3*nc covers the three dx taps
@@ -128,8 +130,14 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
       if (elect_one()) {
         mbar_expect_tx(&full[st], tx);
         if (p.mode == WG_CONV) {
-          const int n = s / p.stages_per_sample;
-          const int mr0 = (s % p.stages_per_sample) * p.nrows;
+          // stage rotation (rot_stages = dz * H1 / nrows when X is the larger operand): the groups of
+          // the three dz planes then read the SAME X rows at the same time (they differ in dY rows
+          // instead), so X is fetched from DRAM once; any permutation of the stages is a valid order
+          int se = s - dzo * p.rot_stages;
+          if (se < 0) se += p.total_stages;
+          else if (se >= p.total_stages) se -= p.total_stages;
+          const int n = se / p.stages_per_sample;
+          const int mr0 = (se % p.stages_per_sample) * p.nrows;
           const int cpv = p.a_chunks >> p.pair;            // channel chunks per dY view
           for (int c = 0; c < p.a_chunks; c++) {
             const int view = c / cpv, cc = c - view * cpv;
@@ -164,7 +172,13 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     const uint32_t a_step = (uint32_t)(p.krows * p.a_row_bytes) >> 4, b_step = (uint32_t)(p.krows * p.b_row_bytes) >> 4;
     const uint32_t idesc_stack = make_idesc(fmt, (uint32_t)p.mc, (uint32_t)(3 * p.nc), 1, 1);
     const uint64_t b_stack_hi = make_smem_desc(0, p.b_row_bytes, b_sbo, b_lay);
-    uint32_t accumulate = 0;
+    // Back-to-back MMAs into the SAME accumulator run at ~3/4 of the rate of MMAs that rotate over
+    // several (tools/umma_probe: N = 128, 1554 vs 2026 TFLOP/s), so consecutive MMAs never share one:
+    // the three dx taps are interleaved inside the k-step loop, and where TMEM has room (nacc = 2)
+    // even / odd k-steps use two accumulator sets that the epilogue adds.
+    const uint32_t set_cols = (uint32_t)(p.ntaps * p.nc);
+    const uint32_t b_row16 = (uint32_t)p.b_row_bytes >> 4;
+    uint32_t kq = 0;                                  // k-steps issued so far by this CTA
     for (int s = s_begin; s < s_end; s++) {
       mbar_wait(&full[st], ph);
       tc_fence_after();
@@ -173,36 +187,43 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
       // CONV: the dY view starts one row into the slab (see header)
       const uint32_t a_base = a_slab + (p.mode == WG_CONV ? (uint32_t)p.a_row_bytes : 0u);
       if (elect_one()) {
+        uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
         if (p.stack_dx) {
           // the three dx taps are the same X slab shifted by one row each: with a single channel
           // chunk per tap they form ONE MN-major operand of N = 3*nc whose chunk stride (LBO) is one
           // slab row, so a single MMA fills the three accumulators (N = 96 / 192 instead of 3 x 32 / 64)
-          uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
           uint64_t bd = b_stack_hi | (uint64_t)((b_base >> 4) & 0x3FFF);
-          umma_any<TF32>(tmem, ad, bd, idesc_stack, accumulate);
-          for (int ks = 1; ks < p.ksteps; ks++) {
+          for (int ks = 0; ks < p.ksteps; ks++, kq++) {
+            const uint32_t set = kq & (uint32_t)(p.nacc - 1);
+            umma_any<TF32>(tmem + set * set_cols, ad, bd, idesc_stack, kq >= (uint32_t)p.nacc ? 1u : 0u);
             ad += a_step;
             bd += b_step;
-            umma_any<TF32>(tmem, ad, bd, idesc_stack, 1u);
+          }
+        } else if (p.ntaps == 3) {
+          uint64_t bd = b_hi | (uint64_t)((b_base >> 4) & 0x3FFF);
+          for (int ks = 0; ks < p.ksteps; ks++, kq++) {
+            const uint32_t d = tmem + (kq & (uint32_t)(p.nacc - 1)) * set_cols;
+            const uint32_t acc = kq >= (uint32_t)p.nacc ? 1u : 0u;
+            umma_any<TF32>(d, ad, bd, idesc, acc);
+            umma_any<TF32>(d + (uint32_t)p.nc, ad, bd + b_row16, idesc, acc);
+            umma_any<TF32>(d + 2u * (uint32_t)p.nc, ad, bd + 2u * b_row16, idesc, acc);
+            ad += a_step;
+            bd += b_step;
           }
         } else {
-          for (int t = 0; t < p.ntaps; t++) {
-            const int b_row0 = (p.mode == WG_CONV) ? t : 0;
-            uint64_t ad = a_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
-            uint64_t bd = b_hi | (uint64_t)(((b_base + (uint32_t)b_row0 * p.b_row_bytes) >> 4) & 0x3FFF);
-            const uint32_t d = tmem + t * p.nc;
-            umma_any<TF32>(d, ad, bd, idesc, accumulate);
-            for (int ks = 1; ks < p.ksteps; ks++) {
-              ad += a_step;
-              bd += b_step;
-              umma_any<TF32>(d, ad, bd, idesc, 1u);
-            }
+          uint64_t bd = b_hi | (uint64_t)((b_base >> 4) & 0x3FFF);
+          for (int ks = 0; ks < p.ksteps; ks++, kq++) {
+            const uint32_t set = kq & (uint32_t)(p.nacc - 1);
+            umma_any<TF32>(tmem + set * set_cols, ad, bd, idesc, kq >= (uint32_t)p.nacc ? 1u : 0u);
+            ad += a_step;
+            bd += b_step;
           }
         }
         umma_commit(&empty[st]);
+      } else {
+        kq += (uint32_t)p.ksteps;
       }
       __syncwarp();
-      accumulate = 1;
       if (++st == p.stages) { st = 0; ph ^= 1; }
     }
     if (elect_one()) umma_commit(acc_full);
@@ -218,6 +239,8 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     bool row_ok;
     if (p.mc == 128) { row = warp * 32 + lane; row_ok = true; }
     else { row = warp * 16 + lane; row_ok = lane < 16; }
+    // the second accumulator set exists only if this CTA issued at least two k-steps
+    const bool two_sets = p.nacc == 2 && (long long)(s_end - s_begin) * p.ksteps >= 2;
     int g = ga, orow = row;
     if (p.pair) {
       if (row >= 64) { g = gb; orow = row - 64; row_ok = gb != ga; }
@@ -230,6 +253,13 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + t * p.nc + c, v);
         tmem_ld_wait();
+        if (two_sets) {
+          uint32_t v2[32];
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + p.ntaps * p.nc + t * p.nc + c, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+        }
         if (row_ok) {
 #pragma unroll
           for (int i = 0; i < 8; i++)
@@ -251,7 +281,8 @@ static int launch_wgrad(WgradParams& p, const CUtensorMap& ta, const CUtensorMap
   while (p.stages > 2 && (size_t)p.stages * stage_bytes > 200 * 1024) p.stages--;
   if ((size_t)p.stages * stage_bytes > 210 * 1024)
     return fail(PCRL_ERR_ARG, "wgrad: stage of %d bytes does not fit shared memory", stage_bytes);
-  int cols = p.ntaps * p.nc, t = 32;
+  p.nacc = (2 * p.ntaps * p.nc <= 512 && !getenv("PCRL_WGRAD_NACC1")) ? 2 : 1;
+  int cols = p.nacc * p.ntaps * p.nc, t = 32;
   while (t < cols) t <<= 1;
   p.tmem_cols = t;
   const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
@@ -321,6 +352,9 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   const int k_extra = p.pair ? (p.H1 - 2 > 1 ? p.H1 - 2 : 1) : 0;
   p.stages_per_sample = (p.MR + k_extra + p.nrows - 1) / p.nrows;
   p.total_stages = p.stages_per_sample * N;
+  // (measured on B200: +3 % with fp32 operands, where the unrotated working set overflows L2; -2 % with bf16)
+  p.rot_stages = (tf32 && Cin >= Cout && !getenv("PCRL_WGRAD_NOROT")) ? p.H1 / p.nrows : 0;
+  if (p.rot_stages >= p.total_stages) p.rot_stages = 0;
   p.a_chunk_bytes = round_up((p.ksteps * p.krows + 1) * p.a_row_bytes, 1024);
   p.b_box_rows = p.nrows * p.Wp;
   p.b_chunk_bytes = round_up((p.ksteps * p.krows + 3) * p.b_row_bytes, 1024);

@@ -344,6 +344,7 @@ struct NormActFwdParams {
   const float* scale; const float* shift; const float* prelu;
   T* a_out; T* pool_out; float* avg_sum;
   int per_sample, act, N, D, H, W, C;
+  int wseg;          // a row of W voxels is processed as wseg segments (rows wider than one block)
 };
 
 struct RowMap {
@@ -381,7 +382,8 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
   const int H1 = p.H + 1;
   const int cd = POOL ? p.D / 2 : p.D, ch = POOL ? p.H / 2 : p.H, cw = POOL ? p.W / 2 : p.W;
   const int R = cd * (ch + 1);                 // merged rows of the (pooled) output
-  const RowMap m = make_row_map(cw, C8);
+  const int cws = cw / p.wseg, Rv = R * p.wseg;   // segment width, virtual (row, segment) count
+  const RowMap m = make_row_map(cws, C8);
   const bool lane_ok = m.t_row < m.rows_per_iter && m.chunks == 1;
   float asum[8], sc[8], sh[8], sl[8];
 #pragma unroll
@@ -397,17 +399,18 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
   }
   constexpr int U = POOL ? 1 : 4;
   const size_t row_elems = (size_t)p.W * p.C;            // elements of one fine row
-  for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < R; row0 += gridDim.x * m.rows_per_iter * U) {
+  for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < Rv; row0 += gridDim.x * m.rows_per_iter * U) {
     if (!POOL) {
       V8<T> yv[U];
       int kind[U];
       size_t off[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int row = row0 + u * m.rows_per_iter + m.t_row;
+        const int vrow = row0 + u * m.rows_per_iter + m.t_row;
+        const int row = vrow / p.wseg, w = (vrow % p.wseg) * cws + m.w;
         kind[u] = 0;
-        if (lane_ok && row < R) {
-          off[u] = ((size_t)n * R + row) * row_elems + (size_t)m.w * p.C + m.c8 * 8;
+        if (lane_ok && vrow < Rv) {
+          off[u] = ((size_t)n * R + row) * row_elems + (size_t)w * p.C + m.c8 * 8;
           kind[u] = (row % H1) == 0 ? 1 : 2;
           if (kind[u] == 2) yv[u] = ld8(p.y + off[u]);
         }
@@ -430,16 +433,17 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
         }
       }
     } else {
-      const int row = row0 + m.t_row;
-      if (!(lane_ok && row < R)) continue;
+      const int vrow = row0 + m.t_row;
+      if (!(lane_ok && vrow < Rv)) continue;
+      const int row = vrow / p.wseg, w = (vrow % p.wseg) * cws + m.w;
       const int hp = row % (ch + 1), d = row / (ch + 1);
-      const size_t pooled_off = (((size_t)n * R + row) * cw + m.w) * p.C + m.c8 * 8;
+      const size_t pooled_off = (((size_t)n * R + row) * cw + w) * p.C + m.c8 * 8;
       if (hp == 0) {  // pad rows of the outputs
         if (p.pool_out) z8(p.pool_out + pooled_off);
         if (p.a_out)
           for (int i = 0; i < 2; i++)
             for (int k = 0; k < 2; k++)
-              z8(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
+              z8(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * w + k) * p.C + m.c8 * 8);
         continue;
       }
       const int h = hp - 1;
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
         yv[pos] = ld8(
-            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
+            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * p.C + m.c8 * 8);
       }
       float mx[8];
 #pragma unroll
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
           mx[q] = fmaxf(mx[q], v[q]);
         }
         if (p.a_out)
-          st8(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8, v);
+          st8(p.a_out + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * p.C + m.c8 * 8, v);
       }
       if (p.pool_out) st8(p.pool_out + pooled_off, mx);
     }
@@ -505,6 +509,7 @@ struct NormActBwdParams {
   T* dy; // pass 2
   double count;      // elements per (group, channel)
   int per_sample, act, N, D, H, W, C;
+  int wseg;          // a row of W voxels is processed as wseg segments (rows wider than one block)
 };
 
 template <typename T, bool POOL, bool APPLY, int ACT>
@@ -515,7 +520,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
   const int H1 = p.H + 1;
   const int cd = POOL ? p.D / 2 : p.D, ch = POOL ? p.H / 2 : p.H, cw = POOL ? p.W / 2 : p.W;
   const int R = cd * (ch + 1);
-  const RowMap m = make_row_map(cw, C8);
+  const int cws = cw / p.wseg, Rv = R * p.wseg;   // segment width, virtual (row, segment) count
+  const RowMap m = make_row_map(cws, C8);
   const bool lane_ok = m.t_row < m.rows_per_iter && m.chunks == 1;
   const size_t so = (p.per_sample ? (size_t)n * p.C : 0) + m.c8 * 8;
   // x_hat = y*is - mis ; z = y*sc + sh ; apply: dy = gs*dz - c1 - y*c2   (constants folded)
@@ -544,17 +550,18 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
   for (int i = 0; i < 8; i++) a0[i] = a1[i] = a2[i] = 0.f;
   constexpr int U = POOL ? 1 : 4;
   const size_t row_elems = (size_t)p.W * p.C;
-  for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < R; row0 += gridDim.x * m.rows_per_iter * U) {
+  for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < Rv; row0 += gridDim.x * m.rows_per_iter * U) {
     if (!POOL) {
       V8<T> yq[U], g1q[U], g2q[U];
       int kind[U];
       size_t off[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int row = row0 + u * m.rows_per_iter + m.t_row;
+        const int vrow = row0 + u * m.rows_per_iter + m.t_row;
+        const int row = vrow / p.wseg, w = (vrow % p.wseg) * cws + m.w;
         kind[u] = 0;
-        if (lane_ok && row < R) {
-          off[u] = ((size_t)n * R + row) * row_elems + (size_t)m.w * p.C + m.c8 * 8;
+        if (lane_ok && vrow < Rv) {
+          off[u] = ((size_t)n * R + row) * row_elems + (size_t)w * p.C + m.c8 * 8;
           kind[u] = (row % H1) == 0 ? 1 : 2;
           if (kind[u] == 2) {
             yq[u] = ld8(p.y + off[u]);
@@ -591,25 +598,26 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
         }
       }
     } else {
-      const int row = row0 + m.t_row;
-      if (!(lane_ok && row < R)) continue;
+      const int vrow = row0 + m.t_row;
+      if (!(lane_ok && vrow < Rv)) continue;
+      const int row = vrow / p.wseg, w = (vrow % p.wseg) * cws + m.w;
       const int hp = row % (ch + 1), d = row / (ch + 1);
       if (hp == 0) {
         if (APPLY)
           for (int i = 0; i < 2; i++)
             for (int k = 0; k < 2; k++)
-              z8(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
+              z8(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * w + k) * p.C + m.c8 * 8);
         continue;
       }
       const int h = hp - 1;
       float gp[8];
-      up8(ld8(p.g1 + (((size_t)n * R + row) * cw + m.w) * p.C + m.c8 * 8), gp);
+      up8(ld8(p.g1 + (((size_t)n * R + row) * cw + w) * p.C + m.c8 * 8), gp);
       V8<T> yq[8];
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
         yq[pos] = ld8(
-            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8);
+            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * p.C + m.c8 * 8);
       }
       int arg[8];
       float mx[8];
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
-        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * m.w + k) * p.C + m.c8 * 8;
+        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * p.C + m.c8 * 8;
         float yv[8], g2v[8], out[8];
         up8(yq[pos], yv);
         if (p.g2) up8(ld8(p.g2 + off), g2v);
@@ -820,15 +828,24 @@ int norm_finalize(const double* stats, double count, const float* gamma, const f
   return PCRL_OK;
 }
 
+// number of equal segments a row of cw voxels x C8 8-channel groups is cut into so that one segment
+// fits a 256-thread block (1 for every 64x64x32 layer; 2..4 for the 128x128x64 crops); 0 = impossible
+static int row_segments(int cw, int C8) {
+  for (int sgm = 1; sgm <= cw; sgm++)
+    if (cw % sgm == 0 && (cw / sgm) * C8 <= 256) return sgm;
+  return 0;
+}
+
 template <typename T>
 static int norm_act_fwd_t(const void* y, const float* scale, const float* shift, const float* prelu,
                           void* a_out, void* pool_out, float* avg_sum, int per_sample, int act, int pool,
                           int N, int D, int H, int W, int C, cudaStream_t s) {
   const int cw = pool ? W / 2 : W;
+  const int wseg = row_segments(cw, C / 8);
   NormActFwdParams<T> p{(const T*)y, scale, shift, prelu, (T*)a_out, (T*)pool_out, avg_sum,
-                        per_sample, act, N, D, H, W, C};
-  const int items = cw * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
-  const int R = pool ? (D / 2) * (H / 2 + 1) : D * (H + 1);
+                        per_sample, act, N, D, H, W, C, wseg};
+  const int items = (cw / wseg) * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
+  const int R = (pool ? (D / 2) * (H / 2 + 1) : D * (H + 1)) * wseg;
   int bx = (R + rpi * U - 1) / (rpi * U);
   const int cap = (num_sms() * 8 + N - 1) / N;
   if (bx > cap) bx = cap;
@@ -853,7 +870,7 @@ int norm_act_fwd(const void* y, const float* scale, const float* shift, const fl
   PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_fwd: C=%d must be 8 * 2^k", C);
   PCRL_REQUIRE(!pool || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "norm_act_fwd: pooling needs even dims");
   PCRL_REQUIRE(!(pool && avg_sum), "norm_act_fwd: avg_sum with pool is not supported");
-  PCRL_REQUIRE((pool ? W / 2 : W) * (C / 8) <= 256, "norm_act_fwd: row of %d x %d channels is too wide", W, C);
+  PCRL_REQUIRE(row_segments(pool ? W / 2 : W, C / 8) > 0, "norm_act_fwd: row of %d x %d channels cannot be split into block-sized segments", W, C);
   if (dtype == PCRL_DTYPE_F32)
     return norm_act_fwd_t<float>(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H, W, C, s);
   return norm_act_fwd_t<bf16_t>(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H, W, C, s);
@@ -867,9 +884,9 @@ static int norm_act_bwd_t(const void* y, const void* g1, const void* g2, const f
                           cudaStream_t s) {
   const int cw = pool ? W / 2 : W;
   NormActBwdParams<T> p{(const T*)y, (const T*)g1, (const T*)g2, gavg, scale, shift, mean, invstd, gamma,
-                        prelu, sums, (T*)dy, count, per_sample, act, N, D, H, W, C};
-  const int items = cw * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
-  const int R = pool ? (D / 2) * (H / 2 + 1) : D * (H + 1);
+                        prelu, sums, (T*)dy, count, per_sample, act, N, D, H, W, C, row_segments(cw, C / 8)};
+  const int items = (cw / p.wseg) * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
+  const int R = (pool ? (D / 2) * (H / 2 + 1) : D * (H + 1)) * p.wseg;
   int bx = (R + rpi * U - 1) / (rpi * U);
   const int cap = (num_sms() * 8 + N - 1) / N;
   if (bx > cap) bx = cap;
@@ -902,7 +919,7 @@ int norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gav
                  int dtype, cudaStream_t s) {
   PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_bwd: C=%d must be 8 * 2^k", C);
   PCRL_REQUIRE(!pool || g1, "norm_act_bwd: pooled backward needs g1");
-  PCRL_REQUIRE((pool ? W / 2 : W) * (C / 8) <= 256, "norm_act_bwd: row of %d x %d channels is too wide", W, C);
+  PCRL_REQUIRE(row_segments(pool ? W / 2 : W, C / 8) > 0, "norm_act_bwd: row of %d x %d channels cannot be split into block-sized segments", W, C);
   if (dtype == PCRL_DTYPE_F32)
     return norm_act_bwd_t<float>(y, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu, sums, dy, count,
                                  per_sample, act, pool, pass, N, D, H, W, C, s);

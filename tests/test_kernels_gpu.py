@@ -152,7 +152,20 @@ def _norm_ref(y, gamma, beta, act, per_sample, slope=None):
 @pytest.mark.parametrize("act", ["relu", "elu", "prelu", "sigmoid"])
 @pytest.mark.parametrize("mode", ["full", "pool", "avg"])
 def test_norm_act(per_sample, act, mode):
-    n, c, d, h, w = 3, 64, 4, 6, 8
+    _norm_act_case(per_sample, act, mode, (3, 64, 4, 6, 8))
+
+
+# rows wider than one 256-thread block (W * C/8 > 256: the 128x128x64 crops of BASELINE configs[3])
+# are processed as several segments per row
+@pytest.mark.parametrize("per_sample", [False, True])
+@pytest.mark.parametrize("mode", ["full", "pool", "avg"])
+@pytest.mark.parametrize("dims", [(2, 64, 2, 4, 64), (1, 128, 2, 2, 48), (2, 32, 4, 2, 128)])
+def test_norm_act_wide_rows(per_sample, mode, dims):
+    _norm_act_case(per_sample, "relu", mode, dims)
+
+
+def _norm_act_case(per_sample, act, mode, dims):
+    n, c, d, h, w = dims
     torch.manual_seed(5)
     y = q(torch.randn(n, c, d, h, w, device=DEV) * 2 + 0.3).requires_grad_(True)
     gamma = (torch.rand(c, device=DEV) + 0.5).requires_grad_(True)

@@ -316,3 +316,48 @@ def test_fp32_restoration_gradients():
         log(f"[fp32 mse-grad] {name:50s} cuda-vs-fp32 {e_cuda:.3e}  tf32-emulation-vs-fp32 {e_emu:.3e}")
         assert e_cuda <= 1.35 * e_emu + 0.01, (name, e_cuda, e_emu)
     log(f"[fp32 mse-grad] worst ratio to the TF32-operand floor {worst_ratio:.2f}")
+
+
+# BASELINE configs[3]: 128x128x64 crops (the large-volume regime; local views 32^3 keep the 1/32
+# voxel ratio).  Parity-test case, not a bench line.
+_LARGE = {}
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_large_volume_128x128x64(precision):
+    m, sd0 = build("bn", precision=precision)
+    x1, _, gt, lv = orc.synthetic_batch(2, seed=11, vol=(128, 128, 64), local=(32, 32, 32), n_local=1)
+    if "ref" not in _LARGE:          # the CPU oracle at this size takes ~30 s: once for both precisions
+        sd = orc.clone_state(sd0)
+        keys = [k for k in sd if orc.is_param(k)]
+        for k in keys:
+            sd[k].requires_grad_(True)
+        o_out, _, o_masks = orc.forward(sd, x1, False, True)
+        o_loss = torch.nn.functional.mse_loss(o_out, gt) + torch.nn.functional.mse_loss(o_masks[1], gt)
+        og = dict(zip(keys, torch.autograd.grad(o_loss, [sd[k] for k in keys], allow_unused=True)))
+        _LARGE["ref"] = (o_out.detach(), [t.detach() for t in o_masks], o_loss.detach(), og)
+    o_out, o_masks, o_loss, og = _LARGE["ref"]
+    out, feats, masks = m(x1.cuda())
+    errs = {"out": rl2(out, o_out)}
+    for s_ in range(3):
+        errs[f"mask{s_}"] = rl2(masks[s_], o_masks[s_])
+    log(f"[128x128x64 {precision}] " + " ".join(f"{k}={v:.3e}" for k, v in errs.items()))
+    tol = 3e-2 if precision == "bf16" else 4e-3
+    assert max(errs.values()) < tol, errs
+    loss = torch.nn.functional.mse_loss(out, gt.cuda()) + torch.nn.functional.mse_loss(masks[1], gt.cuda())
+    loss.backward()
+    log(f"[128x128x64 {precision}] loss {loss.item():.6f} vs {o_loss.item():.6f}")
+    assert abs(loss.item() - o_loss.item()) < (2e-3 if precision == "bf16" else 2e-5)
+    # the decoder's directly supervised tensors (well conditioned at any size)
+    for name in ("out_tr.final_conv.weight", "up_tr64.ops.1.conv1.weight", "up_tr128.deep_supervision_head.conv1.weight"):
+        e = rl2(dict(m.named_parameters())[name].grad, og[name])
+        log(f"[128x128x64 {precision}] {name} grad rel-L2 {e:.3e}")
+        assert e < (0.1 if precision == "bf16" else 2e-2), (name, e)
+    # local views of 32^3 through the local path
+    with torch.no_grad():
+        lout, lfeats, lmasks = m(lv[0].cuda(), local=True)
+        o_lout, o_lfeats, _ = orc.forward(orc.clone_state(sd0), lv[0], True, True)
+    assert lmasks == []
+    e = rl2(lout, o_lout)
+    log(f"[128x128x64 {precision}] local 32^3 out rel-L2 {e:.3e}")
+    assert e < tol
