@@ -20,6 +20,10 @@
 // dY chunk loaded `delta` merged rows earlier (dY[f - delta] * X[f + off_a] = tap off_a + delta), the X
 // slab is shared.  The nine groups become five CTA groups (the last one alone; its upper half is
 // not stored), i.e. 1.8x fewer tensor-pipe cycles on the 64-channel layers.
+// NPAIR mode (fp32 operands, 64-channel X chunk = two 32-channel smem chunks, so the dx taps cannot be
+// stacked along N and a lone N = 64 MMA costs as much as N = 128): the N = 128 operand is the X chunk
+// of TWO (dz,dy) groups, loaded as two slabs.  With PAIR on top ("quad") one MMA chain covers four
+// groups {xg0, xg0+delta, xg1, xg1+delta}; the nine groups take 3 CTA groups instead of 5 (4+3+2 used).
 // Grid order: blockIdx.x = (dz,dy) group fastest, then the (Cout, Cin) chunk pair; blockIdx.y = the
 // reduction split.  CTAs that run at the same time therefore read the SAME K-stages (L2 hits instead
 // of nine DRAM passes over X and dY).
@@ -60,7 +64,10 @@ struct WgradParams {
   int stack_dx;                          // CONV: one MMA of N = 3*nc covers the three dx taps
   int m_chunks_total;                    // Cout / mch
   int pair;                              // CONV: two (dz,dy) groups per CTA stacked along M (see header)
-  int ngroups;                           // CTA groups over (dz,dy): 9, 5 in PAIR mode, 1 in PLAIN mode
+  int ngroups;                           // CTA groups over (dz,dy): 9, 5 in PAIR or NPAIR mode, 3 in both, 1 in PLAIN mode
+  int npair;                             // CONV: two X groups stacked along N (see header)
+  int b_views;                           // X slabs per stage: 2 in NPAIR mode, else 1
+  int ncm;                               // MMA N without dx stacking: nc * b_views
   int mch;                               // dW rows (output channels) per m-chunk: mc, or 64 in PAIR mode
   int cout, cin;                         // leading dims of dW: [tap][cout][cin]
   long long rows_total;
@@ -74,7 +81,7 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int a_stage_bytes = p.a_chunks * p.a_chunk_bytes;
-  const int b_stage_bytes = p.b_chunks * p.b_chunk_bytes;
+  const int b_stage_bytes = p.b_chunks * p.b_views * p.b_chunk_bytes;
   const int stage_bytes = a_stage_bytes + b_stage_bytes;
   uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full = bars;
@@ -86,11 +93,29 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
   const int kchunk = blockIdx.y;
   // (dz,dy) group(s) of this CTA in CONV mode: ga for M rows 0..63 (all rows without PAIR), gb for 64..127
   const int gidx = (int)blockIdx.x % p.ngroups, mn = (int)blockIdx.x / p.ngroups;
-  const int ga = p.pair ? 2 * gidx : gidx;
-  const int gb = p.pair ? min(ga + 1, 8) : ga;
   const int mchunk = mn % p.m_chunks_total, nchunk = mn / p.m_chunks_total;
-  const int dzo = ga / 3 - 1, dyo = ga % 3 - 1;
-  const int delta = (gb / 3 - ga / 3) * p.H1 + (gb % 3 - ga % 3);   // merged rows the second dY view lags
+  // xg[u]: group the X slab u is positioned for; delta: merged rows the second dY view lags;
+  // tapg[v][u]: (dz,dy) group (0..8) accumulator block (dY view v, X slab u) holds, -1 = unused
+  int xg[2], delta = 0, tapg[2][2] = {{-1, -1}, {-1, -1}};
+  if (p.pair && p.npair) {
+    if (gidx == 0) { xg[0] = 0; xg[1] = 3; delta = 1; tapg[0][0] = 0; tapg[1][0] = 1; tapg[0][1] = 3; tapg[1][1] = 4; }
+    else if (gidx == 1) { xg[0] = 6; xg[1] = 2; delta = 1; tapg[0][0] = 6; tapg[1][0] = 7; tapg[0][1] = 2; }
+    else { xg[0] = 5; xg[1] = 8; tapg[0][0] = 5; tapg[0][1] = 8; }
+  } else if (p.pair) {
+    const int ga = 2 * gidx, gb = min(ga + 1, 8);
+    xg[0] = xg[1] = ga;
+    delta = (gb / 3 - ga / 3) * p.H1 + (gb % 3 - ga % 3);
+    tapg[0][0] = ga;
+    if (gb != ga) tapg[1][0] = gb;
+  } else if (p.npair) {
+    xg[0] = 2 * gidx; xg[1] = min(xg[0] + 1, 8);
+    tapg[0][0] = xg[0];
+    if (xg[1] != xg[0]) tapg[0][1] = xg[1];
+  } else {
+    xg[0] = xg[1] = gidx;
+    tapg[0][0] = gidx;
+  }
+  const int dzo = xg[0] / 3 - 1;
 
   // zero all stage buffers once: tails beyond what TMA writes must be finite (dY tails: zero)
   {
@@ -122,7 +147,7 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     // producer: the whole warp loops (operands stay warp-uniform), one elected lane issues
     int st = 0, ph = 0;
     const uint32_t tx = (uint32_t)(p.a_chunks * p.kr * p.a_row_bytes +
-                                   p.b_chunks * p.b_box_rows * p.b_row_bytes);
+                                   p.b_chunks * p.b_views * p.b_box_rows * p.b_row_bytes);
     for (int s = s_begin; s < s_end; s++) {
       mbar_wait(&empty[st], ph ^ 1);
       uint8_t* a_dst = smem + (size_t)st * stage_bytes;
@@ -144,9 +169,12 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
             tma_load_4d(a_dst + (size_t)c * p.a_chunk_bytes, &ta, &full[st],
                         mchunk * p.mch + cc * p.chunk_ch, -1, mr0 - view * delta, n);
           }
-          for (int c = 0; c < p.b_chunks; c++)
-            tma_load_4d(b_dst + (size_t)c * p.b_chunk_bytes, &tb, &full[st],
-                        nchunk * p.nc + c * p.chunk_ch, -1, mr0 + dzo * p.H1 + dyo, n);
+          for (int u = 0; u < p.b_views; u++) {
+            const int xoff = (xg[u] / 3 - 1) * p.H1 + (xg[u] % 3 - 1);
+            for (int c = 0; c < p.b_chunks; c++)
+              tma_load_4d(b_dst + (size_t)(u * p.b_chunks + c) * p.b_chunk_bytes, &tb, &full[st],
+                          nchunk * p.nc + c * p.chunk_ch, -1, mr0 + xoff, n);
+          }
         } else {
           const int r0 = s * p.nrows;
           for (int c = 0; c < p.a_chunks; c++)
@@ -161,7 +189,7 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
   } else if (warp == 1) {
     int st = 0, ph = 0;
     const uint32_t fmt = TF32 ? 2u : 1u;
-    const uint32_t idesc = make_idesc(fmt, (uint32_t)p.mc, (uint32_t)p.nc, 1, 1);
+    const uint32_t idesc = make_idesc(fmt, (uint32_t)p.mc, (uint32_t)p.ncm, 1, 1);
     // MN-major layouts: 16-bit operands use the 128B/64B swizzle (K atom = 8 rows); fp32 (tf32)
     // operands need the 32-byte-atom variant (K atom = 4 rows) -- profiles/r01_umma_probe.md
     const uint32_t a_lay = TF32 ? LAYOUT_SW128_B32 : (p.a_row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64);
@@ -176,7 +204,7 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     // several (tools/umma_probe: N = 128, 1554 vs 2026 TFLOP/s), so consecutive MMAs never share one:
     // the three dx taps are interleaved inside the k-step loop, and where TMEM has room (nacc = 2)
     // even / odd k-steps use two accumulator sets that the epilogue adds.
-    const uint32_t set_cols = (uint32_t)(p.ntaps * p.nc);
+    const uint32_t set_cols = (uint32_t)(p.ntaps * p.ncm);
     const uint32_t b_row16 = (uint32_t)p.b_row_bytes >> 4;
     uint32_t kq = 0;                                  // k-steps issued so far by this CTA
     for (int s = s_begin; s < s_end; s++) {
@@ -205,8 +233,8 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
             const uint32_t d = tmem + (kq & (uint32_t)(p.nacc - 1)) * set_cols;
             const uint32_t acc = kq >= (uint32_t)p.nacc ? 1u : 0u;
             umma_any<TF32>(d, ad, bd, idesc, acc);
-            umma_any<TF32>(d + (uint32_t)p.nc, ad, bd + b_row16, idesc, acc);
-            umma_any<TF32>(d + 2u * (uint32_t)p.nc, ad, bd + 2u * b_row16, idesc, acc);
+            umma_any<TF32>(d + (uint32_t)p.ncm, ad, bd + b_row16, idesc, acc);
+            umma_any<TF32>(d + 2u * (uint32_t)p.ncm, ad, bd + 2u * b_row16, idesc, acc);
             ad += a_step;
             bd += b_step;
           }
@@ -241,30 +269,33 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
     else { row = warp * 16 + lane; row_ok = lane < 16; }
     // the second accumulator set exists only if this CTA issued at least two k-steps
     const bool two_sets = p.nacc == 2 && (long long)(s_end - s_begin) * p.ksteps >= 2;
-    int g = ga, orow = row;
-    if (p.pair) {
-      if (row >= 64) { g = gb; orow = row - 64; row_ok = gb != ga; }
-    }
+    const int vw = (p.pair && row >= 64) ? 1 : 0;        // dY view of this row (warp-uniform)
+    const int orow = p.pair ? (row & 63) : row;
     for (int t = 0; t < p.ntaps; t++) {
-      const int tap = (p.mode == WG_CONV) ? g * 3 + t : 0;
-      float* dst = p.dw + ((size_t)tap * p.cout + (size_t)mchunk * p.mch + orow) * p.cin +
-                   (size_t)nchunk * p.nc;
-      for (int c = 0; c < p.nc; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + t * p.nc + c, v);
-        tmem_ld_wait();
-        if (two_sets) {
-          uint32_t v2[32];
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + p.ntaps * p.nc + t * p.nc + c, v2);
+      for (int u = 0; u < p.b_views; u++) {
+        const int g = (p.mode == WG_CONV) ? tapg[vw][u] : 0;
+        if (g < 0) continue;                               // unused block of a PAIR / NPAIR chain
+        const int tap = (p.mode == WG_CONV) ? g * 3 + t : 0;
+        float* dst = p.dw + ((size_t)tap * p.cout + (size_t)mchunk * p.mch + orow) * p.cin +
+                     (size_t)nchunk * p.nc;
+        for (int c = 0; c < p.nc; c += 32) {
+          const uint32_t col = (uint32_t)(t * p.ncm + u * p.nc + c);
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + col, v);
           tmem_ld_wait();
+          if (two_sets) {
+            uint32_t v2[32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(p.ntaps * p.ncm) + col, v2);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
-        }
-        if (row_ok) {
+            for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+          }
+          if (row_ok) {
 #pragma unroll
-          for (int i = 0; i < 8; i++)
-            red_add_v4(dst + c + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                       __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            for (int i = 0; i < 8; i++)
+              red_add_v4(dst + c + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          }
         }
       }
     }
@@ -276,13 +307,14 @@ igemm_mnmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_consta
 
 static int launch_wgrad(WgradParams& p, const CUtensorMap& ta, const CUtensorMap& tb, dim3 grid,
                         cudaStream_t stream) {
-  const int stage_bytes = p.a_chunks * p.a_chunk_bytes + p.b_chunks * p.b_chunk_bytes;
+  if (p.b_views < 1) { p.b_views = 1; p.ncm = p.nc; }
+  const int stage_bytes = p.a_chunks * p.a_chunk_bytes + p.b_chunks * p.b_views * p.b_chunk_bytes;
   p.stages = 3;
   while (p.stages > 2 && (size_t)p.stages * stage_bytes > 200 * 1024) p.stages--;
   if ((size_t)p.stages * stage_bytes > 210 * 1024)
     return fail(PCRL_ERR_ARG, "wgrad: stage of %d bytes does not fit shared memory", stage_bytes);
-  p.nacc = (2 * p.ntaps * p.nc <= 512 && !getenv("PCRL_WGRAD_NACC1")) ? 2 : 1;
-  int cols = p.nacc * p.ntaps * p.nc, t = 32;
+  p.nacc = (2 * p.ntaps * p.ncm <= 512 && !getenv("PCRL_WGRAD_NACC1")) ? 2 : 1;
+  int cols = p.nacc * p.ntaps * p.ncm, t = 32;
   while (t < cols) t <<= 1;
   p.tmem_cols = t;
   const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
@@ -324,6 +356,9 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   p.a_row_bytes = 128; p.a_chunks = p.mc / p.chunk_ch;
   if (!tf32 && p.nc == 32) { p.b_row_bytes = 64; p.b_chunks = 1; }
   else { p.b_row_bytes = 128; p.b_chunks = p.nc / p.chunk_ch; }
+  p.npair = (tf32 && p.nc == 64 && p.b_chunks == 2 && !getenv("PCRL_WGRAD_NONPAIR")) ? 1 : 0;
+  p.b_views = p.npair ? 2 : 1;
+  p.ncm = p.nc * p.b_views;
   // merged rows per stage: start from ~128 reduction rows (64 for fp32 operands) and shrink until
   // three stages fit in shared memory (latency hiding needs the depth more than the stage size);
   // if even one merged row per stage does not allow three, take the largest two-stage tiling
@@ -339,7 +374,7 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
       const int ab = round_up((ks * p.krows + 1) * p.a_row_bytes, 1024);
       const int bb = round_up((ks * p.krows + 3) * p.b_row_bytes, 1024);
       const bool padded_ok = want == 2 || 100 * ks * p.krows <= 115 * nr * p.Wp;   // <= 15 % zero rows
-      if (padded_ok && (size_t)want * (p.a_chunks * ab + p.b_chunks * bb) <= 200 * 1024) { chosen = nr; break; }
+      if (padded_ok && (size_t)want * (p.a_chunks * ab + p.b_chunks * p.b_views * bb) <= 200 * 1024) { chosen = nr; break; }
       if (want == 3 && 2 * nr <= nrows0) break;       // do not shrink the stage below half the target
     }
   }
@@ -349,11 +384,11 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   p.ksteps = (p.kr + p.krows - 1) / p.krows;
   // PAIR: the second dY view lags by up to H1 - 2 merged rows (groups (dz=-1,dy=+1) | (dz=0,dy=-1)),
   // so the reduction range is extended by that much (rows outside the sample are TMA zero fill)
-  const int k_extra = p.pair ? (p.H1 - 2 > 1 ? p.H1 - 2 : 1) : 0;
+  const int k_extra = p.pair ? (p.npair ? 1 : (p.H1 - 2 > 1 ? p.H1 - 2 : 1)) : 0;
   p.stages_per_sample = (p.MR + k_extra + p.nrows - 1) / p.nrows;
   p.total_stages = p.stages_per_sample * N;
   // (measured on B200: +3 % with fp32 operands, where the unrotated working set overflows L2; -2 % with bf16)
-  p.rot_stages = (tf32 && Cin >= Cout && !getenv("PCRL_WGRAD_NOROT")) ? p.H1 / p.nrows : 0;
+  p.rot_stages = (tf32 && Cin >= Cout && !p.npair && !getenv("PCRL_WGRAD_NOROT")) ? p.H1 / p.nrows : 0;
   if (p.rot_stages >= p.total_stages) p.rot_stages = 0;
   p.a_chunk_bytes = round_up((p.ksteps * p.krows + 1) * p.a_row_bytes, 1024);
   p.b_box_rows = p.nrows * p.Wp;
@@ -363,7 +398,7 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   p.m_chunks_total = Cout / p.mch;
   p.cout = Cout; p.cin = Cin; p.dw = dw;
   // split the reduction so that the grid has a few waves
-  p.ngroups = p.pair ? 5 : 9;
+  p.ngroups = (p.pair && p.npair) ? 3 : ((p.pair || p.npair) ? 5 : 9);
   const int other = p.ngroups * (Cout / p.mch) * (Cin / p.nc);
   int kchunks = (4 * num_sms() + other - 1) / other;
   if (kchunks > p.total_stages) kchunks = p.total_stages;

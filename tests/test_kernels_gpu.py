@@ -32,6 +32,8 @@ CONV_SHAPES = [
     (2, 8, 12, 32, 64, 64),
     (1, 4, 4, 4, 512, 256),
     (1, 6, 10, 16, 128, 64),
+    (1, 4, 6, 8, 64, 128),
+    (2, 5, 3, 7, 64, 64),
 ]
 
 
