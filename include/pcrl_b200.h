@@ -154,6 +154,46 @@ int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long 
 int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, int dtype,
                  void* stream);
 
+/* ---- projection / prediction heads and loss terms (small fp32 tensors) --------------------- */
+/* nn.BatchNorm1d over the rows of x [B][C] (UpTransition.bn, predictor_head[1];
+ * models/pcrlv2_model_3d.py:54,56,67,69), optionally followed by ReLU (predictor_head[2], :57).
+ * training: batch statistics (biased variance), running_mean / running_var / num_batches_tracked
+ * updated as torch does (momentum, unbiased variance); eval: running statistics.
+ * save_mean / save_invstd [C] are written for the backward pass. */
+int pcrl_bn1d_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
+                  float* running_var, long long* num_batches_tracked, float* y, float* save_mean,
+                  float* save_invstd, int B, int C, int relu, int training, float momentum, float eps,
+                  void* stream);
+/* autograd of the above: dx [B][C], dgamma [C], dbeta [C]; y = forward output (ReLU mask) */
+int pcrl_bn1d_bwd(const float* x, const float* y, const float* dy, const float* gamma,
+                  const float* save_mean, const float* save_invstd, float* dx, float* dgamma,
+                  float* dbeta, int B, int C, int relu, int training, void* stream);
+/* nn.Linear (predictor_head[0], [3]; :55,58,69): y [B][J] = x [B][K] * w [J][K]^T + bias [J] */
+int pcrl_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int K, int J,
+                    void* stream);
+/* its autograd: dx [B][K] = dy * w, dw [J][K] = dy^T * x, dbias [J] = column sums (each may be NULL) */
+int pcrl_linear_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw,
+                    float* dbias, int B, int K, int J, void* stream);
+/* nn.CosineSimilarity(dim=1)(x, y).mean() of train_3d.py:90-91 with y detached, forward and
+ * gradient in one launch: *mean_out += coef * mean_b cos(x_b, y_b);
+ * dx [B][C] = coef * d(mean cos)/dx (dx may be NULL). */
+int pcrl_cosine_mean_fwd_bwd(const float* x, const float* y, float* mean_out, float* dx, int B, int C,
+                             float eps, float coef, void* stream);
+/* nn.MSELoss() of train_3d.py:135,137: *out += mean((p - t)^2) over n elements */
+int pcrl_mse_fwd(const float* p, const float* t, float* out, long long n, void* stream);
+/* dp = g[0] * 2 (p - t) / n, g = upstream gradient (device scalar) */
+int pcrl_mse_bwd(const float* p, const float* t, const float* g, float* dp, long long n, void* stream);
+/* torch.sigmoid of the 1-channel output volume (models/pcrlv2_model_3d.py:79,132) and its autograd */
+int pcrl_sigmoid_fwd(const float* x, float* y, long long n, void* stream);
+int pcrl_sigmoid_bwd(const float* y, const float* dy, float* dx, long long n, void* stream);
+/* F.interpolate(scale_factor=sf, mode='trilinear') of a 1-channel volume x [N][D][H][W] -> y
+ * [N][D*sf][H*sf][W*sf] (deep-supervision masks, models/pcrlv2_model_3d.py:125-126); the backward
+ * scatters dy into dx, which must be zero on entry */
+int pcrl_upsample_trilinear_fwd(const float* x, float* y, int N, int D, int H, int W, int sf,
+                                void* stream);
+int pcrl_upsample_trilinear_bwd(const float* dy, float* dx, int N, int D, int H, int W, int sf,
+                                void* stream);
+
 /* ---- optimizer: torch.optim.SGD(momentum, weight_decay), train_3d.py:48-51,151 ------------- */
 int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf,
                   const long long* seg_offsets, const int* seg_active, const int* seg_first,

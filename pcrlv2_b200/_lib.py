@@ -51,6 +51,17 @@ SIGNATURES = {
     "pcrl_gemm_nt": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P],
     "pcrl_gemm_tn": [_P, _P, _P, _L, _I, _I, _I, _P],
     "pcrl_sgd_flat": [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _P],
+    "pcrl_bn1d_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
+    "pcrl_bn1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pcrl_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "pcrl_linear_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "pcrl_cosine_mean_fwd_bwd": [_P, _P, _P, _P, _I, _I, _F, _F, _P],
+    "pcrl_mse_fwd": [_P, _P, _P, _L, _P],
+    "pcrl_mse_bwd": [_P, _P, _P, _P, _L, _P],
+    "pcrl_sigmoid_fwd": [_P, _P, _L, _P],
+    "pcrl_sigmoid_bwd": [_P, _P, _P, _L, _P],
+    "pcrl_upsample_trilinear_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_upsample_trilinear_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
 }
 
 _lib = None
@@ -100,7 +111,8 @@ def _conv(a):
 
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches count)
-LAUNCHES = {"pcrl_convT3d_k2s2_fprop": 2, "pcrl_convT3d_k2s2_bwd": 3, "pcrl_conv3d_k3_dgrad_unshuffled": 2}
+LAUNCHES = {"pcrl_convT3d_k2s2_fprop": 2, "pcrl_convT3d_k2s2_bwd": 3, "pcrl_conv3d_k3_dgrad_unshuffled": 2,
+            "pcrl_linear_bwd": 3}
 launch_count = [0]
 # when set to a list, every call is bracketed by CUDA events on the launching stream and
 # (name, int-args, start, end) is appended -- bench.py uses this for the per-kernel roofline

@@ -44,6 +44,18 @@ int im2col27(const float*, void*, int, int, int, int, int, cudaStream_t);
 int chan1_sigmoid_fwd(const float*, const float*, const float*, float*, int, int, long long, cudaStream_t);
 int chan1_sigmoid_bwd(const float*, const float*, const float*, const float*, const float*, const float*, double*, float*, double, int, int, int, long long, cudaStream_t);
 int sgd_flat(float*, const float*, float*, const long long*, const int*, const int*, int, float, float, float, float, cudaStream_t);
+// losses.cu
+int bn1d_fwd(const float*, const float*, const float*, float*, float*, long long*, float*, float*, float*, int, int, int, int, float, float, cudaStream_t);
+int bn1d_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, cudaStream_t);
+int linear_fwd(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+int linear_bwd(const float*, const float*, const float*, float*, float*, float*, int, int, int, cudaStream_t);
+int cosine_mean_fwd_bwd(const float*, const float*, float*, float*, int, int, float, float, cudaStream_t);
+int mse_fwd(const float*, const float*, float*, long long, cudaStream_t);
+int mse_bwd(const float*, const float*, const float*, float*, long long, cudaStream_t);
+int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
+int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
+int upsample_trilinear_fwd(const float*, float*, int, int, int, int, int, cudaStream_t);
+int upsample_trilinear_bwd(const float*, float*, int, int, int, int, int, cudaStream_t);
 
 }  // namespace pcrl
 
@@ -54,7 +66,7 @@ using namespace pcrl;
 extern "C" {
 
 const char* pcrl_last_error(void) { return last_error_buf(); }
-int pcrl_version(void) { return 101; }
+int pcrl_version(void) { return 102; }
 static inline int esz(int dtype) { return dtype == PCRL_DTYPE_F32 ? 4 : 2; }
 #define CHECK_DTYPE(d) PCRL_REQUIRE((d) == PCRL_DTYPE_BF16 || (d) == PCRL_DTYPE_F32, "%s: unknown dtype %d", __func__, (d))
 
@@ -215,6 +227,58 @@ int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long 
 int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, int dtype, void* stream) {
   NONNULL(a); NONNULL(b); NONNULL(c); CHECK_DTYPE(dtype);
   return gemm_tn_igemm(a, b, c, rows, P, Q, ST(stream), dtype);
+}
+
+int pcrl_bn1d_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                  long long* num_batches_tracked, float* y, float* save_mean, float* save_invstd, int B, int C,
+                  int relu, int training, float momentum, float eps, void* stream) {
+  NONNULL(x); NONNULL(gamma); NONNULL(beta); NONNULL(y); NONNULL(save_mean); NONNULL(save_invstd);
+  return bn1d_fwd(x, gamma, beta, running_mean, running_var, num_batches_tracked, y, save_mean, save_invstd, B, C,
+                  relu, training, momentum, eps, ST(stream));
+}
+int pcrl_bn1d_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+                  const float* save_invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int relu,
+                  int training, void* stream) {
+  NONNULL(x); NONNULL(dy); NONNULL(gamma); NONNULL(save_mean); NONNULL(save_invstd); NONNULL(dx); NONNULL(dgamma); NONNULL(dbeta);
+  return bn1d_bwd(x, y, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, B, C, relu, training, ST(stream));
+}
+int pcrl_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int K, int J, void* stream) {
+  NONNULL(x); NONNULL(w); NONNULL(y);
+  return linear_fwd(x, w, bias, y, B, K, J, ST(stream));
+}
+int pcrl_linear_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias, int B,
+                    int K, int J, void* stream) {
+  NONNULL(x); NONNULL(w); NONNULL(dy);
+  return linear_bwd(x, w, dy, dx, dw, dbias, B, K, J, ST(stream));
+}
+int pcrl_cosine_mean_fwd_bwd(const float* x, const float* y, float* mean_out, float* dx, int B, int C, float eps,
+                             float coef, void* stream) {
+  NONNULL(x); NONNULL(y); NONNULL(mean_out);
+  return cosine_mean_fwd_bwd(x, y, mean_out, dx, B, C, eps, coef, ST(stream));
+}
+int pcrl_mse_fwd(const float* p, const float* t, float* out, long long n, void* stream) {
+  NONNULL(p); NONNULL(t); NONNULL(out);
+  return mse_fwd(p, t, out, n, ST(stream));
+}
+int pcrl_mse_bwd(const float* p, const float* t, const float* g, float* dp, long long n, void* stream) {
+  NONNULL(p); NONNULL(t); NONNULL(g); NONNULL(dp);
+  return mse_bwd(p, t, g, dp, n, ST(stream));
+}
+int pcrl_sigmoid_fwd(const float* x, float* y, long long n, void* stream) {
+  NONNULL(x); NONNULL(y);
+  return sigmoid_fwd(x, y, n, ST(stream));
+}
+int pcrl_sigmoid_bwd(const float* y, const float* dy, float* dx, long long n, void* stream) {
+  NONNULL(y); NONNULL(dy); NONNULL(dx);
+  return sigmoid_bwd(y, dy, dx, n, ST(stream));
+}
+int pcrl_upsample_trilinear_fwd(const float* x, float* y, int N, int D, int H, int W, int sf, void* stream) {
+  NONNULL(x); NONNULL(y);
+  return upsample_trilinear_fwd(x, y, N, D, H, W, sf, ST(stream));
+}
+int pcrl_upsample_trilinear_bwd(const float* dy, float* dx, int N, int D, int H, int W, int sf, void* stream) {
+  NONNULL(dy); NONNULL(dx);
+  return upsample_trilinear_bwd(dy, dx, N, D, H, W, sf, ST(stream));
 }
 
 int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf, const long long* seg_offsets,

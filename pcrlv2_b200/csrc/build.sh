@@ -7,12 +7,12 @@ BUILD=${PCRL_BUILD_DIR:-build}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --use_fast_math -Xptxas -v $PCRL_EXTRA_FLAGS"
 mkdir -p $BUILD
 pids=()
-for f in api igemm_kmajor igemm_mnmajor streaming heads; do
+for f in api igemm_kmajor igemm_mnmajor streaming heads losses; do
   if [ ! -f $BUILD/$f.o ] || [ $f.cu -nt $BUILD/$f.o ] || [ sm100.cuh -nt $BUILD/$f.o ] || [ common.cuh -nt $BUILD/$f.o ]; then
     nvcc $FLAGS -c $f.cu -o $BUILD/$f.o > $BUILD/$f.log 2>&1 &
     pids+=($!)
   fi
 done
 for p in "${pids[@]}"; do wait $p || { cat $BUILD/*.log | grep -E "error|Error" ; exit 1; }; done
-nvcc -shared -o $OUT $BUILD/api.o $BUILD/igemm_kmajor.o $BUILD/igemm_mnmajor.o $BUILD/streaming.o $BUILD/heads.o -lcudart
+nvcc -shared -o $OUT $BUILD/api.o $BUILD/igemm_kmajor.o $BUILD/igemm_mnmajor.o $BUILD/streaming.o $BUILD/heads.o $BUILD/losses.o -lcudart
 echo "built $(realpath $OUT)"

@@ -338,3 +338,96 @@ def sgd_flat(params, grads, bufs, seg_off, seg_active, seg_first, lr, momentum, 
     nseg = seg_active.numel()
     _lib.call("pcrl_sgd_flat", params, grads, bufs, seg_off, seg_active, seg_first, nseg, float(lr),
               float(momentum), float(weight_decay), float(grad_scale))
+
+
+# ------------------------------------------------------------------------------ heads / losses (fp32)
+def _f32c(t):
+    assert t.dtype == torch.float32 and t.is_contiguous(), "expected a contiguous fp32 tensor"
+    return t
+
+
+def bn1d_fwd(x, gamma, beta, running_mean, running_var, nbt, relu, training, momentum=0.1, eps=1e-5):
+    """BatchNorm1d over the rows of x (B, C) [+ ReLU]; returns (y, save_mean, save_invstd)."""
+    b, c = x.shape
+    y = torch.empty_like(_f32c(x))
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    _lib.call("pcrl_bn1d_fwd", x, _f32c(gamma), _f32c(beta), running_mean, running_var, nbt, y, mean, invstd,
+              b, c, int(relu), int(training), float(momentum), float(eps))
+    return y, mean, invstd
+
+
+def bn1d_bwd(x, y, dy, gamma, mean, invstd, relu, training):
+    b, c = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    _lib.call("pcrl_bn1d_bwd", x, y, _f32c(dy), gamma, mean, invstd, dx, dgamma, dbeta, b, c, int(relu), int(training))
+    return dx, dgamma, dbeta
+
+
+def linear_fwd(x, w, bias):
+    b, k = x.shape
+    j = w.shape[0]
+    y = torch.empty((b, j), dtype=torch.float32, device=x.device)
+    _lib.call("pcrl_linear_fwd", _f32c(x), _f32c(w), bias, y, b, k, j)
+    return y
+
+
+def linear_bwd(x, w, dy, need_dx=True):
+    b, k = x.shape
+    j = w.shape[0]
+    dx = torch.empty((b, k), dtype=torch.float32, device=x.device) if need_dx else None
+    dw = torch.empty((j, k), dtype=torch.float32, device=x.device)
+    db = torch.empty((j,), dtype=torch.float32, device=x.device)
+    _lib.call("pcrl_linear_bwd", x, w, _f32c(dy), dx, dw, db, b, k, j)
+    return dx, dw, db
+
+
+def cosine_mean_fwd_bwd(x, y, eps=1e-8, coef=1.0, need_dx=True):
+    """coef * mean_b cos(x_b, y_b) (0-dim tensor) and its gradient wrt x."""
+    b, c = x.shape
+    out = torch.zeros((), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x) if need_dx else None
+    _lib.call("pcrl_cosine_mean_fwd_bwd", _f32c(x), _f32c(y), out, dx, b, c, float(eps), float(coef))
+    return out, dx
+
+
+def mse_fwd(p, t):
+    out = torch.zeros((), dtype=torch.float32, device=p.device)
+    _lib.call("pcrl_mse_fwd", _f32c(p), _f32c(t), out, p.numel())
+    return out
+
+
+def mse_bwd(p, t, g):
+    dp = torch.empty_like(p)
+    _lib.call("pcrl_mse_bwd", p, t, _f32c(g), dp, p.numel())
+    return dp
+
+
+def sigmoid_fwd(x):
+    y = torch.empty_like(_f32c(x))
+    _lib.call("pcrl_sigmoid_fwd", x, y, x.numel())
+    return y
+
+
+def sigmoid_bwd(y, dy):
+    dx = torch.empty_like(y)
+    _lib.call("pcrl_sigmoid_bwd", y, _f32c(dy), dx, y.numel())
+    return dx
+
+
+def upsample_trilinear_fwd(x, sf):
+    """x (N,1,D,H,W) fp32 -> (N,1,D*sf,H*sf,W*sf)."""
+    n, _, d, h, w = x.shape
+    y = torch.empty((n, 1, d * sf, h * sf, w * sf), dtype=torch.float32, device=x.device)
+    _lib.call("pcrl_upsample_trilinear_fwd", _f32c(x), y, n, d, h, w, int(sf))
+    return y
+
+
+def upsample_trilinear_bwd(dy, sf):
+    n, _, od, oh, ow = dy.shape
+    d, h, w = od // sf, oh // sf, ow // sf
+    dx = torch.zeros((n, 1, d, h, w), dtype=torch.float32, device=dy.device)
+    _lib.call("pcrl_upsample_trilinear_bwd", _f32c(dy), dx, n, d, h, w, int(sf))
+    return dx

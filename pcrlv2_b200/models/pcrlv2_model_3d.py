@@ -23,8 +23,8 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
+from .. import functional as Fn
 from .. import kernels as K
 
 # bumped by pcrlv2_b200.train_3d.FlatSGD after every in-place parameter update made through raw
@@ -350,8 +350,11 @@ class UpTransition(nn.Module):
         outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final, dtype=dtype)
         a, avg, y1, st1 = outs[0], outs[1], outs[2], outs[3]
         y0 = outs[4] if final is not None else None
-        x_pro = self.bn(avg)
-        x_pre = self.predictor_head(x_pro)
+        # projection (BatchNorm1d) and prediction (Linear-BN-ReLU-Linear) heads, reference :54-58,67-69:
+        # the nn modules hold the parameters / running statistics, csrc/losses.cu does the arithmetic
+        x_pro = Fn.batch_norm1d(avg, self.bn)
+        ph = self.predictor_head
+        x_pre = Fn.linear(Fn.batch_norm1d(Fn.linear(x_pro, ph[0]), ph[1], relu=True), ph[3])
         bn = self.deep_supervision_head.bn1
         mask = _Chan1NormSigmoidFn.apply(y1, bn.weight, bn.bias, st1, bn, self.norm, self.training)
         return a, x_pro, x_pre, mask, y0
@@ -408,9 +411,9 @@ class PCRLv23d(nn.Module):
         h, pro_64, pre_64, m64, y0 = self.up_tr64.run(h, final=self.out_tr.final_conv, dtype=dt)
         middle_masks = []
         if not local:
-            middle_masks.append(F.interpolate(m256, scale_factor=4, mode="trilinear"))
-            middle_masks.append(F.interpolate(m128, scale_factor=2, mode="trilinear"))
+            middle_masks.append(Fn.upsample_trilinear(m256, 4))
+            middle_masks.append(Fn.upsample_trilinear(m128, 2))
             middle_masks.append(m64)
         middle_features = [[pro_256, pre_256], [pro_128, pre_128], [pro_64, pre_64]]
-        out = torch.sigmoid(y0)
+        out = Fn.sigmoid(y0)
         return out, middle_features, middle_masks

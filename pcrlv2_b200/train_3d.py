@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from . import functional as Fn
 from . import kernels as K
 from .models import PCRLv23d
 from .models.pcrlv2_model_3d import bump_param_epoch
@@ -135,9 +136,27 @@ def cos_loss(cosine, output1, output2):
     index = random.randint(0, len(output1) - 1)
     sample1 = output1[index]
     sample2 = output2[index]
-    loss = -(cosine(sample1[1], sample2[0].detach()).mean() + cosine(sample2[1],
-                                                                     sample1[0].detach()).mean()) * 0.5
+    if _is_plain_cosine(cosine) and sample1[1].is_cuda and sample1[1].dim() == 2:
+        # nn.CosineSimilarity(dim=1): fused forward + gradient kernel (csrc/losses.cu), -1/2 folded in
+        loss = (Fn.cosine_mean(sample1[1], sample2[0], cosine.eps, -0.5) +
+                Fn.cosine_mean(sample2[1], sample1[0], cosine.eps, -0.5))
+    else:   # a caller-supplied similarity: evaluate it as the reference does
+        loss = -(cosine(sample1[1], sample2[0].detach()).mean() + cosine(sample2[1],
+                                                                         sample1[0].detach()).mean()) * 0.5
     return loss, index
+
+
+def _is_plain_cosine(cosine):
+    return type(cosine) is nn.CosineSimilarity and cosine.dim == 1
+
+
+def _mse(criterion, pred, target):
+    """criterion(pred, target); nn.MSELoss() (the reference's criterion, train_3d.py:56) runs on the
+    fused squared-error kernels."""
+    if type(criterion) is nn.MSELoss and criterion.reduction == "mean" and pred.is_cuda \
+            and pred.dtype == torch.float32 and pred.shape == target.shape:
+        return Fn.mse_loss(pred, target)
+    return criterion(pred, target)
 
 
 def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine):
@@ -158,9 +177,9 @@ def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine):
         local_loss += loss_local_1
         local_loss += loss_local_2
     local_loss = local_loss / (2 * len(local_views))
-    loss1 = criterion(mask1, gt)
+    loss1 = _mse(criterion, mask1, gt)
     beta = 0.5 * (1. + math.cos(math.pi * epoch / 240))
-    loss4 = beta * criterion(middle_masks1[index2], gt)
+    loss4 = beta * _mse(criterion, middle_masks1[index2], gt)
     loss = loss1 + loss2 + loss4 + local_loss
     return loss, loss1, loss2, local_loss
 

@@ -506,3 +506,117 @@ def test_heads_and_stem_fp32():
     dy = q32(torch.randn_like(ref))
     ref.backward(dy)
     assert rel(K.stem_conv_wgrad_gemm(K.pad_ndhwc(dy, F32), x), wt.grad) < TOL32
+
+
+# ------------------------------------------------------------------------------ heads / losses (csrc/losses.cu)
+@pytest.mark.parametrize("shape", [(32, 256), (192, 64), (2, 128), (7, 40)])
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn1d(shape, relu, training):
+    from pcrlv2_b200 import functional as Fn
+    b, c = shape
+    torch.manual_seed(30)
+    bn = torch.nn.BatchNorm1d(c).to(DEV)
+    ref = torch.nn.BatchNorm1d(c).to(DEV)
+    with torch.no_grad():
+        for m in (bn, ref):
+            m.weight.copy_(torch.linspace(0.5, 1.5, c))
+            m.bias.copy_(torch.linspace(-0.3, 0.3, c))
+            m.running_mean.copy_(torch.linspace(-0.1, 0.1, c))
+            m.running_var.copy_(torch.linspace(0.8, 1.2, c))
+    bn.train(training)
+    ref.train(training)
+    x = (torch.randn(b, c, device=DEV) * 1.5 + 0.2).requires_grad_(True)
+    x2 = x.detach().clone().requires_grad_(True)
+    y = Fn.batch_norm1d(x, bn, relu=relu)
+    y_ref = ref(x2)
+    if relu:
+        y_ref = torch.relu(y_ref)
+    assert rel(y, y_ref) < 1e-5
+    assert rel(bn.running_mean, ref.running_mean) < 1e-5 and rel(bn.running_var, ref.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
+    g = torch.randn_like(y_ref)
+    y.backward(g)
+    y_ref.backward(g)
+    assert rel(x.grad, x2.grad) < 2e-4
+    assert rel(bn.weight.grad, ref.weight.grad) < 1e-4 and rel(bn.bias.grad, ref.bias.grad) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(32, 256, 512), (192, 128, 64), (2, 64, 128), (5, 33, 70)])
+def test_linear(shape):
+    from pcrlv2_b200 import functional as Fn
+    b, k, j = shape
+    torch.manual_seed(31)
+    lin = torch.nn.Linear(k, j).to(DEV)
+    x = torch.randn(b, k, device=DEV, requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        y = Fn.linear(x, lin)
+        y_ref = F.linear(x2, lin.weight, lin.bias)
+        assert rel(y, y_ref) < 1e-5
+        g = torch.randn_like(y_ref)
+        y.backward(g)
+        gw, gb = lin.weight.grad.clone(), lin.bias.grad.clone()
+        lin.zero_grad()
+        y_ref.backward(g)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert rel(x.grad, x2.grad) < 1e-5
+    assert rel(gw, lin.weight.grad) < 1e-5 and rel(gb, lin.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(32, 256), (192, 64), (2, 128), (3, 50)])
+def test_cosine_mean(shape):
+    from pcrlv2_b200 import functional as Fn
+    b, c = shape
+    torch.manual_seed(32)
+    x = torch.randn(b, c, device=DEV, requires_grad=True)
+    yv = torch.randn(b, c, device=DEV, requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    out = Fn.cosine_mean(x, yv, 1e-8, -0.5)
+    ref = -0.5 * torch.nn.CosineSimilarity()(x2, yv.detach()).mean()
+    assert abs(out.item() - ref.item()) < 1e-6
+    (out * 3.0).backward()
+    (ref * 3.0).backward()
+    assert rel(x.grad, x2.grad) < 1e-5
+    assert yv.grad is None
+
+
+@pytest.mark.parametrize("n", [(2, 1, 64, 64, 32), (3, 1, 5, 7, 3), (1, 1, 16, 16, 16)])
+def test_mse_and_sigmoid(n):
+    from pcrlv2_b200 import functional as Fn
+    torch.manual_seed(33)
+    z = torch.randn(n, device=DEV, requires_grad=True)
+    z2 = z.detach().clone().requires_grad_(True)
+    t = torch.rand(n, device=DEV)
+    p = Fn.sigmoid(z)
+    loss = Fn.mse_loss(p, t)
+    p_ref = torch.sigmoid(z2)
+    loss_ref = torch.nn.MSELoss()(p_ref, t)
+    assert rel(p, p_ref) < 1e-6
+    assert abs(loss.item() - loss_ref.item()) < 1e-6 * max(1.0, abs(loss_ref.item()))
+    (loss * 0.7).backward()
+    (loss_ref * 0.7).backward()
+    assert rel(z.grad, z2.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape,sf", [((2, 1, 16, 16, 8), 4), ((2, 1, 32, 32, 16), 2), ((1, 1, 3, 5, 2), 2), ((3, 1, 4, 4, 4), 4)])
+def test_upsample_trilinear(shape, sf):
+    from pcrlv2_b200 import functional as Fn
+    torch.manual_seed(34)
+    x = torch.randn(shape, device=DEV, requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    y = Fn.upsample_trilinear(x, sf)
+    y_ref = F.interpolate(x2, scale_factor=sf, mode="trilinear")
+    assert y.shape == y_ref.shape
+    assert rel(y, y_ref) < 1e-6
+    g = torch.randn_like(y_ref)
+    y.backward(g)
+    y_ref.backward(g)
+    assert rel(x.grad, x2.grad) < 1e-5
+    # closed form of SURVEY 8c: trilinear x2 of [0,1,2,3] along one axis
+    ramp = torch.arange(4, dtype=torch.float32, device=DEV).view(1, 1, 1, 1, 4).expand(1, 1, 2, 2, 4).contiguous()
+    up = Fn.upsample_trilinear(ramp, 2)[0, 0, 0, 0]
+    assert torch.allclose(up, torch.tensor([0, .25, .75, 1.25, 1.75, 2.25, 2.75, 3], device=DEV))
