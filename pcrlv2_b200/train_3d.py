@@ -213,7 +213,7 @@ def train_pcrlv2_inner(args, epoch, train_loader, model, optimizer, criterion, c
         # ===================meters=====================
         mg_loss_meter.update(loss1.item(), bsz)
         loss_meter.update(loss2.item(), bsz)
-        prob_meter.update(float(local_loss), bsz)
+        prob_meter.update(local_loss.item() if torch.is_tensor(local_loss) else float(local_loss), bsz)
         torch.cuda.synchronize()
         batch_time.update(time.time() - end)
         end = time.time()
