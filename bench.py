@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+print_line = print   # main() swaps in a collector so that stdout carries only the JSON line
 METRIC = "LUNA 64x64x32 pretrain volumes/sec"
 UNIT = "volumes/s"
 VOL = (64, 64, 32)
@@ -183,7 +184,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_line(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -391,7 +392,7 @@ def run_ours(args):
                         "workload": WORKLOADS[other_p].format(B=B), "value": also["value"], "unit": UNIT,
                         "ms_per_step": also["ms_per_step"], "overall_tflops": also["value"] * fl / 1e12,
                         "clocks": also["clocks"]}
-    print(json.dumps(line))
+    print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -410,12 +411,27 @@ def main():
     ap.add_argument("--no-also", action="store_true",
                     help="skip the device-resident measurement at the other precision ('also' key)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        if not torch.cuda.is_available():
-            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-        run_ours(args)
+    # stdout carries exactly ONE line (the JSON): anything libraries print there while the job
+    # runs (e.g. NCCL's version banner) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = []
+    global print_line
+    print_line = buf.append
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            if not torch.cuda.is_available():
+                raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in buf:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
