@@ -411,9 +411,15 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
                 for (int i = 0; i < 32; i++) y[i] = rna_tf32(y[i]);
               }
               if (valid) {
-                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c);
+                // 256-bit stores: a lane's 32 B fill a whole sector per instruction (the rows of a
+                // warp are a row pitch apart, so nothing else coalesces)
+                float* o = reinterpret_cast<float*>(p.out) + off + c;
 #pragma unroll
-                for (int i = 0; i < 8; i++) o[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                for (int i = 0; i < 4; i++)
+                  st_global_v8(o + 8 * i, __float_as_uint(y[8 * i]), __float_as_uint(y[8 * i + 1]),
+                               __float_as_uint(y[8 * i + 2]), __float_as_uint(y[8 * i + 3]),
+                               __float_as_uint(y[8 * i + 4]), __float_as_uint(y[8 * i + 5]),
+                               __float_as_uint(y[8 * i + 6]), __float_as_uint(y[8 * i + 7]));
               }
             } else {
               uint32_t pk[16];
@@ -426,9 +432,11 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
                 y[2 * i + 1] = __high2float(h);
               }
               if (valid) {
-                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + c);
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c;
 #pragma unroll
-                for (int i = 0; i < 4; i++) o[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                for (int i = 0; i < 2; i++)
+                  st_global_v8(o + 16 * i, pk[8 * i], pk[8 * i + 1], pk[8 * i + 2], pk[8 * i + 3],
+                               pk[8 * i + 4], pk[8 * i + 5], pk[8 * i + 6], pk[8 * i + 7]);
               }
             }
             if (p.has_stats) {

@@ -246,4 +246,12 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint
          ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// 256-bit global store (sm_100+, STG.E.256): p must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2),
+               "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 }  // namespace pcrl
