@@ -339,7 +339,7 @@ def run_ours(args):
     # committed ncu --set full capture: equal to its algorithmic bytes (read x once, write y once)
     traffic = {"bf16": 1.0910e9 + 0.5056e9, "fp32": 2.1829e9 + 1.0389e9}[main_p]
     traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of this kernel "
-                    "(up_tr64.ops.0 forward, b=32; algorithmic bytes %.3f GB), profiles/r01b_ncu_tensor_kernels.md"
+                    "(up_tr64.ops.0 forward, b=32; algorithmic bytes %.3f GB), profiles/r01c_ncu_tensor_kernels.md"
                     % ({"bf16": 1.640, "fp32": 3.279}[main_p]))
     fam = ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_dgrad_unshuffled")
     kmajor_ms = sum(per[k]["ms"] for k in fam if k in per)

@@ -22,6 +22,8 @@ PCRL_PREC=fp32 timeout 400 ncu --set full --clock-control none --import-source o
   -o gpurun_out/prof_kmajor_fp32 -f python tools/bench_layers.py 32 up_tr64.ops.0 > gpurun_out/ncu_top_fp32.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:igemm_mnmajor -s 1 -c 1 \
   -o gpurun_out/prof_mnmajor_bf16 -f python tools/bench_layers.py 32 up_tr64.ops.0 > gpurun_out/ncu_top2.log 2>&1
+PCRL_PREC=fp32 timeout 400 ncu --set full --clock-control none --import-source on -k regex:igemm_mnmajor -s 1 -c 1 \
+  -o gpurun_out/prof_mnmajor_fp32 -f python tools/bench_layers.py 32 up_tr64.ops.0 > gpurun_out/ncu_top3.log 2>&1
 echo "[t] ncu full $((SECONDS-T0)) s"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 5200 -c 2600 --csv \
   --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-also > gpurun_out/ncu_bench.log 2>&1
