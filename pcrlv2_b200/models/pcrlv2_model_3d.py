@@ -36,6 +36,63 @@ def bump_param_epoch():
     _PARAM_EPOCH[0] += 1
 
 
+# ---- weight gradients off the critical path ----------------------------------------------------
+# In the backward chain  dgrad(L+1) -> norm/act backward(L) -> dgrad(L) -> ...  nothing waits for the
+# weight gradient of layer L until the optimizer step.  When the parameters live in a FlatSGD buffer
+# the weight-gradient kernels therefore run on a side stream and add their result directly into the
+# parameter's slice of the flat gradient buffer: the tensor-core-bound weight-gradient kernel then
+# shares the SMs with the HBM-bound norm/act backward passes of the following layers instead of
+# queueing behind them.  The main stream re-joins the side stream when backward() finishes (engine
+# callback), so ``p.grad`` is complete for whatever runs after ``loss.backward()``.
+# PCRL_OVERLAP_WGRAD=0 disables it.
+import os as _os
+
+_SIDE = {}            # device index -> side stream
+_JOIN_PENDING = [False]
+
+
+def _side_stream(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE.get(idx)
+    if st is None:
+        st = _SIDE[idx] = torch.cuda.Stream(device=idx)
+    return st
+
+
+def join_side_streams():
+    """Make the current stream wait for everything queued on the side streams."""
+    for st in _SIDE.values():
+        torch.cuda.current_stream(st.device).wait_stream(st)
+    _JOIN_PENDING[0] = False
+
+
+def _overlap_target(weight):
+    """(optimizer, index) when the weight gradient may be accumulated in place from the side stream."""
+    if _os.environ.get("PCRL_OVERLAP_WGRAD", "1") == "0":
+        return None
+    flat = getattr(weight, "_pcrl_flat", None)
+    if flat is None or weight.grad is None or not weight.grad.is_contiguous():
+        return None
+    return flat
+
+
+def _wgrad_overlapped(dy, x, weight, flat):
+    side = _side_stream(dy.device)
+    side.wait_stream(torch.cuda.current_stream())          # dy (and zero_grad) are ordered before
+    with torch.cuda.stream(side):
+        g = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
+        weight.grad.add_(g)
+    # dy / x were allocated on the main stream: the allocator may not hand their memory out again
+    # before the side stream is done with them
+    dy.record_stream(side)
+    x.record_stream(side)
+    opt, idx = flat
+    opt._touched[idx] = True
+    if not _JOIN_PENDING[0]:
+        _JOIN_PENDING[0] = True
+        torch.autograd.Variable._execution_engine.queue_callback(join_side_streams)
+
+
 def _packed(module, kind, dtype=torch.bfloat16):
     """Tensor-core operand layouts of a conv weight in the activation storage type, cached until
     the parameter changes."""
@@ -184,7 +241,11 @@ class _LUConvFn(torch.autograd.Function):
             grads[1] = K.stem_conv_wgrad_gemm(dy, x)
         else:
             _, wd = _packed(cfg.conv, "conv3", cfg.dtype)
-            grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
+            flat = _overlap_target(cfg.conv.weight)
+            if flat is not None:
+                _wgrad_overlapped(dy, x, cfg.conv.weight, flat)      # grads[1] stays None: added in place
+            else:
+                grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
             if cfg.up is not None:
                 # data gradient lands coarse-major; its column sums are the ConvTranspose bias gradient
                 scratch, colsum = K.conv3d_k3_dgrad_unshuffled(dy, wd)

@@ -30,7 +30,7 @@ import torch.nn as nn
 from . import functional as Fn
 from . import kernels as K
 from .models import PCRLv23d
-from .models.pcrlv2_model_3d import bump_param_epoch
+from .models.pcrlv2_model_3d import bump_param_epoch, join_side_streams
 from .utils import AverageMeter, adjust_learning_rate
 
 
@@ -83,6 +83,10 @@ class FlatSGD(torch.optim.Optimizer):
         self._has_buf = [False] * len(ps)
         for i, p in enumerate(ps):
             p.register_hook(self._make_hook(i))
+            # lets the convolution backward accumulate its weight gradient straight into the flat
+            # buffer from a side stream (models/pcrlv2_model_3d.py:_wgrad_overlapped) and mark the
+            # parameter as reached itself
+            p._pcrl_flat = (self, i)
         self._distributed = (dist.is_available() and dist.is_initialized()
                              and dist.get_world_size(process_group) > 1) if distributed is None else distributed
         self._pg = process_group
@@ -111,6 +115,7 @@ class FlatSGD(torch.optim.Optimizer):
     def step(self, closure=None):
         group = self.param_groups[0]
         scale = 1.0
+        join_side_streams()   # weight gradients still in flight on the side stream (no-op after backward())
         if self._distributed:
             scale = allreduce_flat_gradients(self._flat_g, self._pg)
         dev = self._flat_p.device

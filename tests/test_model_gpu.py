@@ -363,3 +363,33 @@ def test_large_volume_128x128x64(precision):
     e = rl2(lout, o_lout)
     log(f"[128x128x64 {precision}] local 32^3 out rel-L2 {e:.3e}")
     assert e < tol
+
+
+def test_side_stream_weight_gradients_match(monkeypatch):
+    """With a FlatSGD attached, the 3x3x3 weight gradients are accumulated into the flat buffer from a
+    side stream (models/pcrlv2_model_3d.py:_wgrad_overlapped).  Same gradients, same set of reached
+    parameters, same update as the in-line path (PCRL_OVERLAP_WGRAD=0).  The restoration terms are
+    used (well conditioned at batch 2; the contrastive terms are chaotic there: BatchNorm1d over two
+    rows), and the run-to-run noise of the in-line path (atomics) calibrates the comparison."""
+    x1, _, gt, _ = orc.synthetic_batch(2, seed=9, vol=(32, 32, 16))
+    runs = []
+    for mode in ("1", "0", "0"):
+        monkeypatch.setenv("PCRL_OVERLAP_WGRAD", mode)
+        m, _ = build("bn")
+        opt = T.FlatSGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+        out, _, masks = m(x1.cuda())
+        loss = torch.nn.functional.mse_loss(out, gt.cuda()) + torch.nn.functional.mse_loss(masks[1], gt.cuda())
+        opt.zero_grad()
+        loss.backward()
+        g = opt._flat_g.clone()                # reads p.grad right after backward(): must be complete
+        touched = list(opt._touched)
+        opt.step()
+        runs.append((g, touched, opt._flat_p.clone(), loss.item()))
+    (g1, t1, p1, l1), (g0, t0, p0, l0), (gb, tb, pb, lb) = runs
+    assert t1 == t0 == tb
+    assert abs(l1 - l0) < 1e-6
+    noise = rl2(gb, g0)
+    diff = rl2(g1, g0)
+    log(f"[side-stream wgrad] flat gradient rel-L2 overlapped vs in-line {diff:.3e}; in-line run-to-run {noise:.3e}")
+    assert diff < max(5 * noise, 1e-5)
+    assert rl2(p1, p0) < max(5 * rl2(pb, p0), 1e-7)
