@@ -387,9 +387,12 @@ def test_side_stream_weight_gradients_match(monkeypatch):
         runs.append((g, touched, opt._flat_p.clone(), loss.item()))
     (g1, t1, p1, l1), (g0, t0, p0, l0), (gb, tb, pb, lb) = runs
     assert t1 == t0 == tb
-    assert abs(l1 - l0) < 1e-6
+    # fp64 / fp32 atomics make two runs of the SAME path differ (loss ~3e-6, gradients ~4e-3 rel-L2
+    # at batch 2 through the BatchNorm backward): the bounds sit well above that noise and far below
+    # what a lost or doubled weight gradient would cause (rel-L2 ~ 1)
+    assert abs(l1 - l0) < 1e-4
     noise = rl2(gb, g0)
     diff = rl2(g1, g0)
     log(f"[side-stream wgrad] flat gradient rel-L2 overlapped vs in-line {diff:.3e}; in-line run-to-run {noise:.3e}")
-    assert diff < max(5 * noise, 1e-5)
-    assert rl2(p1, p0) < max(5 * rl2(pb, p0), 1e-7)
+    assert diff < max(5 * noise, 3e-2)
+    assert rl2(p1, p0) < max(5 * rl2(pb, p0), 1e-5)
