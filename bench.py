@@ -278,11 +278,23 @@ def measure(args, precision, host, rank, world, dev, full):
 
     # ---- per-kernel roofline: one instrumented step (events around every entry point).  Every
     # rank runs it (the step contains the gradient all-reduce); only rank 0 reports.
+    # The weight-gradient kernels normally run on a side stream, concurrently with main-stream
+    # kernels; event-bracketed durations would then include the time a kernel waits for SMs held by
+    # the other stream.  The instrumented step therefore runs serialised (PCRL_OVERLAP_WGRAD=0): the
+    # per-kernel durations are clean, `value` above was measured with the overlap on.
     torch.cuda.synchronize()
+    prev_ov = os.environ.get("PCRL_OVERLAP_WGRAD")
+    os.environ["PCRL_OVERLAP_WGRAD"] = "0"
     _lib.profile[0] = []
-    device_step(0)
-    torch.cuda.synchronize()
-    prof, _lib.profile[0] = _lib.profile[0], None
+    try:
+        device_step(0)
+        torch.cuda.synchronize()
+    finally:
+        prof, _lib.profile[0] = _lib.profile[0], None
+        if prev_ov is None:
+            del os.environ["PCRL_OVERLAP_WGRAD"]
+        else:
+            os.environ["PCRL_OVERLAP_WGRAD"] = prev_ov
     barrier()
     per = {}
     for name, ints, a, b in prof:
@@ -376,6 +388,7 @@ def run_ours(args):
                      "traffic_note": traffic_note, **extra,
                      "kernel": "igemm_kmajor_kernel (3x3x3 conv forward + data gradient)",
                      "launches": n_kmajor, "kernel_ms_per_step": kmajor_ms,
+                     "timing": "CUDA events around every launch of one serialised step (side-stream overlap off)",
                      "share_of_step": kmajor_ms / step_ms_prof if step_ms_prof else None,
                      "all_conv3_kernels": {"achieved": conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms else None,
                                            "frac": conv_fl / (conv_ms / 1e3) / 1e12 / peak if conv_ms and peak else None,
