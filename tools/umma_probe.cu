@@ -763,6 +763,165 @@ static int run_dual(int n, int iters, int flags, int nw) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// cta2: tcgen05.mma.cta_group::2 (CTA pair, M = 256).  Each CTA of the pair holds 128 rows of A
+// (plus `shift` spare rows for the row-shifted view the conv kernels use) and n/2 rows of B; the
+// leader issues the MMAs, each CTA's TMEM receives its own 128 accumulator rows x n columns.
+// Checks the result against a CPU reference for both candidate B-half assignments and measures the
+// issue rate with operands resident in shared memory (what a CTA pair buys: every SM reads only
+// half of B per MMA, i.e. less shared-memory bandwidth per flop than two independent M = 128 MMAs).
+struct C2Params { int n, kblocks, shift, iters, ra; };
+
+__device__ __forceinline__ void umma_bf16_cta2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cta2(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+probe_cta2(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb, C2Params p,
+           float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int nh = p.n / 2;
+  const int a_bytes = ((p.ra * 128 + 1023) / 1024) * 1024;
+  const int b_bytes = ((nh * 128 + 1023) / 1024) * 1024;
+  uint8_t* a_s = smem;
+  uint8_t* b_s = smem + (size_t)p.kblocks * a_bytes;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_full, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar_full, (uint32_t)(p.kblocks * (p.ra + nh) * 128));
+    for (int kb = 0; kb < p.kblocks; kb++) {
+      tma_load_2d(a_s + (size_t)kb * a_bytes, &ta, &bar_full, kb * 64, (int)rank * p.ra);
+      tma_load_2d(b_s + (size_t)kb * b_bytes, &tb, &bar_full, kb * 64, (int)rank * nh);
+    }
+    mbar_wait(&bar_full, 0);
+  }
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' operands are in shared memory
+  tc_fence_after();
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(1, 256, p.n, 0, 0);
+    for (int it = 0; it < p.iters; it++) {
+      uint32_t acc = 0;
+      for (int kb = 0; kb < p.kblocks; kb++)
+        for (int ks = 0; ks < 4; ks++) {
+          const uint32_t a_addr = smem_u32(a_s + (size_t)kb * a_bytes) + p.shift * 128 + ks * 32;
+          const uint32_t b_addr = smem_u32(b_s + (size_t)kb * b_bytes) + ks * 32;
+          umma_bf16_cta2(tmem, make_smem_desc(a_addr, 16, 1024, LAYOUT_SW128, 0),
+                         make_smem_desc(b_addr, 16, 1024, LAYOUT_SW128, 0), idesc, acc);
+          acc = 1;
+        }
+    }
+    umma_commit_cta2(&bar_mma, 3);
+  }
+  __syncwarp();
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  if (pair == 0) {
+    for (int c = 0; c < p.n; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+      tmem_ld_wait();
+      float* o = out + (size_t)(rank * 128 + warp * 32 + (threadIdx.x & 31)) * p.n + c;
+      for (int i = 0; i < 32; i++) o[i] = __uint_as_float(v[i]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+static int run_cta2(C2Params p) {
+  const int K = 64 * p.kblocks, nh = p.n / 2;
+  p.ra = 128 + ((p.shift + 7) / 8) * 8;
+  std::vector<float> A((size_t)2 * p.ra * K), B((size_t)p.n * K);
+  for (auto& x : A) x = bf16_round(frand());
+  for (auto& x : B) x = bf16_round(frand());
+  std::vector<__nv_bfloat16> a16(A.size()), b16(B.size());
+  for (size_t i = 0; i < A.size(); i++) a16[i] = __float2bfloat16(A[i]);
+  for (size_t i = 0; i < B.size(); i++) b16[i] = __float2bfloat16(B[i]);
+  void *dA, *dB; float* dO;
+  CK(cudaMalloc(&dA, a16.size() * 2)); CK(cudaMalloc(&dB, b16.size() * 2));
+  CK(cudaMalloc(&dO, (size_t)256 * p.n * 4));
+  CK(cudaMemcpy(dA, a16.data(), a16.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice));
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)(2 * p.ra)}, sa[1] = {(uint64_t)K * 2};
+  uint32_t ba[2] = {64, (uint32_t)p.ra};
+  CUtensorMap ta = make_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_128B);
+  uint64_t db[2] = {(uint64_t)K, (uint64_t)p.n};
+  uint32_t bb[2] = {64, (uint32_t)nh};
+  CUtensorMap tb = make_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, db, sa, bb, CU_TENSOR_MAP_SWIZZLE_128B);
+  size_t smem = (size_t)p.kblocks * ((((size_t)p.ra * 128 + 1023) / 1024) * 1024 + (((size_t)nh * 128 + 1023) / 1024) * 1024) + 2048;
+  CK(cudaFuncSetAttribute(probe_cta2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  C2Params q = p; q.iters = 1;
+  probe_cta2<<<2, 128, smem>>>(ta, tb, q, dO);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> O((size_t)256 * p.n);
+  CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
+  // hypothesis 0: column j < n/2 comes from CTA 0's B rows, j >= n/2 from CTA 1's (B row j of the global matrix)
+  double maxerr = 0, maxref = 0;
+  for (int m = 0; m < 256; m++)
+    for (int j = 0; j < p.n; j++) {
+      const int arow = (m / 128) * p.ra + (m % 128) + p.shift;
+      double ref = 0;
+      for (int k = 0; k < K; k++) ref += (double)A[(size_t)arow * K + k] * B[(size_t)j * K + k];
+      maxerr = fmax(maxerr, fabs(ref - O[(size_t)m * p.n + j]));
+      maxref = fmax(maxref, fabs(ref));
+    }
+  printf("RESULT cta2 n=%d kb=%d shift=%d : maxerr=%.3e maxref=%.3e %s\n", p.n, p.kblocks, p.shift, maxerr, maxref,
+         maxerr <= 1e-3 * fmax(maxref, 1.0) ? "OK" : "MISMATCH");
+  // issue rate: every pair of SMs runs `iters` passes over the resident operands
+  int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  int khz = 0; CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int grid = (sms / 2) * 2;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    probe_cta2<<<grid, 128, smem>>>(ta, tb, p, dO);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double nmma = (double)p.iters * p.kblocks * 4;
+    const double flops = 2.0 * 256 * p.n * 16 * nmma * (grid / 2);
+    if (rep == 2)
+      printf("RESULT cta2 rate n=%d iters=%d pairs=%d : %.3f ms  %.1f TFLOP/s  %.1f clk/MMA@%dMHz\n", p.n, p.iters,
+             grid / 2, ms, flops / ms * 1e-9, ms * 1e-3 * khz * 1e3 / nmma, khz / 1000);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage\n"); return 2; }
   std::string t = argv[1];
@@ -778,6 +937,10 @@ int main(int argc, char** argv) {
     return run_mnmajor(p);
   } else if (t == "halo") {
     return run_halo();
+  } else if (t == "cta2") {
+    // cta2 n kblocks shift iters
+    C2Params p; p.n = I(2, 256); p.kblocks = I(3, 2); p.shift = I(4, 0); p.iters = I(5, 2000);
+    return run_cta2(p);
   } else if (t == "dual") {
     return run_dual(I(2, 128), I(3, 4000), I(4, 0), I(5, 2));
   } else if (t == "lean") {
