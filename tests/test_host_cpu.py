@@ -46,6 +46,14 @@ def test_product_path_fails_loudly_without_gpu():
         m(torch.zeros(2, 1, 16, 16, 16))
     with pytest.raises(_lib.PcrlError, match="CPU tensor"):
         _lib.call("pcrl_zero_pad_rows", torch.zeros(8), 1, 1, 8)
+    # the head / loss functions are CUDA kernels as well: no silent CPU evaluation
+    from pcrlv2_b200 import functional as Fn
+    with pytest.raises(_lib.PcrlError, match="CPU tensor"):
+        Fn.mse_loss(torch.zeros(4, 4), torch.zeros(4, 4))
+    with pytest.raises(_lib.PcrlError, match="CPU tensor"):
+        Fn.cosine_mean(torch.randn(4, 8), torch.randn(4, 8))
+    with pytest.raises(_lib.PcrlError, match="CPU tensor"):
+        Fn.batch_norm1d(torch.randn(4, 8), torch.nn.BatchNorm1d(8))
     # nothing in the product package imports the oracle
     for dirpath, _, files in os.walk(os.path.join(ROOT, "pcrlv2_b200")):
         for f in files:
@@ -147,3 +155,21 @@ def test_two_rank_gradient_exchange_gloo(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm): exactly one line on stdout, valid JSON with the keys
+    of the contract, whatever libraries print while it runs."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "volumes/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["metric"].startswith("LUNA 64x64x32")
