@@ -55,7 +55,11 @@ class FlatSGD(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0, process_group=None,
                  distributed=None):
         params = list(params)
-        defaults = dict(lr=float(lr), momentum=float(momentum), weight_decay=float(weight_decay))
+        # the remaining keys are torch.optim.SGD's own defaults: ``state_dict()`` then has exactly the
+        # layout the reference's checkpoints carry (train_3d.py:74-76) and loads into torch.optim.SGD,
+        # and a reference checkpoint loads into FlatSGD (load_state_dict below)
+        defaults = dict(lr=float(lr), momentum=float(momentum), dampening=0, weight_decay=float(weight_decay),
+                        nesterov=False, maximize=False, foreach=None, differentiable=False, fused=None)
         super().__init__(params, defaults)
         ps = [p for g in self.param_groups for p in g["params"]]
         if len(self.param_groups) != 1:
@@ -129,6 +133,27 @@ class FlatSGD(torch.optim.Optimizer):
                 o = self._offs[i]
                 self.state[p]["momentum_buffer"] = self._flat_m[o:o + p.numel()].view_as(p)
         bump_param_epoch()
+
+    def load_state_dict(self, state_dict):
+        """Accepts the ``optimizer`` entry of a reference checkpoint (torch.optim.SGD.state_dict(),
+        train_3d.py:76) or FlatSGD's own: momentum buffers are copied into the flat buffer."""
+        for g in state_dict["param_groups"]:
+            if g.get("nesterov") or g.get("dampening", 0) != 0 or g.get("maximize"):
+                raise ValueError("FlatSGD implements SGD with momentum and weight decay only "
+                                 "(nesterov / dampening / maximize are not used by the reference)")
+        super().load_state_dict(state_dict)
+        with torch.no_grad():
+            for i, p in enumerate(self._ps):
+                o = self._offs[i]
+                view = self._flat_m[o:o + p.numel()].view_as(p)
+                buf = self.state.get(p, {}).get("momentum_buffer")
+                if buf is not None:
+                    view.copy_(buf)
+                    self.state[p]["momentum_buffer"] = view
+                    self._has_buf[i] = True
+                else:
+                    view.zero_()
+                    self._has_buf[i] = False
 
     def touched_names(self, model):
         names = {id(p): n for n, p in model.named_parameters()}

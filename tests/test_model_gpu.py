@@ -396,3 +396,57 @@ def test_side_stream_weight_gradients_match(monkeypatch):
     log(f"[side-stream wgrad] flat gradient rel-L2 overlapped vs in-line {diff:.3e}; in-line run-to-run {noise:.3e}")
     assert diff < max(5 * noise, 3e-2)
     assert rl2(p1, p0) < max(5 * rl2(pb, p0), 1e-5)
+
+
+def test_checkpoint_round_trip_with_torch_sgd():
+    """the checkpoint the trainer writes (reference train_3d.py:71-80) is
+    interchangeable with the reference's: FlatSGD.state_dict() loads into torch.optim.SGD and steps
+    identically, torch.optim.SGD.state_dict() loads into FlatSGD, model.state_dict() round-trips."""
+    import io
+    x1, _, gt, _ = orc.synthetic_batch(2, seed=4, vol=(32, 32, 16))
+    m, _ = build("bn")
+    opt = T.FlatSGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+
+    def backward_once():
+        out, _, masks = m(x1.cuda())
+        loss = torch.nn.functional.mse_loss(out, gt.cuda()) + torch.nn.functional.mse_loss(masks[2], gt.cuda())
+        opt.zero_grad()
+        loss.backward()
+
+    backward_once()
+    opt.step()
+    # the checkpoint dict of the trainer, through torch.save / torch.load
+    buf = io.BytesIO()
+    torch.save({"state_dict": m.state_dict(), "optimizer": opt.state_dict(), "epoch": 0}, buf)
+    buf.seek(0)
+    ck = torch.load(buf, weights_only=False)
+    assert list(ck["state_dict"].keys()) == [k for k, _, _ in orc.state_spec()]
+    # reference side: plain parameters + torch.optim.SGD restored from OUR optimizer state
+    names = [n for n, _ in m.named_parameters()]
+    ref_params = [torch.nn.Parameter(ck["state_dict"][n].detach().clone().cuda()) for n in names]
+    ref_opt = torch.optim.SGD(ref_params, lr=1e-2, momentum=0.9, weight_decay=1e-4)
+    ref_opt.load_state_dict(ck["optimizer"])
+    n_buf = sum(1 for p in ref_params if "momentum_buffer" in ref_opt.state.get(p, {}))
+    assert n_buf == sum(opt._has_buf) and 0 < n_buf < len(ref_params)   # unreached heads have no buffer (N3)
+    # a second step with the same gradients on both sides
+    backward_once()
+    for p, q, touched in zip(m.parameters(), ref_params, opt._touched):
+        q.grad = p.grad.detach().clone() if touched else None
+    opt.step()
+    ref_opt.step()
+    worst = max(rl2(p, q) for p, q in zip(m.parameters(), ref_params))
+    log(f"[checkpoint] FlatSGD vs torch.optim.SGD restored from its state_dict: worst parameter rel-L2 {worst:.3e}")
+    assert worst < 1e-6
+    # and back: torch.optim.SGD's state into a fresh FlatSGD
+    m2, _ = build("bn", seed=1)
+    opt2 = T.FlatSGD(m2.parameters(), lr=1e-3, momentum=0.0, weight_decay=0.0)
+    m2.load_state_dict({**m.state_dict()})
+    opt2.load_state_dict(ref_opt.state_dict())
+    assert opt2.param_groups[0]["lr"] == 1e-2 and opt2.param_groups[0]["momentum"] == 0.9
+    assert opt2._has_buf == opt._has_buf
+    assert rl2(opt2._flat_m, opt._flat_m) < 1e-6
+    assert rl2(opt2._flat_p, opt._flat_p) < 1e-7
+    with pytest.raises(ValueError):
+        bad = ref_opt.state_dict()
+        bad["param_groups"][0]["nesterov"] = True
+        opt2.load_state_dict(bad)
