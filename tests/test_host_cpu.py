@@ -173,3 +173,28 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["metric"].startswith("LUNA 64x64x32")
+
+
+def test_c_abi_argument_errors_without_gpu():
+    """Error behaviour of the C ABI (include/pcrl_b200.h): bad arguments are rejected with
+    PCRL_ERR_ARG (-1) and a message BEFORE any CUDA call, so this runs without a GPU."""
+    from pcrlv2_b200 import _lib
+    lib = _lib.lib()
+    P = ctypes.c_void_p
+    # NULL operand
+    assert lib.pcrl_linear_fwd(None, None, None, None, 4, 8, 8, None) == -1
+    assert b"NULL" in lib.pcrl_last_error()
+    assert lib.pcrl_mse_fwd(None, None, None, 16, None) == -1
+    fake = P(4096)      # never dereferenced: the shape checks fire first
+    # weight gradient needs Cout % 64 == 0
+    assert lib.pcrl_conv3d_k3_wgrad(fake, fake, fake, 1, 4, 4, 4, 64, 48, 0, None) == -1
+    assert b"multiple of 64" in lib.pcrl_last_error()
+    # unknown storage type
+    assert lib.pcrl_conv3d_k3_fprop(fake, fake, fake, None, 0, 0, 1, 4, 4, 4, 64, 64, 7, None) == -1
+    assert b"dtype" in lib.pcrl_last_error()
+    # BatchNorm1d in training mode needs more than one row (torch raises the same condition)
+    assert lib.pcrl_bn1d_fwd(fake, fake, fake, None, None, None, fake, fake, fake, 1, 8, 0, 1, 0.1, 1e-5, None) == -1
+    assert b"more than 1 value per channel" in lib.pcrl_last_error()
+    # norm/act channel count must be 8 * 2^k
+    assert lib.pcrl_norm_act_fwd(fake, fake, fake, None, fake, None, None, 0, 0, 0, 1, 4, 4, 4, 24, 0, None) == -1
+    assert b"8 * 2^k" in lib.pcrl_last_error()
