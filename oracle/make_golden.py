@@ -12,7 +12,8 @@ What it does
      (``.cuda()``/``torch.cuda.synchronize`` patched to no-ops, smp stubbed because
      models/__init__.py imports the 2-D model) and checks the oracle's ``train_step`` reproduces
      its parameters, momentum buffers, BN buffers and loss meters;
-  4. writes digests of all of the above as golden fixtures.
+  4. writes digests of all of the above as golden fixtures;
+  2b. the same forward + restoration-gradient check for act='prelu' and act='elu' (32x32x16).
 """
 from __future__ import annotations
 
@@ -142,6 +143,45 @@ def main():
                 out[f"{norm}.buf.{k}"] = digest(v)
     np.savez_compressed(os.path.join(GOLD, "forward_b2.npz"), **out)
     print("wrote forward_b2.npz")
+
+    # ---- 2b. activation variants (reference models/pcrlv2_model_3d.py:20-27): forward + gradients of
+    # the restoration terms at b=2, 32x32x16
+    out = {}
+    for act in ("prelu", "elu"):
+        sd0 = orc.init_state(0, act=act)
+        x1, _, gt, _ = orc.synthetic_batch(2, seed=7, vol=(32, 32, 16))
+        ref = refmod.PCRLv23d(act=act)
+        ref.load_state_dict(orc.clone_state(sd0))
+        ref.train()
+        r_out, _, r_masks = ref(x1)
+        r_loss = torch.nn.functional.mse_loss(r_out, gt) + torch.nn.functional.mse_loss(r_masks[1], gt)
+        r_loss.backward()
+        r_grads = {n: p.grad for n, p in ref.named_parameters()}
+        sd = orc.clone_state(sd0)
+        keys = [k for k in sd if orc.is_param(k)]
+        for k in keys:
+            sd[k].requires_grad_(True)
+        o_out, _, o_masks = orc.forward(sd, x1, False, True, act, "bn")
+        o_loss = torch.nn.functional.mse_loss(o_out, gt) + torch.nn.functional.mse_loss(o_masks[1], gt)
+        o_grads = dict(zip(keys, torch.autograd.grad(o_loss, [sd[k] for k in keys], allow_unused=True)))
+        print(f"[2b] act={act}: loss oracle {o_loss.item():.8f} ref {r_loss.item():.8f}")
+        check_close("out", o_out, r_out, 1e-6)
+        for s_ in range(3):
+            check_close(f"mask[{s_}]", o_masks[s_], r_masks[s_], 1e-6)
+        for k in keys:
+            if r_grads[k] is None:
+                assert o_grads[k] is None, k
+            else:
+                check_close(f"grad {k}", o_grads[k], r_grads[k], 2e-5)
+        out[f"{act}.loss"] = np.float64(r_loss.item())
+        out[f"{act}.out"] = digest(r_out)
+        for s_ in range(3):
+            out[f"{act}.mask{s_}"] = digest(r_masks[s_])
+        for k in keys:
+            if r_grads[k] is not None and (k.endswith("activation.weight") or k.endswith("conv1.weight")):
+                out[f"{act}.grad.{k}"] = digest(r_grads[k])
+    np.savez_compressed(os.path.join(GOLD, "acts_b2.npz"), **out)
+    print("wrote acts_b2.npz")
 
     # ---- 3. the real reference trainer, two iterations on CPU
     train_3d = load_ref_train_module()

@@ -450,3 +450,32 @@ def test_checkpoint_round_trip_with_torch_sgd():
         bad = ref_opt.state_dict()
         bad["param_groups"][0]["nesterov"] = True
         opt2.load_state_dict(bad)
+
+
+@pytest.mark.parametrize("act", ["prelu", "elu"])
+def test_activation_variants_vs_reference_fixture(act):
+    """act='prelu' / 'elu' (reference models/pcrlv2_model_3d.py:20-27) through the CUDA path, fp32
+    mode, against the digests written from the reference model itself (tests/golden/acts_b2.npz)."""
+    g = np.load(os.path.join(GOLD, "acts_b2.npz"))
+    m, _ = build("bn", act=act, precision="fp32")
+    x1, _, gt, _ = orc.synthetic_batch(2, seed=7, vol=(32, 32, 16))
+    out, _, masks = m(x1.cuda())
+    loss = torch.nn.functional.mse_loss(out, gt.cuda()) + torch.nn.functional.mse_loss(masks[1], gt.cuda())
+    loss.backward()
+    assert abs(loss.item() - float(g[f"{act}.loss"])) < 2e-5
+    f = out.detach().double().cpu().flatten()
+    stride = max(1, f.numel() // 256)
+    ref = g[f"{act}.out"]
+    err = np.linalg.norm(f[::stride][:256].numpy() - ref[4:]) / np.linalg.norm(ref[4:])
+    log(f"[act {act}] loss {loss.item():.7f} vs reference {float(g[f'{act}.loss']):.7f}; out samples rel-L2 {err:.3e}")
+    assert err < 4e-3
+    assert abs(f.sum().item() - ref[0]) / abs(ref[0]) < 1e-3
+    # the decoder's last convolution and (prelu) its slope gradient: digest = [sum, |.|sum, sq sum, n, samples]
+    params = dict(m.named_parameters())
+    for name in ("up_tr64.ops.1.conv1.weight",) + (("up_tr64.ops.1.activation.weight",) if act == "prelu" else ()):
+        d = g[f"{act}.grad.{name}"]
+        gr = params[name].grad.detach().double().cpu().flatten()
+        st = max(1, gr.numel() // 256)
+        e = np.linalg.norm(gr[::st][:256].numpy() - d[4:]) / np.linalg.norm(d[4:])
+        log(f"[act {act}] {name} grad samples rel-L2 {e:.3e}")
+        assert e < 5e-2, (name, e)

@@ -138,3 +138,29 @@ def test_tf32_emulation_rounding_and_drift():
     assert 1e-5 < err < 5e-3, err
     for u, v in zip(ma, mb):
         assert ((u - v).norm() / u.norm()).item() < 1e-2
+
+
+@pytest.mark.parametrize("act", ["prelu", "elu"])
+def test_activation_variants_against_reference_fixture(act):
+    """Forward and restoration gradients of the oracle for act='prelu' / 'elu' against digests written
+    from the reference model itself (oracle/make_golden.py section 2b)."""
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "acts_b2.npz"))
+    sd = orc.init_state(0, act=act)
+    x1, _, gt, _ = orc.synthetic_batch(2, seed=7, vol=(32, 32, 16))
+    keys = [k for k in sd if orc.is_param(k)]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    out, _, masks = orc.forward(sd, x1, False, True, act, "bn")
+    loss = torch.nn.functional.mse_loss(out, gt) + torch.nn.functional.mse_loss(masks[1], gt)
+    grads = dict(zip(keys, torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)))
+    assert abs(loss.item() - float(g[f"{act}.loss"])) < 1e-6
+    assert close(digest(out), g[f"{act}.out"])
+    for s in range(3):
+        assert close(digest(masks[s]), g[f"{act}.mask{s}"])
+    n = 0
+    for k in g.files:
+        if k.startswith(f"{act}.grad."):
+            assert close(digest(grads[k[len(act) + 6:]]), g[k], 2e-4), k
+            n += 1
+    assert n >= 15      # 14 trunk convolutions + the supervised deep-supervision head (+ PReLU slopes)
