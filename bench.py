@@ -248,8 +248,21 @@ def measure(args, precision, host, rank, world, dev, full):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = ms.item()
+    # host cost of one step: Python + ctypes + launches with an EMPTY launch queue (sync before, no sync
+    # inside the bracket); when this approaches ms_per_step the job is host-bound
+    host = []
+    for i in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        device_step(i)
+        host.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    host_ms = torch.tensor([statistics.median(host)], device=dev)
+    if world > 1:
+        dist.all_reduce(host_ms, op=dist.ReduceOp.MAX)
     out = {"value": world * B * args.steps / (ms_total / 1e3), "ms_per_step": ms_total / args.steps,
-           "gpu_launches": launches, "clocks": clocks, "precision": precision}
+           "gpu_launches": launches, "clocks": clocks, "precision": precision,
+           "host_ms_per_step": host_ms.item()}
     if not full:
         return out
 
@@ -398,12 +411,15 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": r["e2e"],
         "gpu_launches": r["gpu_launches"],
+        "launches_per_step": r["gpu_launches"] / args.steps,
+        "host_ms_per_step": r["host_ms_per_step"],
         "clocks": r["clocks"],
     }
     if also is not None:
         line["also"] = {"dtype": "bf16" if other_p == "bf16" else "tf32",
                         "workload": WORKLOADS[other_p].format(B=B), "value": also["value"], "unit": UNIT,
-                        "ms_per_step": also["ms_per_step"], "overall_tflops": also["value"] * fl / 1e12,
+                        "ms_per_step": also["ms_per_step"], "host_ms_per_step": also["host_ms_per_step"],
+                        "overall_tflops": also["value"] * fl / 1e12,
                         "clocks": also["clocks"]}
     print_line(json.dumps(line))
     if world > 1:

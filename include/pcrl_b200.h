@@ -29,6 +29,10 @@ extern "C" {
 /* storage type of activations and tensor-core operands: bf16 (kind::f16 MMA) or fp32 (kind::tf32) */
 #define PCRL_DTYPE_BF16 0
 #define PCRL_DTYPE_F32 1
+/* fp32 storage WITHOUT the tf32 rounding on store (precision='fp32x3'): activations keep all 24
+ * mantissa bits; the tensor-core kernels are then fed operands split by pcrl_split3_tf32 (3xTF32:
+ * x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32-equivalent products).  Accepted wherever `dtype` is. */
+#define PCRL_DTYPE_F32X 2
 
 /* activation codes: models/pcrlv2_model_3d.py:20-27 */
 #define PCRL_ACT_RELU 0
@@ -193,6 +197,18 @@ int pcrl_upsample_trilinear_fwd(const float* x, float* y, int N, int D, int H, i
                                 void* stream);
 int pcrl_upsample_trilinear_bwd(const float* dy, float* dx, int N, int D, int H, int W, int sf,
                                 void* stream);
+
+/* ---- 3xTF32 operand split (precision='fp32x3': fp32-equivalent tensor-core products) ----------- */
+/* src [rows][C] fp32 -> three tf32-representable parts, hi = rna_tf32(x), lo = rna_tf32(x - hi):
+ *   pattern 0 (the A / activation side):  (hi, lo, hi)     pattern 1 (the B / weight side): (hi, hi, lo)
+ *   stack_rows = 0: dst [rows][3*C], the parts concatenated along the contraction (K) index, for
+ *                   the K-major kernels (conv fprop / dgrad, gemm_nt): sum_k A3*B3 = hi*hi + lo*hi + hi*lo;
+ *   stack_rows = 1: dst [3][rows][C], the parts stacked along the row index, for the kernels that
+ *                   reduce over rows (conv wgrad over N*voxels, gemm_tn).
+ * The reference computes these products in fp32 (models/pcrlv2_model_3d.py:9,52,60,78 under
+ * allow_tf32=False); this is how the same precision is reached on tf32 tensor cores. */
+int pcrl_split3_tf32(const float* src, float* dst, long long rows, int C, int pattern, int stack_rows,
+                     void* stream);
 
 /* ---- optimizer: torch.optim.SGD(momentum, weight_decay), train_3d.py:48-51,151 ------------- */
 int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf,

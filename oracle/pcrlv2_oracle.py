@@ -124,6 +124,15 @@ def is_param(key: str) -> bool:
                 or key.endswith("num_batches_tracked"))
 
 
+def is_cancelling(key: str) -> bool:
+    """Parameters whose exact gradient is ZERO in train mode because a batch-statistics normalisation
+    follows directly (SURVEY note N1): every LUConv ``conv1.bias`` (BatchNorm3d / InstanceNorm3d
+    next), ``<up>.bn.bias`` and ``predictor_head.0.bias`` (Linear -> BatchNorm1d next).  The
+    reference's gradient for them is rounding noise (1e-15 .. 1e-18 in fp64), so their updates are
+    weight decay only and comparisons of their gradients are meaningless."""
+    return (key.endswith("conv1.bias") or key.endswith(".bn.bias") or key.endswith("predictor_head.0.bias"))
+
+
 # --------------------------------------------------------------------------- forward
 def _norm3d(x, sd, prefix, norm, training):
     """BatchNorm3d(momentum=0.1, eps=1e-5, affine) / InstanceNorm3d(affine, no running stats)
@@ -307,4 +316,4 @@ def clone_state(sd, dtype=None):
 
 
 __all__ = ["state_spec", "init_state", "forward", "cos_loss", "step_loss", "sgd_step",
-           "train_step", "synthetic_batch", "clone_state", "is_param", "lr_at", "random"]
+           "train_step", "synthetic_batch", "clone_state", "is_param", "is_cancelling", "lr_at", "random"]

@@ -44,6 +44,7 @@ int im2col27(const float*, void*, int, int, int, int, int, cudaStream_t);
 int chan1_sigmoid_fwd(const float*, const float*, const float*, float*, int, int, long long, cudaStream_t);
 int chan1_sigmoid_bwd(const float*, const float*, const float*, const float*, const float*, const float*, double*, float*, double, int, int, int, long long, cudaStream_t);
 int sgd_flat(float*, const float*, float*, const long long*, const int*, const int*, int, float, float, float, float, cudaStream_t);
+int split3_tf32(const float*, float*, long long, int, int, int, cudaStream_t);
 // losses.cu
 int bn1d_fwd(const float*, const float*, const float*, float*, float*, long long*, float*, float*, float*, int, int, int, int, float, float, cudaStream_t);
 int bn1d_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, cudaStream_t);
@@ -67,8 +68,8 @@ extern "C" {
 
 const char* pcrl_last_error(void) { return last_error_buf(); }
 int pcrl_version(void) { return 102; }
-static inline int esz(int dtype) { return dtype == PCRL_DTYPE_F32 ? 4 : 2; }
-#define CHECK_DTYPE(d) PCRL_REQUIRE((d) == PCRL_DTYPE_BF16 || (d) == PCRL_DTYPE_F32, "%s: unknown dtype %d", __func__, (d))
+static inline int esz(int dtype) { return dtype == PCRL_DTYPE_BF16 ? 2 : 4; }
+#define CHECK_DTYPE(d) PCRL_REQUIRE((d) == PCRL_DTYPE_BF16 || (d) == PCRL_DTYPE_F32 || (d) == PCRL_DTYPE_F32X, "%s: unknown dtype %d", __func__, (d))
 
 int pcrl_pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int dtype, void* stream) {
   NONNULL(w); NONNULL(wf); CHECK_DTYPE(dtype);
@@ -129,7 +130,7 @@ int pcrl_convT3d_k2s2_fprop(const void* x, const void* wf, const float* bias, vo
                             int D, int H, int W, int Cin, int Cout, int dtype, void* stream) {
   NONNULL(x); NONNULL(wf); NONNULL(y_fine); CHECK_DTYPE(dtype);
   const long long rows = (long long)N * D * (H + 1) * W;
-  int rc = gemm_nt_igemm(x, wf, y_fine, bias, rows, Cin, 8 * Cout, Cout, dtype == PCRL_DTYPE_F32, /*OUT_CONVT*/ 2,
+  int rc = gemm_nt_igemm(x, wf, y_fine, bias, rows, Cin, 8 * Cout, Cout, dtype != PCRL_DTYPE_BF16, /*OUT_CONVT*/ 2,
                          D, H, W, Cout, ST(stream), dtype);
   if (rc) return rc;
   return zero_pad_rows(y_fine, (long long)N * 2 * D, 2 * H + 1, (long long)2 * W * Cout * esz(dtype), ST(stream));
@@ -146,7 +147,7 @@ int pcrl_convT3d_k2s2_bwd(const void* g_fine, const void* x, const void* wd, voi
   }
   if (dx) {
     NONNULL(wd);
-    rc = gemm_nt_igemm(scratch, wd, dx, nullptr, rows, 8 * Cout, Cin, Cin, dtype == PCRL_DTYPE_F32, /*OUT_ROWS*/ 1,
+    rc = gemm_nt_igemm(scratch, wd, dx, nullptr, rows, 8 * Cout, Cin, Cin, dtype != PCRL_DTYPE_BF16, /*OUT_ROWS*/ 1,
                        0, 0, 0, 0, ST(stream), dtype);
     if (rc) return rc;
   }
@@ -279,6 +280,11 @@ int pcrl_upsample_trilinear_fwd(const float* x, float* y, int N, int D, int H, i
 int pcrl_upsample_trilinear_bwd(const float* dy, float* dx, int N, int D, int H, int W, int sf, void* stream) {
   NONNULL(dy); NONNULL(dx);
   return upsample_trilinear_bwd(dy, dx, N, D, H, W, sf, ST(stream));
+}
+
+int pcrl_split3_tf32(const float* src, float* dst, long long rows, int C, int pattern, int stack_rows, void* stream) {
+  NONNULL(src); NONNULL(dst);
+  return split3_tf32(src, dst, rows, C, pattern, stack_rows, ST(stream));
 }
 
 int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf, const long long* seg_offsets,

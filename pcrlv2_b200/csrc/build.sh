@@ -4,12 +4,16 @@ set -e
 cd "$(dirname "$0")"
 OUT=${PCRL_OUT:-../libpcrl_b200.so}
 BUILD=${PCRL_BUILD_DIR:-build}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --use_fast_math -Xptxas -v $PCRL_EXTRA_FLAGS"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $PCRL_EXTRA_FLAGS"
+# --use_fast_math only where no transcendental / division decides a result: the tensor-core kernels
+# (their arithmetic is the MMA).  The streaming / head / loss kernels use IEEE division, sqrt and expf.
+FAST="--use_fast_math"
 mkdir -p $BUILD
 pids=()
 for f in api igemm_kmajor igemm_mnmajor streaming heads losses; do
   if [ ! -f $BUILD/$f.o ] || [ $f.cu -nt $BUILD/$f.o ] || [ sm100.cuh -nt $BUILD/$f.o ] || [ common.cuh -nt $BUILD/$f.o ]; then
-    nvcc $FLAGS -c $f.cu -o $BUILD/$f.o > $BUILD/$f.log 2>&1 &
+    EXTRA=""; case $f in igemm_*) EXTRA=$FAST;; esac
+    nvcc $FLAGS $EXTRA -c $f.cu -o $BUILD/$f.o > $BUILD/$f.log 2>&1 &
     pids+=($!)
   fi
 done

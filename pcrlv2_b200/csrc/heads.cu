@@ -20,6 +20,13 @@ namespace pcrl {
 typedef __nv_bfloat16 bf16_t;
 __device__ __forceinline__ void cvt_store1(bf16_t* p, float v) { *p = __float2bfloat16(v); }
 __device__ __forceinline__ void cvt_store1(float* p, float v) { *p = rna_tf32(v); }
+struct f32x { float v; };   // fp32 stored exactly (PCRL_DTYPE_F32X), see streaming.cu
+__device__ __forceinline__ void cvt_store1(f32x* p, float v) { p->v = v; }
+__device__ __forceinline__ void store_row32(f32x* p, const float (&v)[32]) {
+  float4* o = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
 // store 32 consecutive values of one row
 __device__ __forceinline__ void store_row32(bf16_t* p, const float (&v)[32]) {
   uint4* o = reinterpret_cast<uint4*>(p);
@@ -199,10 +206,10 @@ chan1_sigmoid_fwd_kernel(const float* __restrict__ y, const float* __restrict__ 
        i += (long long)gridDim.x * blockDim.x * 4) {
     const float4 v = *reinterpret_cast<const float4*>(yy + i);
     float4 o;
-    o.x = 1.f / (1.f + __expf(-fmaf(v.x, sc, sh)));
-    o.y = 1.f / (1.f + __expf(-fmaf(v.y, sc, sh)));
-    o.z = 1.f / (1.f + __expf(-fmaf(v.z, sc, sh)));
-    o.w = 1.f / (1.f + __expf(-fmaf(v.w, sc, sh)));
+    o.x = 1.f / (1.f + expf(-fmaf(v.x, sc, sh)));
+    o.y = 1.f / (1.f + expf(-fmaf(v.y, sc, sh)));
+    o.z = 1.f / (1.f + expf(-fmaf(v.z, sc, sh)));
+    o.w = 1.f / (1.f + expf(-fmaf(v.w, sc, sh)));
     *reinterpret_cast<float4*>(mm + i) = o;
   }
 }
@@ -293,7 +300,8 @@ static inline unsigned blocks_for(long long items, int per_block, int cap) {
 }
 
 int head_pack_weights(const float* w3, const float* w1, void* wext, void* wextT, int C, int dtype, cudaStream_t s) {
-  if (dtype == PCRL_DTYPE_F32) head_pack_kernel<float><<<(32 * C + 255) / 256, 256, 0, s>>>(w3, w1, (float*)wext, (float*)wextT, C);
+  if (dtype == PCRL_DTYPE_F32X) head_pack_kernel<f32x><<<(32 * C + 255) / 256, 256, 0, s>>>(w3, w1, (f32x*)wext, (f32x*)wextT, C);
+  else if (dtype == PCRL_DTYPE_F32) head_pack_kernel<float><<<(32 * C + 255) / 256, 256, 0, s>>>(w3, w1, (float*)wext, (float*)wextT, C);
   else head_pack_kernel<bf16_t><<<(32 * C + 255) / 256, 256, 0, s>>>(w3, w1, (bf16_t*)wext, (bf16_t*)wextT, C);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
@@ -309,14 +317,16 @@ int head_gather(const float* tT, const float* b3, const float* b1, float* y1, fl
 }
 int head_scatter(const float* dy1, const float* dy0, void* dT, int N, int D, int H, int W, int dtype, cudaStream_t s) {
   const long long rows = (long long)N * D * (H + 1) * W;
-  if (dtype == PCRL_DTYPE_F32) head_scatter_kernel<float><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(dy1, dy0, (float*)dT, N, D, H, W);
+  if (dtype == PCRL_DTYPE_F32X) head_scatter_kernel<f32x><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(dy1, dy0, (f32x*)dT, N, D, H, W);
+  else if (dtype == PCRL_DTYPE_F32) head_scatter_kernel<float><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(dy1, dy0, (float*)dT, N, D, H, W);
   else head_scatter_kernel<bf16_t><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(dy1, dy0, (bf16_t*)dT, N, D, H, W);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
 int im2col27(const float* x, void* out, int N, int D, int H, int W, int dtype, cudaStream_t s) {
   const long long rows = (long long)N * D * (H + 1) * W;
-  if (dtype == PCRL_DTYPE_F32) im2col27_kernel<float><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(x, (float*)out, N, D, H, W);
+  if (dtype == PCRL_DTYPE_F32X) im2col27_kernel<f32x><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(x, (f32x*)out, N, D, H, W);
+  else if (dtype == PCRL_DTYPE_F32) im2col27_kernel<float><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(x, (float*)out, N, D, H, W);
   else im2col27_kernel<bf16_t><<<blocks_for(rows, 256, num_sms() * 16), 256, 0, s>>>(x, (bf16_t*)out, N, D, H, W);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;

@@ -55,6 +55,7 @@ struct IgemmParams {
   long long rows_total;       // PLAIN: number of A rows
   // epilogue
   int out_mode, out_fp32, ldc, has_bias, has_stats, stats_per_sample, cout_total;
+  int exact_out;              // PCRL_DTYPE_F32X: fp32 results are stored without the tf32 rounding
   int ct_D, ct_H, ct_W;       // coarse dims for the ConvT scatter
   void* out;
   const float* bias;
@@ -405,7 +406,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
                 for (int i = 0; i < 32; i++) o[(size_t)(co0 + c + i) * p.ldc] = y[i];
               }
             } else if (p.out_fp32) {
-              if (p.out_mode == OUT_CONVT || p.out_mode == OUT_UNSHUFFLE) {
+              if ((p.out_mode == OUT_CONVT || p.out_mode == OUT_UNSHUFFLE) && !p.exact_out) {
                 // these outputs are tensor-core operands of the next kernel: store tf32-rounded
 #pragma unroll
                 for (int i = 0; i < 32; i++) y[i] = rna_tf32(y[i]);
@@ -573,7 +574,7 @@ static int make_b_maps(IgemmLaunch& L, const void* w, int K, int cols, int taps)
 int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int stats_per_sample,
                     int out_fp32, int N, int D, int H, int W, int Cin, int Cout,
                     cudaStream_t stream, int unshuffle, int dtype) {
-  const int tf32 = dtype == PCRL_DTYPE_F32;
+  const int tf32 = dtype != PCRL_DTYPE_BF16;
   if (tf32) {
     PCRL_REQUIRE(Cin % 32 == 0, "conv3d_k3 (fp32): Cin=%d must be a multiple of 32", Cin);
     out_fp32 = 1;
@@ -630,7 +631,7 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
     p.ct_D = D / 2; p.ct_H = H / 2; p.ct_W = W / 2;
   }
   p.has_stats = stats != nullptr; p.stats_per_sample = stats_per_sample;
-  p.out = y; p.stats = stats;
+  p.out = y; p.stats = stats; p.exact_out = dtype == PCRL_DTYPE_F32X;
   uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)p.MR, (uint64_t)N};
   uint64_t str[3] = {(uint64_t)Cin * elt, (uint64_t)W * Cin * elt, (uint64_t)p.MR * W * Cin * elt};
   uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.Wp, (uint32_t)p.nh_box, 1};
@@ -647,7 +648,7 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
 int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
                   int cols, int ldc, int out_fp32, int out_mode, int ct_D, int ct_H, int ct_W,
                   int ct_cout, cudaStream_t stream, int dtype) {
-  const int tf32 = dtype == PCRL_DTYPE_F32;
+  const int tf32 = dtype != PCRL_DTYPE_BF16;
   if (tf32) {
     PCRL_REQUIRE(K % 32 == 0, "gemm_nt (fp32): K=%d must be a multiple of 32", K);
     out_fp32 = 1;
@@ -677,7 +678,7 @@ int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long
   p.out_mode = out_mode; p.out_fp32 = out_fp32; p.ldc = ldc;
   p.cout_total = (out_mode == OUT_CONVT) ? ct_cout : cols;
   p.ct_D = ct_D; p.ct_H = ct_H; p.ct_W = ct_W;
-  p.has_bias = bias != nullptr; p.bias = bias; p.out = c;
+  p.has_bias = bias != nullptr; p.bias = bias; p.out = c; p.exact_out = dtype == PCRL_DTYPE_F32X;
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
   uint64_t str[1] = {(uint64_t)K * elt};
   uint32_t box[2] = {(uint32_t)p.kc, 128};

@@ -338,7 +338,7 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 //   dy: [N][D][H+1][W][Cout] bf16 (pad rows zero), x: [N][D][H+1][W][Cin] bf16 (pad rows zero)
 int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D, int H, int W,
                           int Cin, int Cout, cudaStream_t stream, int dtype) {
-  const int tf32 = dtype == PCRL_DTYPE_F32;
+  const int tf32 = dtype != PCRL_DTYPE_BF16;
   PCRL_REQUIRE(Cout % 64 == 0, "conv3d_k3_wgrad: Cout=%d must be a multiple of 64", Cout);
   PCRL_REQUIRE(Cin == 32 || Cin % 64 == 0, "conv3d_k3_wgrad: Cin=%d must be 32 or a multiple of 64", Cin);
   WgradParams p;
@@ -430,7 +430,7 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
 // dW[P][Q] (fp32, leading dimension Q) += A[rows][P]^T * B[rows][Q]; A, B bf16 row-major.
 int gemm_tn_igemm(const void* a, const void* b, float* dw, long long rows, int P, int Q,
                   cudaStream_t stream, int dtype) {
-  const int tf32 = dtype == PCRL_DTYPE_F32;
+  const int tf32 = dtype != PCRL_DTYPE_BF16;
   PCRL_REQUIRE(P % 64 == 0 && (Q % 64 == 0 || Q == 32), "gemm_tn: P=%d (multiple of 64), Q=%d (32 or multiple of 64)", P, Q);
   WgradParams p;
   memset(&p, 0, sizeof(p));

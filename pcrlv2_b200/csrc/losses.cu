@@ -52,7 +52,7 @@ bn1d_kernel(const float* __restrict__ x, const float* __restrict__ y_fwd, const 
 #pragma unroll
       for (int i = 0; i < 8; i++) q += red[1][i][tx];
       const float var = q / (float)B;                    // biased: normalisation
-      invstd = rsqrtf(var + eps);
+      invstd = 1.f / sqrtf(var + eps);
       if (ok && ty == 0) {
         if (running_mean) {
           running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
@@ -62,7 +62,7 @@ bn1d_kernel(const float* __restrict__ x, const float* __restrict__ y_fwd, const 
       }
     } else {
       mean = ok ? running_mean[c] : 0.f;
-      invstd = ok ? rsqrtf(running_var[c] + eps) : 0.f;
+      invstd = ok ? 1.f / sqrtf(running_var[c] + eps) : 0.f;
     }
     if (ok) {
       if (ty == 0) { save_mean[c] = mean; save_invstd[c] = invstd; }
@@ -317,7 +317,7 @@ int mse_bwd(const float* p, const float* t, const float* g, float* dp, long long
 __global__ void __launch_bounds__(256)
 sigmoid_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n, int bwd) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (!bwd) out[i] = 1.f / (1.f + __expf(-a[i]));
+    if (!bwd) out[i] = 1.f / (1.f + expf(-a[i]));
     else { const float y = a[i]; out[i] = b[i] * y * (1.f - y); }      // a = y (forward output), b = dy
   }
 }

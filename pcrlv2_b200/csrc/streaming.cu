@@ -54,6 +54,30 @@ __device__ __forceinline__ void st8(float* p, const float (&f)[8]) {
   reinterpret_cast<float4*>(p)[0] = make_float4(rna_tf32(f[0]), rna_tf32(f[1]), rna_tf32(f[2]), rna_tf32(f[3]));
   reinterpret_cast<float4*>(p)[1] = make_float4(rna_tf32(f[4]), rna_tf32(f[5]), rna_tf32(f[6]), rna_tf32(f[7]));
 }
+// fp32 stored exactly (PCRL_DTYPE_F32X): same memory format as float, no tf32 rounding on store
+struct f32x { float v; };
+template <> struct V8<f32x> { uint4 a, b; };
+__device__ __forceinline__ V8<f32x> ld8(const f32x* p) {
+  V8<f32x> v;
+  v.a = reinterpret_cast<const uint4*>(p)[0];
+  v.b = reinterpret_cast<const uint4*>(p)[1];
+  return v;
+}
+__device__ __forceinline__ void up8(const V8<f32x>& v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.a.x); f[1] = __uint_as_float(v.a.y); f[2] = __uint_as_float(v.a.z); f[3] = __uint_as_float(v.a.w);
+  f[4] = __uint_as_float(v.b.x); f[5] = __uint_as_float(v.b.y); f[6] = __uint_as_float(v.b.z); f[7] = __uint_as_float(v.b.w);
+}
+__device__ __forceinline__ void st8(f32x* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void z8(f32x* p) {
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(0, 0, 0, 0);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void rnd8(f32x, float (&)[8]) {}
+__device__ __forceinline__ void cvt_store(f32x* p, float v) { p->v = v; }
+__device__ __forceinline__ float to_f(f32x v) { return v.v; }
 __device__ __forceinline__ void z8(bf16_t* p) { *reinterpret_cast<uint4*>(p) = make_uint4(0, 0, 0, 0); }
 __device__ __forceinline__ void z8(float* p) {
   reinterpret_cast<uint4*>(p)[0] = make_uint4(0, 0, 0, 0);
@@ -78,7 +102,7 @@ __device__ __forceinline__ float act_fwd(float z, int act, float slope) {
     case ACT_RELU: return fmaxf(z, 0.f);
     case ACT_PRELU: return z > 0.f ? z : slope * z;
     case ACT_ELU: return z > 0.f ? z : expm1f(z);
-    case ACT_SIGMOID: return 1.f / (1.f + __expf(-z));
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-z));
     default: return z;
   }
 }
@@ -87,8 +111,8 @@ __device__ __forceinline__ float act_bwd(float z, int act, float slope) {
   switch (act) {
     case ACT_RELU: return z > 0.f ? 1.f : 0.f;
     case ACT_PRELU: return z > 0.f ? 1.f : slope;
-    case ACT_ELU: return z > 0.f ? 1.f : __expf(z);
-    case ACT_SIGMOID: { float s = 1.f / (1.f + __expf(-z)); return s * (1.f - s); }
+    case ACT_ELU: return z > 0.f ? 1.f : expf(z);
+    case ACT_SIGMOID: { float s = 1.f / (1.f + expf(-z)); return s * (1.f - s); }
     default: return 1.f;
   }
 }
@@ -745,6 +769,35 @@ convT_unshuffle_kernel(const T* __restrict__ g, T* __restrict__ out,
   }
 }
 
+// ------------------------------------------------------------------------------ 3xTF32 operand split
+// src [rows][C] fp32 -> (hi, lo, hi) or (hi, hi, lo) with hi = rna_tf32(x), lo = rna_tf32(x - hi), written
+// as [rows][3C] (parts along the contraction index) or [3][rows][C] (parts along the row index).
+__global__ void __launch_bounds__(256)
+split3_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long rows, int C4,
+                   int pattern, int stack_rows) {
+  const long long total = rows * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C4;
+    const int c = (int)(i % C4);
+    const float4 x = src[i];
+    float4 hi, lo;
+    hi.x = rna_tf32(x.x); hi.y = rna_tf32(x.y); hi.z = rna_tf32(x.z); hi.w = rna_tf32(x.w);
+    lo.x = rna_tf32(x.x - hi.x); lo.y = rna_tf32(x.y - hi.y); lo.z = rna_tf32(x.z - hi.z); lo.w = rna_tf32(x.w - hi.w);
+    const float4 p1 = pattern == 0 ? lo : hi, p2 = pattern == 0 ? hi : lo;
+    if (stack_rows) {
+      dst[i] = hi;
+      dst[total + i] = p1;
+      dst[2 * total + i] = p2;
+    } else {
+      float4* o = dst + r * 3 * C4 + c;
+      o[0] = hi;
+      o[C4] = p1;
+      o[2 * C4] = p2;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ launch wrappers
 static inline int grid_for(long long items, int block, int max_blocks) {
   long long b = (items + block - 1) / block;
@@ -760,14 +813,24 @@ static inline int block_for_c8(int C8) {
 }
 
 // dtype: PCRL_DTYPE_BF16 (0) or PCRL_DTYPE_F32 (1) = storage type of activations / packed operands
-#define PCRL_BY_DTYPE(dtype, EXPR_BF16, EXPR_F32) \
-  do { if ((dtype) == PCRL_DTYPE_F32) { EXPR_F32; } else { EXPR_BF16; } } while (0)
+#define PCRL_BY_DTYPE(dtype, EXPR_BF16, EXPR_F32, EXPR_F32X) \
+  do { if ((dtype) == PCRL_DTYPE_F32) { EXPR_F32; } else if ((dtype) == PCRL_DTYPE_F32X) { EXPR_F32X; } else { EXPR_BF16; } } while (0)
+
+int split3_tf32(const float* src, float* dst, long long rows, int C, int pattern, int stack_rows, cudaStream_t s) {
+  PCRL_REQUIRE(C % 4 == 0 && rows > 0, "split3_tf32: C=%d must be a multiple of 4", C);
+  PCRL_REQUIRE(pattern == 0 || pattern == 1, "split3_tf32: pattern must be 0 (hi,lo,hi) or 1 (hi,hi,lo)");
+  split3_tf32_kernel<<<grid_for(rows * (C / 4), 256, num_sms() * 16), 256, 0, s>>>(
+      (const float4*)src, (float4*)dst, rows, C / 4, pattern, stack_rows);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
 
 int pack_conv3_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int dtype, cudaStream_t s) {
   const long long total = (long long)Cout * Cin * 27;
   PCRL_BY_DTYPE(dtype,
     (pack_conv3_kernel<bf16_t><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (bf16_t*)wf, (bf16_t*)wd, Cout, Cin)),
-    (pack_conv3_kernel<float><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (float*)wf, (float*)wd, Cout, Cin)));
+    (pack_conv3_kernel<float><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (float*)wf, (float*)wd, Cout, Cin)),
+    (pack_conv3_kernel<f32x><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (f32x*)wf, (f32x*)wd, Cout, Cin)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -781,7 +844,8 @@ int pack_convT_weights(const float* w, void* wf, void* wd, int Cin, int Cout, in
   const long long total = (long long)Cin * Cout * 8;
   PCRL_BY_DTYPE(dtype,
     (pack_convT_kernel<bf16_t><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (bf16_t*)wf, (bf16_t*)wd, Cin, Cout)),
-    (pack_convT_kernel<float><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (float*)wf, (float*)wd, Cin, Cout)));
+    (pack_convT_kernel<float><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (float*)wf, (float*)wd, Cin, Cout)),
+    (pack_convT_kernel<f32x><<<grid_for(total, 256, 4096), 256, 0, s>>>(w, (f32x*)wf, (f32x*)wd, Cin, Cout)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -798,7 +862,8 @@ int stem_conv_fprop(const float* x, const float* w, void* y, double* stats, int 
   dim3 grid((slots + 127) / 128, N);
   PCRL_BY_DTYPE(dtype,
     (stem_conv_fprop_kernel<bf16_t><<<grid, 128, 0, s>>>(x, w, (bf16_t*)y, stats, stats_per_sample, N, D, H, W)),
-    (stem_conv_fprop_kernel<float><<<grid, 128, 0, s>>>(x, w, (float*)y, stats, stats_per_sample, N, D, H, W)));
+    (stem_conv_fprop_kernel<float><<<grid, 128, 0, s>>>(x, w, (float*)y, stats, stats_per_sample, N, D, H, W)),
+    (stem_conv_fprop_kernel<f32x><<<grid, 128, 0, s>>>(x, w, (f32x*)y, stats, stats_per_sample, N, D, H, W)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -812,7 +877,8 @@ int stem_conv_wgrad(const void* dy, const float* x, float* dw, int N, int D, int
   const int blocks = (int)((nwarps + 7) / 8);
   PCRL_BY_DTYPE(dtype,
     (stem_conv_wgrad_kernel<bf16_t><<<blocks, 256, 0, s>>>((const bf16_t*)dy, x, dw, N, D, H, W, vpw)),
-    (stem_conv_wgrad_kernel<float><<<blocks, 256, 0, s>>>((const float*)dy, x, dw, N, D, H, W, vpw)));
+    (stem_conv_wgrad_kernel<float><<<blocks, 256, 0, s>>>((const float*)dy, x, dw, N, D, H, W, vpw)),
+    (stem_conv_wgrad_kernel<f32x><<<blocks, 256, 0, s>>>((const f32x*)dy, x, dw, N, D, H, W, vpw)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -871,6 +937,8 @@ int norm_act_fwd(const void* y, const float* scale, const float* shift, const fl
   PCRL_REQUIRE(!pool || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "norm_act_fwd: pooling needs even dims");
   PCRL_REQUIRE(!(pool && avg_sum), "norm_act_fwd: avg_sum with pool is not supported");
   PCRL_REQUIRE(row_segments(pool ? W / 2 : W, C / 8) > 0, "norm_act_fwd: row of %d x %d channels cannot be split into block-sized segments", W, C);
+  if (dtype == PCRL_DTYPE_F32X)
+    return norm_act_fwd_t<f32x>(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H, W, C, s);
   if (dtype == PCRL_DTYPE_F32)
     return norm_act_fwd_t<float>(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H, W, C, s);
   return norm_act_fwd_t<bf16_t>(y, scale, shift, prelu, a_out, pool_out, avg_sum, per_sample, act, pool, N, D, H, W, C, s);
@@ -920,6 +988,9 @@ int norm_act_bwd(const void* y, const void* g1, const void* g2, const float* gav
   PCRL_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "norm_act_bwd: C=%d must be 8 * 2^k", C);
   PCRL_REQUIRE(!pool || g1, "norm_act_bwd: pooled backward needs g1");
   PCRL_REQUIRE(row_segments(pool ? W / 2 : W, C / 8) > 0, "norm_act_bwd: row of %d x %d channels cannot be split into block-sized segments", W, C);
+  if (dtype == PCRL_DTYPE_F32X)
+    return norm_act_bwd_t<f32x>(y, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu, sums, dy, count,
+                                per_sample, act, pool, pass, N, D, H, W, C, s);
   if (dtype == PCRL_DTYPE_F32)
     return norm_act_bwd_t<float>(y, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu, sums, dy, count,
                                  per_sample, act, pool, pass, N, D, H, W, C, s);
@@ -945,7 +1016,8 @@ int convT_unshuffle(const void* g, void* out, float* dbias, int N, int D, int H,
   const size_t smem = dbias ? (size_t)block * 8 * 4 : 0;
   PCRL_BY_DTYPE(dtype,
     (convT_unshuffle_kernel<bf16_t><<<blocks, block, smem, s>>>((const bf16_t*)g, (bf16_t*)out, dbias, N, D, H, W, C)),
-    (convT_unshuffle_kernel<float><<<blocks, block, smem, s>>>((const float*)g, (float*)out, dbias, N, D, H, W, C)));
+    (convT_unshuffle_kernel<float><<<blocks, block, smem, s>>>((const float*)g, (float*)out, dbias, N, D, H, W, C)),
+    (convT_unshuffle_kernel<f32x><<<blocks, block, smem, s>>>((const f32x*)g, (f32x*)out, dbias, N, D, H, W, C)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

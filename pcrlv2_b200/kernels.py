@@ -16,13 +16,41 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 # storage types of activations / tensor-core operands (include/pcrl_b200.h: PCRL_DTYPE_*)
 DTYPE_CODE = {torch.bfloat16: 0, torch.float32: 1}
+F32X = 2     # PCRL_DTYPE_F32X: fp32 stored without tf32 rounding, tensor-core operands split 3xTF32
 
 
-def _dt(t: torch.Tensor) -> int:
+def _dt(t: torch.Tensor, exact: bool = False) -> int:
+    """``exact`` (precision='fp32x3'): fp32 tensors keep all mantissa bits in memory and every
+    tensor-core product is evaluated as x_hi*w_hi + x_lo*w_hi + x_hi*w_lo on operands split by
+    ``split3`` -- fp32-equivalent arithmetic on the tf32 tensor cores."""
     try:
-        return DTYPE_CODE[t.dtype]
+        code = DTYPE_CODE[t.dtype]
     except KeyError:
         raise TypeError(f"activations must be bf16 or fp32, got {t.dtype}")
+    if exact:
+        assert code == 1, "exact (3xTF32) mode stores fp32"
+        return F32X
+    return code
+
+
+def _code(dtype, exact: bool = False) -> int:
+    return F32X if exact else DTYPE_CODE[dtype]
+
+
+def split3(t: torch.Tensor, pattern: int, stack: bool = False) -> torch.Tensor:
+    """3xTF32 operand split of a contiguous fp32 tensor [..., C] (csrc/streaming.cu:split3_tf32_kernel).
+    pattern 0 (activation side) = (hi, lo, hi), pattern 1 (weight side) = (hi, hi, lo);
+    ``stack=False`` -> [..., 3C] (parts along the contraction index), ``stack=True`` -> [3*t.shape[0], ...]
+    (parts along the leading / row index, for kernels that reduce over rows)."""
+    _chk(t, torch.float32)
+    c = t.shape[-1]
+    rows = t.numel() // c
+    if stack:
+        out = torch.empty((3 * t.shape[0],) + tuple(t.shape[1:]), dtype=torch.float32, device=t.device)
+    else:
+        out = torch.empty(tuple(t.shape[:-1]) + (3 * c,), dtype=torch.float32, device=t.device)
+    _lib.call("pcrl_split3_tf32", t, out, rows, c, int(pattern), int(stack))
+    return out
 
 
 def pad_ndhwc(x: torch.Tensor, dtype=BF16) -> torch.Tensor:
@@ -51,13 +79,16 @@ def _chk(t: torch.Tensor, dtype=None):
 
 
 # ------------------------------------------------------------------------------ weights
-def pack_conv3_weights(w: torch.Tensor, need_dgrad: bool = True, dtype=BF16):
-    """(Cout,Cin,3,3,3) fp32 -> (wf [27,Cout,Cin], wd [27,Cin,Cout] or None) in ``dtype``."""
+def pack_conv3_weights(w: torch.Tensor, need_dgrad: bool = True, dtype=BF16, exact=False):
+    """(Cout,Cin,3,3,3) fp32 -> (wf [27,Cout,Cin], wd [27,Cin,Cout] or None) in ``dtype``;
+    ``exact``: the 3xTF32 weight-side split along the contraction index ([27,Cout,3Cin], [27,Cin,3Cout])."""
     _chk(w, torch.float32)
     cout, cin = w.shape[0], w.shape[1]
     wf = torch.empty((27, cout, cin), dtype=dtype, device=w.device)
     wd = torch.empty((27, cin, cout), dtype=dtype, device=w.device) if need_dgrad else None
-    _lib.call("pcrl_pack_conv3_weights", w, wf, wd, cout, cin, DTYPE_CODE[dtype])
+    _lib.call("pcrl_pack_conv3_weights", w, wf, wd, cout, cin, _code(dtype, exact))
+    if exact:
+        return split3(wf, 1), (split3(wd, 1) if need_dgrad else None)
     return wf, wd
 
 
@@ -69,13 +100,15 @@ def unpack_conv3_wgrad(gpk: torch.Tensor) -> torch.Tensor:
     return g
 
 
-def pack_convT_weights(w: torch.Tensor, dtype=BF16):
-    """(Cin,Cout,2,2,2) fp32 -> (wf [8*Cout,Cin], wd [Cin,8*Cout]) in ``dtype``."""
+def pack_convT_weights(w: torch.Tensor, dtype=BF16, exact=False):
+    """(Cin,Cout,2,2,2) fp32 -> (wf [8*Cout,Cin], wd [Cin,8*Cout]) in ``dtype`` (``exact``: K tripled)."""
     _chk(w, torch.float32)
     cin, cout = w.shape[0], w.shape[1]
     wf = torch.empty((8 * cout, cin), dtype=dtype, device=w.device)
     wd = torch.empty((cin, 8 * cout), dtype=dtype, device=w.device)
-    _lib.call("pcrl_pack_convT_weights", w, wf, wd, cin, cout, DTYPE_CODE[dtype])
+    _lib.call("pcrl_pack_convT_weights", w, wf, wd, cin, cout, _code(dtype, exact))
+    if exact:
+        return split3(wf, 1), split3(wd, 1)
     return wf, wd
 
 
@@ -87,8 +120,10 @@ def unpack_convT_wgrad(gpk: torch.Tensor, cin: int, cout: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------ 3x3x3 conv
-def conv3d_k3_fprop(xp, wf, stats=None, per_sample=False, out_fp32=False):
+def conv3d_k3_fprop(xp, wf, stats=None, per_sample=False, out_fp32=False, exact=False):
     _chk(xp), _chk(wf, xp.dtype)
+    if exact:
+        xp = split3(xp, 0)          # [N,D,H+1,W,3Cin] against wf [27,Cout,3Cin]
     n, d, h, w, cin = dims_of(xp)
     cout = wf.shape[1]
     assert wf.shape == (27, cout, cin)
@@ -97,62 +132,80 @@ def conv3d_k3_fprop(xp, wf, stats=None, per_sample=False, out_fp32=False):
     if stats is not None:
         _chk(stats, torch.float64)
     _lib.call("pcrl_conv3d_k3_fprop", xp, wf, y, stats, int(per_sample), int(out_fp32), n, d, h, w,
-              cin, cout, _dt(xp))
+              cin, cout, _dt(xp, exact))
     return y
 
 
-def conv3d_k3_dgrad(dyp, wd):
+def conv3d_k3_dgrad(dyp, wd, exact=False):
     _chk(dyp), _chk(wd, dyp.dtype)
+    if exact:
+        dyp = split3(dyp, 0)
     n, d, h, w, cout = dims_of(dyp)
     cin = wd.shape[1]
     assert wd.shape == (27, cin, cout)
     dx = torch.empty((n, d, h + 1, w, cin), dtype=dyp.dtype, device=dyp.device)
-    _lib.call("pcrl_conv3d_k3_dgrad", dyp, wd, dx, n, d, h, w, cin, cout, _dt(dyp))
+    _lib.call("pcrl_conv3d_k3_dgrad", dyp, wd, dx, n, d, h, w, cin, cout, _dt(dyp, exact))
     return dx
 
 
-def conv3d_k3_dgrad_unshuffled(dyp, wd):
+def conv3d_k3_dgrad_unshuffled(dyp, wd, exact=False):
     """Data gradient written coarse-major for the ConvTranspose that produced the conv input.
     Returns (scratch [N*(D/2)*(H/2+1)*(W/2), 8*Cin] bf16, colsum [Cin,2] fp64)."""
     _chk(dyp), _chk(wd, dyp.dtype)
+    if exact:
+        dyp = split3(dyp, 0)
     n, d, h, w, cout = dims_of(dyp)
     cin = wd.shape[1]
     rows = n * (d // 2) * (h // 2 + 1) * (w // 2)
     scratch = torch.empty((rows, 8 * cin), dtype=dyp.dtype, device=dyp.device)
     colsum = torch.zeros((cin, 2), dtype=torch.float64, device=dyp.device)
-    _lib.call("pcrl_conv3d_k3_dgrad_unshuffled", dyp, wd, scratch, colsum, n, d, h, w, cin, cout, _dt(dyp))
+    _lib.call("pcrl_conv3d_k3_dgrad_unshuffled", dyp, wd, scratch, colsum, n, d, h, w, cin, cout, _dt(dyp, exact))
     return scratch, colsum
 
 
-def convT_bwd_from_scratch(scratch, xp, wd, need_dx=True):
+def convT_bwd_from_scratch(scratch, xp, wd, need_dx=True, exact=False):
     """ConvTranspose3d(k2,s2) gradient GEMMs on an already coarse-major output gradient."""
     n, d, h, w, cin = dims_of(xp)
     cout = scratch.shape[1] // 8
+    if exact:
+        # the two GEMMs of pcrl_convT3d_k2s2_bwd with split operands: dx = scratch * wd^T (parts along
+        # K = 8*Cout), dw = scratch^T * x (parts stacked along the rows)
+        rows = scratch.shape[0]
+        dx = None
+        if need_dx:
+            dx = torch.empty((n, d, h + 1, w, cin), dtype=xp.dtype, device=xp.device)
+            _lib.call("pcrl_gemm_nt", split3(scratch, 0), wd, dx, None, rows, 24 * cout, cin, cin, 1, F32X)
+        dw = torch.zeros((8 * cout, cin), dtype=torch.float32, device=xp.device)
+        _lib.call("pcrl_gemm_tn", split3(scratch, 1, stack=True), split3(xp.reshape(rows, cin), 0, stack=True),
+                  dw, 3 * rows, 8 * cout, cin, F32X)
+        return dx, dw
     dx = torch.empty((n, d, h + 1, w, cin), dtype=xp.dtype, device=xp.device) if need_dx else None
     dw = torch.zeros((8 * cout, cin), dtype=torch.float32, device=xp.device)
     _lib.call("pcrl_convT3d_k2s2_bwd", None, xp, wd, scratch, dx, dw, None, n, d, h, w, cin, cout, _dt(xp))
     return dx, dw
 
 
-def conv3d_k3_wgrad(dyp, xp, out=None):
+def conv3d_k3_wgrad(dyp, xp, out=None, exact=False):
     """Returns / accumulates into the packed gradient [27,Cout,Cin] fp32."""
     _chk(dyp), _chk(xp, dyp.dtype)
+    if exact:     # the reduction runs over (sample, voxel): parts stacked along the sample index
+        dyp, xp = split3(dyp, 1, stack=True), split3(xp, 0, stack=True)
     n, d, h, w, cout = dims_of(dyp)
     cin = xp.shape[-1]
     if out is None:
         out = torch.zeros((27, cout, cin), dtype=torch.float32, device=xp.device)
-    _lib.call("pcrl_conv3d_k3_wgrad", dyp, xp, out, n, d, h, w, cin, cout, _dt(dyp))
+    _lib.call("pcrl_conv3d_k3_wgrad", dyp, xp, out, n, d, h, w, cin, cout, _dt(dyp, exact))
     return out
 
 
 # ------------------------------------------------------------------------------ stem
-def stem_conv_fprop(x, w, stats=None, per_sample=False, dtype=BF16):
+def stem_conv_fprop(x, w, stats=None, per_sample=False, dtype=BF16, exact=False):
     """x (N,1,D,H,W) fp32, w (32,1,3,3,3) fp32 -> H-padded [N,D,H+1,W,32] in ``dtype``."""
     _chk(x, torch.float32), _chk(w, torch.float32)
     n, _, d, h, wd_ = x.shape
     assert w.shape[0] == 32 and w.shape[1] == 1
     y = torch.empty((n, d, h + 1, wd_, 32), dtype=dtype, device=x.device)
-    _lib.call("pcrl_stem_conv_fprop", x, w, y, stats, int(per_sample), n, d, h, wd_, DTYPE_CODE[dtype])
+    _lib.call("pcrl_stem_conv_fprop", x, w, y, stats, int(per_sample), n, d, h, wd_, _code(dtype, exact))
     return y
 
 
@@ -165,12 +218,14 @@ def stem_conv_wgrad(dyp, x):
 
 
 # ------------------------------------------------------------------------------ ConvTranspose
-def convT_fprop(xp, wf, bias):
+def convT_fprop(xp, wf, bias, exact=False):
     _chk(xp), _chk(wf, xp.dtype)
+    if exact:
+        xp = split3(xp, 0)
     n, d, h, w, cin = dims_of(xp)
     cout = wf.shape[0] // 8
     y = torch.empty((n, 2 * d, 2 * h + 1, 2 * w, cout), dtype=xp.dtype, device=xp.device)
-    _lib.call("pcrl_convT3d_k2s2_fprop", xp, wf, bias, y, n, d, h, w, cin, cout, _dt(xp))
+    _lib.call("pcrl_convT3d_k2s2_fprop", xp, wf, bias, y, n, d, h, w, cin, cout, _dt(xp, exact))
     return y
 
 
@@ -205,7 +260,7 @@ def norm_finalize(stats, count, gamma, beta, conv_bias=None, running_mean=None, 
 
 
 def norm_act_fwd(yp, scale, shift, act="relu", prelu=None, want_full=True, want_pool=False,
-                 want_avg=False, per_sample=False):
+                 want_avg=False, per_sample=False, exact=False):
     _chk(yp)
     n, d, h, w, c = dims_of(yp)
     a = torch.empty_like(yp) if want_full else None
@@ -213,57 +268,73 @@ def norm_act_fwd(yp, scale, shift, act="relu", prelu=None, want_full=True, want_
             if want_pool else None)
     avg = torch.zeros((n, c), dtype=torch.float32, device=yp.device) if want_avg else None
     _lib.call("pcrl_norm_act_fwd", yp, scale, shift, prelu, a, pool, avg, int(per_sample), ACT[act],
-              int(want_pool), n, d, h, w, c, _dt(yp))
+              int(want_pool), n, d, h, w, c, _dt(yp, exact))
     return a, pool, avg
 
 
 def norm_act_bwd(yp, g1, g2, gavg, scale, shift, mean, invstd, gamma, act="relu", prelu=None,
-                 pool=False, per_sample=False):
-    """Returns (dy padded bf16, sums [G,C,3] fp64 = (dbeta, dgamma, dprelu partial))."""
+                 pool=False, per_sample=False, batch_stats=True, exact=False):
+    """Returns (dy padded, sums [G,C,3] fp64 = (dbeta, dgamma, dprelu partial)).
+    ``batch_stats=False`` (BatchNorm in eval mode: mean / invstd are the running statistics, constants
+    of the graph): dy = gamma*invstd*dz without the mean(dz) / xhat*mean(dz*xhat) terms -- an infinite
+    element count makes those terms vanish in the apply pass; the parameter-gradient sums are unchanged."""
     _chk(yp)
     n, d, h, w, c = dims_of(yp)
     g = scale.shape[0]
     sums = torch.zeros((g, c, 3), dtype=torch.float64, device=yp.device)
     count = float(d * h * w) if per_sample else float(n * d * h * w)
+    if not batch_stats:
+        count = float("inf")
     dy = torch.empty_like(yp)
     for p in (0, 1):
         _lib.call("pcrl_norm_act_bwd", yp, g1, g2, gavg, scale, shift, mean, invstd, gamma, prelu,
-                  sums, dy, count, int(per_sample), ACT[act], int(pool), p, n, d, h, w, c, _dt(yp))
+                  sums, dy, count, int(per_sample), ACT[act], int(pool), p, n, d, h, w, c, _dt(yp, exact))
     return dy, sums
 
 
 # ------------------------------------------------------------------------------ heads
-def head_pack_weights(w3, w1=None, dtype=BF16):
-    """(1,C,3,3,3) [+ (1,C,1,1,1)] fp32 -> (wext [32,C], wextT [C,32]) in ``dtype``."""
+def head_pack_weights(w3, w1=None, dtype=BF16, exact=False):
+    """(1,C,3,3,3) [+ (1,C,1,1,1)] fp32 -> (wext [32,C], wextT [C,32]) in ``dtype`` (``exact``: K tripled)."""
     c = w3.shape[1]
     wext = torch.empty((32, c), dtype=dtype, device=w3.device)
     wext_t = torch.empty((c, 32), dtype=dtype, device=w3.device)
     _lib.call("pcrl_head_pack_weights", w3.contiguous(), None if w1 is None else w1.contiguous(),
-              wext, wext_t, c, DTYPE_CODE[dtype])
+              wext, wext_t, c, _code(dtype, exact))
+    if exact:
+        return split3(wext, 1), split3(wext_t, 1)
     return wext, wext_t
 
 
-def head_fwd(ap, wext, b3, b1=None, stats=None, per_sample=False):
+def head_fwd(ap, wext, b3, b1=None, stats=None, per_sample=False, exact=False):
     """1-channel head convolutions of an H-padded activation: T = A * wext^T on the tensor cores,
     then the 27-point gather.  Returns (y1 (N,1,D,H,W) fp32, y0 or None)."""
     _chk(ap), _chk(wext, ap.dtype)
     n, d, h, w, c = dims_of(ap)
     rows = n * d * (h + 1) * w
     t_t = torch.empty((32, rows), dtype=torch.float32, device=ap.device)
-    _lib.call("pcrl_gemm_nt", ap, wext, t_t, None, rows, c, 32, rows, 2, _dt(ap))
+    if exact:
+        _lib.call("pcrl_gemm_nt", split3(ap, 0), wext, t_t, None, rows, 3 * c, 32, rows, 2, F32X)
+    else:
+        _lib.call("pcrl_gemm_nt", ap, wext, t_t, None, rows, c, 32, rows, 2, _dt(ap))
     y1 = torch.empty((n, 1, d, h, w), dtype=torch.float32, device=ap.device)
     y0 = torch.empty_like(y1) if b1 is not None else None
     _lib.call("pcrl_head_gather", t_t, b3, b1, y1, y0, stats, int(per_sample), n, d, h, w)
     return y1, y0
 
 
-def head_bwd(ap, dy1, dy0, wext_t):
+def head_bwd(ap, dy1, dy0, wext_t, exact=False):
     """Returns (dA H-padded bf16, dwext [C,32] fp32: columns 0..26 = d w3 (tap order), 27 = d w1)."""
     n, d, h, w, c = dims_of(ap)
     rows = n * d * (h + 1) * w
     d_t = torch.empty((rows, 32), dtype=ap.dtype, device=ap.device)
-    _lib.call("pcrl_head_scatter", dy1, dy0, d_t, n, d, h, w, _dt(ap))
+    _lib.call("pcrl_head_scatter", dy1, dy0, d_t, n, d, h, w, _dt(ap, exact))
     da = torch.empty((n, d, h + 1, w, c), dtype=ap.dtype, device=ap.device)
+    if exact:
+        _lib.call("pcrl_gemm_nt", split3(d_t, 0), wext_t, da, None, rows, 96, c, c, 1, F32X)
+        dwext = torch.zeros((c, 32), dtype=torch.float32, device=ap.device)
+        _lib.call("pcrl_gemm_tn", split3(ap.reshape(rows, c), 0, stack=True), split3(d_t, 1, stack=True),
+                  dwext, 3 * rows, c, 32, F32X)
+        return da, dwext
     _lib.call("pcrl_gemm_nt", d_t, wext_t, da, None, rows, 32, c, c, _dt(ap), _dt(ap))
     dwext = torch.zeros((c, 32), dtype=torch.float32, device=ap.device)
     _lib.call("pcrl_gemm_tn", ap, d_t, dwext, rows, c, 32, _dt(ap))
@@ -280,20 +351,21 @@ def chan1_sigmoid_fwd(y, scale, shift, per_sample):
     return mask
 
 
-def chan1_sigmoid_bwd(y, mask, dmask, mean, invstd, gamma, per_sample):
-    """Returns (dy, sums [G,3] fp64 with (d beta, d gamma, 0) partials)."""
+def chan1_sigmoid_bwd(y, mask, dmask, mean, invstd, gamma, per_sample, batch_stats=True):
+    """Returns (dy, sums [G,3] fp64 with (d beta, d gamma, 0) partials); ``batch_stats`` as in
+    norm_act_bwd."""
     n = y.shape[0]
     vol = y.numel() // n
     g, v = (n, vol) if per_sample else (1, y.numel())
     sums = torch.zeros((g, 3), dtype=torch.float64, device=y.device)
     dy = torch.empty_like(y)
     for p in (0, 1):
-        _lib.call("pcrl_chan1_sigmoid_bwd", y, mask, dmask, mean, invstd, gamma, sums, dy, float(v),
-                  int(per_sample), p, g, v)
+        _lib.call("pcrl_chan1_sigmoid_bwd", y, mask, dmask, mean, invstd, gamma, sums, dy,
+                  float(v) if batch_stats else float("inf"), int(per_sample), p, g, v)
     return dy, sums
 
 
-def stem_conv_wgrad_gemm(dyp, x):
+def stem_conv_wgrad_gemm(dyp, x, exact=False):
     """Stem weight gradient on the tensor cores: im2col of the 1-channel input to [rows,32]
     (27 taps), rows paired into 64-wide operands, dW = sum of the diagonal 32x32 blocks of
     gemm_tn(dY, X27)."""
@@ -301,9 +373,13 @@ def stem_conv_wgrad_gemm(dyp, x):
     n, _, d, h, w = x.shape
     rows = n * d * (h + 1) * w
     x27 = torch.empty((rows, 32), dtype=dyp.dtype, device=x.device)
-    _lib.call("pcrl_im2col27", x, x27, n, d, h, w, _dt(dyp))
+    _lib.call("pcrl_im2col27", x, x27, n, d, h, w, _dt(dyp, exact))
     out = torch.zeros((64, 64), dtype=torch.float32, device=x.device)
-    _lib.call("pcrl_gemm_tn", dyp, x27, out, rows // 2, 64, 64, _dt(dyp))
+    if exact:
+        _lib.call("pcrl_gemm_tn", split3(dyp.reshape(rows // 2, 64), 1, stack=True),
+                  split3(x27.reshape(rows // 2, 64), 0, stack=True), out, 3 * (rows // 2), 64, 64, F32X)
+    else:
+        _lib.call("pcrl_gemm_tn", dyp, x27, out, rows // 2, 64, 64, _dt(dyp))
     dw = out[:32, :32] + out[32:, 32:]
     return dw[:, :27].reshape(32, 1, 3, 3, 3).contiguous()
 

@@ -14,8 +14,9 @@ autograd Functions in this file:
   backward          two-pass norm/act/pool backward, conv data gradient (same implicit GEMM with
                     mirrored filters), MN-major split-K weight gradient
 
-Activations between kernels are bf16 "H-padded NDHWC" (csrc/common.cuh); accumulation, norm
-statistics, parameters and the tensors returned to the caller are fp32.  The convolution bias in
+Activations between kernels are "H-padded NDHWC" (csrc/common.cuh) in the storage type selected by
+``precision`` (fp32 / TF32 operands by default, like the reference on a GPU; bf16 under ``--amp``);
+accumulation, norm statistics, parameters and the tensors returned to the caller are fp32.  The convolution bias in
 front of a normalisation cancels exactly: it is not added, its gradient is exactly zero, and it
 is folded into ``running_mean`` (SURVEY note N1).
 """
@@ -45,10 +46,14 @@ def bump_param_epoch():
 # queueing behind them.  The main stream re-joins the side stream when backward() finishes (engine
 # callback), so ``p.grad`` is complete for whatever runs after ``loss.backward()``.
 # PCRL_OVERLAP_WGRAD=0 disables it.
+# Limitation (documented): on this path the 3x3x3 weight gradient is accumulated in
+# place and autograd sees ``None`` for it, so ``torch.autograd.grad(loss, conv_weight)`` and tensor
+# hooks on those weights do not observe it; use ``loss.backward()`` (what the trainer does) or set
+# PCRL_OVERLAP_WGRAD=0.
 import os as _os
 
 _SIDE = {}            # device index -> side stream
-_JOIN_PENDING = [False]
+_JOIN_PENDING = [None]    # id of the autograd graph task that already queued the join callback
 
 
 def _side_stream(device):
@@ -63,7 +68,7 @@ def join_side_streams():
     """Make the current stream wait for everything queued on the side streams."""
     for st in _SIDE.values():
         torch.cuda.current_stream(st.device).wait_stream(st)
-    _JOIN_PENDING[0] = False
+    _JOIN_PENDING[0] = None
 
 
 def _overlap_target(weight):
@@ -76,11 +81,11 @@ def _overlap_target(weight):
     return flat
 
 
-def _wgrad_overlapped(dy, x, weight, flat):
+def _wgrad_overlapped(dy, x, weight, flat, exact=False):
     side = _side_stream(dy.device)
     side.wait_stream(torch.cuda.current_stream())          # dy (and zero_grad) are ordered before
     with torch.cuda.stream(side):
-        g = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
+        g = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x, exact=exact))
         weight.grad.add_(g)
     # dy / x were allocated on the main stream: the allocator may not hand their memory out again
     # before the side stream is done with them
@@ -88,23 +93,26 @@ def _wgrad_overlapped(dy, x, weight, flat):
     x.record_stream(side)
     opt, idx = flat
     opt._touched[idx] = True
-    if not _JOIN_PENDING[0]:
-        _JOIN_PENDING[0] = True
+    # one join per backward(): keyed on the running graph task, so a backward that raised before its
+    # callback ran cannot leave the flag stuck for the next one
+    task = torch._C._current_graph_task_id()
+    if _JOIN_PENDING[0] != task:
+        _JOIN_PENDING[0] = task
         torch.autograd.Variable._execution_engine.queue_callback(join_side_streams)
 
 
-def _packed(module, kind, dtype=torch.bfloat16):
+def _packed(module, kind, dtype=torch.bfloat16, exact=False):
     """Tensor-core operand layouts of a conv weight in the activation storage type, cached until
     the parameter changes."""
     w = module.weight
-    key = (w._version, _PARAM_EPOCH[0], w.data_ptr(), dtype)
+    key = (w._version, _PARAM_EPOCH[0], w.data_ptr(), dtype, exact)
     cache = getattr(module, "_pcrl_packed", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():
             if kind == "conv3":
-                pk = K.pack_conv3_weights(w.detach().contiguous(), dtype=dtype)
+                pk = K.pack_conv3_weights(w.detach().contiguous(), dtype=dtype, exact=exact)
             elif kind == "convT":
-                pk = K.pack_convT_weights(w.detach().contiguous(), dtype=dtype)
+                pk = K.pack_convT_weights(w.detach().contiguous(), dtype=dtype, exact=exact)
             elif kind == "head":    # (ds conv, final conv or None) -> wext [32,C], wextT [C,32]
                 raise ValueError("use _packed_head")
             else:
@@ -114,15 +122,16 @@ def _packed(module, kind, dtype=torch.bfloat16):
     return cache[1]
 
 
-def _packed_head(ds, fin, dtype=torch.bfloat16):
+def _packed_head(ds, fin, dtype=torch.bfloat16, exact=False):
     """bf16 GEMM operands of the 1-channel head convolutions (deep-supervision conv [+ 1x1x1 output
     conv]), cached until either weight changes."""
-    key = (ds.weight._version, ds.weight.data_ptr(), _PARAM_EPOCH[0], dtype,
+    key = (ds.weight._version, ds.weight.data_ptr(), _PARAM_EPOCH[0], dtype, exact,
            None if fin is None else (fin.weight._version, fin.weight.data_ptr()))
     cache = getattr(ds, "_pcrl_head", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():
-            pk = K.head_pack_weights(ds.weight.detach(), None if fin is None else fin.weight.detach(), dtype=dtype)
+            pk = K.head_pack_weights(ds.weight.detach(), None if fin is None else fin.weight.detach(), dtype=dtype,
+                                     exact=exact)
         cache = (key, pk)
         ds._pcrl_head = cache
     return cache[1]
@@ -130,7 +139,8 @@ def _packed_head(ds, fin, dtype=torch.bfloat16):
 
 class _Cfg:
     """Static (non-tensor) configuration of one fused LUConv call."""
-    __slots__ = ("stem", "pool", "tail", "final", "act", "norm", "training", "conv", "bn", "ds", "fin", "up", "dtype")
+    __slots__ = ("stem", "pool", "tail", "final", "act", "norm", "training", "conv", "bn", "ds", "fin", "up", "dtype",
+                 "exact")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -148,14 +158,15 @@ class _LUConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, prelu, ds_w, ds_b, fin_w, fin_b, up_w, up_b, cfg):
         ctx.set_materialize_grads(False)
+        ex = bool(cfg.exact)
         per_sample = cfg.norm == "in"
         cout = weight.shape[0]
         use_batch_stats = cfg.training or per_sample
         x_coarse = None
         if cfg.up is not None:
-            wtf, _ = _packed(cfg.up, "convT", cfg.dtype)
+            wtf, _ = _packed(cfg.up, "convT", cfg.dtype, ex)
             x_coarse = x
-            x = K.convT_fprop(x, wtf, up_b.detach().contiguous())
+            x = K.convT_fprop(x, wtf, up_b.detach().contiguous(), exact=ex)
         if cfg.stem:
             n, _, d, h, w = x.shape
         else:
@@ -164,10 +175,11 @@ class _LUConvFn(torch.autograd.Function):
         stats = (torch.zeros((groups, cout, 2), dtype=torch.float64, device=x.device)
                  if use_batch_stats else None)
         if cfg.stem:
-            y = K.stem_conv_fprop(x.contiguous(), weight.detach().contiguous(), stats, per_sample, dtype=cfg.dtype)
+            y = K.stem_conv_fprop(x.contiguous(), weight.detach().contiguous(), stats, per_sample, dtype=cfg.dtype,
+                                  exact=ex)
         else:
-            wf, _ = _packed(cfg.conv, "conv3", cfg.dtype)
-            y = K.conv3d_k3_fprop(x, wf, stats, per_sample)
+            wf, _ = _packed(cfg.conv, "conv3", cfg.dtype, ex)
+            y = K.conv3d_k3_fprop(x, wf, stats, per_sample, exact=ex)
         if use_batch_stats:
             count = d * h * w * (1 if per_sample else n)
             bn = cfg.bn
@@ -185,13 +197,13 @@ class _LUConvFn(torch.autograd.Function):
             mean, invstd = mean.contiguous(), invstd.contiguous()
         slope = prelu.detach() if prelu is not None else None
         a, pooled, avg = K.norm_act_fwd(y, scale, shift, cfg.act, slope, want_full=not cfg.pool,
-                                        want_pool=cfg.pool, want_avg=cfg.tail, per_sample=per_sample)
+                                        want_pool=cfg.pool, want_avg=cfg.tail, per_sample=per_sample, exact=ex)
         outs = [pooled if cfg.pool else a]
         if cfg.tail:
-            wext, _ = _packed_head(cfg.ds, cfg.fin, cfg.dtype)
+            wext, _ = _packed_head(cfg.ds, cfg.fin, cfg.dtype, ex)
             st1 = torch.zeros((groups, 1, 2), dtype=torch.float64, device=x.device)
             y1, y0 = K.head_fwd(a, wext, ds_b.detach(), fin_b.detach() if cfg.final else None,
-                                st1, per_sample)
+                                st1, per_sample, exact=ex)
             # the kernel accumulates sums; hand autograd the MEAN so that the incoming gradient is
             # dL/d(mean), which is what norm_act_bwd expects for its gavg argument
             outs += [avg * (1.0 / float(d * h * w)), y1, st1]
@@ -207,6 +219,7 @@ class _LUConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out, g_avg=None, g_y1=None, _g_st1=None, g_y0=None):
         cfg = ctx.cfg
+        ex = bool(cfg.exact)
         x, y, scale, shift, mean, invstd, gamma, prelu, a, ds_w, fin_w, x_coarse = ctx.saved_tensors
         n, d, h, w, cout = ctx.dims
         per_sample = cfg.norm == "in"
@@ -216,8 +229,8 @@ class _LUConvFn(torch.autograd.Function):
             dy1 = g_y1.contiguous() if g_y1 is not None else torch.zeros(
                 (n, 1, d, h, w), dtype=torch.float32, device=y.device)
             dy0 = g_y0.contiguous() if (cfg.final and g_y0 is not None) else None
-            _, wext_t = _packed_head(cfg.ds, cfg.fin, cfg.dtype)
-            g2, dwext = K.head_bwd(a, dy1, dy0, wext_t)
+            _, wext_t = _packed_head(cfg.ds, cfg.fin, cfg.dtype, ex)
+            g2, dwext = K.head_bwd(a, dy1, dy0, wext_t, exact=ex)
             if g_y1 is not None:
                 grads[6] = dwext[:, :27].reshape(1, cout, 3, 3, 3)
                 grads[7] = dy1.sum().reshape(1)
@@ -230,7 +243,7 @@ class _LUConvFn(torch.autograd.Function):
         gavg = g_avg.contiguous() if g_avg is not None else None
         dy, sums = K.norm_act_bwd(y, g1, g2, gavg, scale, shift, mean, invstd, gamma.detach(), cfg.act,
                                   prelu.detach() if prelu is not None else None, pool=cfg.pool,
-                                  per_sample=per_sample)
+                                  per_sample=per_sample, batch_stats=cfg.training or per_sample, exact=ex)
         sums = sums.sum(0).float()
         grads[3] = sums[:, 1].contiguous()          # d gamma
         grads[4] = sums[:, 0].contiguous()          # d beta
@@ -238,25 +251,25 @@ class _LUConvFn(torch.autograd.Function):
             grads[5] = sums[:, 2].contiguous()
         grads[2] = torch.zeros(cout, dtype=torch.float32, device=y.device)  # conv bias: exactly 0
         if cfg.stem:
-            grads[1] = K.stem_conv_wgrad_gemm(dy, x)
+            grads[1] = K.stem_conv_wgrad_gemm(dy, x, exact=ex)
         else:
-            _, wd = _packed(cfg.conv, "conv3", cfg.dtype)
+            _, wd = _packed(cfg.conv, "conv3", cfg.dtype, ex)
             flat = _overlap_target(cfg.conv.weight)
             if flat is not None:
-                _wgrad_overlapped(dy, x, cfg.conv.weight, flat)      # grads[1] stays None: added in place
+                _wgrad_overlapped(dy, x, cfg.conv.weight, flat, ex)  # grads[1] stays None: added in place
             else:
-                grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x))
+                grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x, exact=ex))
             if cfg.up is not None:
                 # data gradient lands coarse-major; its column sums are the ConvTranspose bias gradient
-                scratch, colsum = K.conv3d_k3_dgrad_unshuffled(dy, wd)
-                _, wtd = _packed(cfg.up, "convT", cfg.dtype)
-                dxc, dwt = K.convT_bwd_from_scratch(scratch, x_coarse, wtd, need_dx=ctx.needs_input_grad[0])
+                scratch, colsum = K.conv3d_k3_dgrad_unshuffled(dy, wd, exact=ex)
+                _, wtd = _packed(cfg.up, "convT", cfg.dtype, ex)
+                dxc, dwt = K.convT_bwd_from_scratch(scratch, x_coarse, wtd, need_dx=ctx.needs_input_grad[0], exact=ex)
                 cin_t, cout_t = cfg.up.weight.shape[0], cfg.up.weight.shape[1]
                 grads[0] = dxc
                 grads[10] = K.unpack_convT_wgrad(dwt, cin_t, cout_t)
                 grads[11] = colsum[:, 0].float().contiguous()
             elif ctx.needs_input_grad[0]:
-                grads[0] = K.conv3d_k3_dgrad(dy, wd)
+                grads[0] = K.conv3d_k3_dgrad(dy, wd, exact=ex)
         return tuple(grads)
 
 
@@ -282,6 +295,7 @@ class _Chan1NormSigmoidFn(torch.autograd.Function):
             shift = (beta.detach().reshape(1, 1) - mean * scale).contiguous()
         mask = K.chan1_sigmoid_fwd(y1, scale, shift, per_sample)
         ctx.per_sample = per_sample
+        ctx.batch_stats = training or per_sample
         ctx.save_for_backward(y1, mask, mean, invstd, gamma)
         return mask
 
@@ -289,7 +303,7 @@ class _Chan1NormSigmoidFn(torch.autograd.Function):
     def backward(ctx, dmask):
         y1, mask, mean, invstd, gamma = ctx.saved_tensors
         dy, sums = K.chan1_sigmoid_bwd(y1, mask, dmask.contiguous(), mean, invstd, gamma.detach(),
-                                       ctx.per_sample)
+                                       ctx.per_sample, batch_stats=ctx.batch_stats)
         sums = sums.sum(0).float()
         return dy, sums[1].reshape(1), sums[0].reshape(1), None, None, None, None
 
@@ -346,12 +360,13 @@ class LUConv(nn.Module):
         self.act, self.norm = act, norm
         self.in_chan, self.out_chan = in_chan, out_chan
 
-    def run(self, x, pool=False, tail=None, final=None, up=None, dtype=torch.bfloat16):
+    def run(self, x, pool=False, tail=None, final=None, up=None, dtype=torch.bfloat16, exact=False):
         """x: fp32 (N,1,D,H,W) for the stem, otherwise an H-padded activation in ``dtype``.
-        ``up``: the ConvTranspose3d module to apply to x first (UpTransition)."""
+        ``up``: the ConvTranspose3d module to apply to x first (UpTransition).
+        ``exact``: 3xTF32 split operands on unrounded fp32 storage (precision='fp32x3')."""
         cfg = _Cfg(stem=self.in_chan == 1, pool=pool, tail=tail is not None, final=final is not None,
                    act=self.act, norm=self.norm, training=self.training, conv=self.conv1, bn=self.bn1,
-                   ds=tail.conv1 if tail is not None else None, fin=final, up=up, dtype=dtype)
+                   ds=tail.conv1 if tail is not None else None, fin=final, up=up, dtype=dtype, exact=exact)
         prelu = self.activation.weight if self.act == "prelu" else None
         return _LUConvFn.apply(
             x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, prelu,
@@ -385,8 +400,8 @@ class DownTransition(nn.Module):
         super().__init__()
         self.ops = _make_nConv(in_channel, depth, act, norm)
 
-    def run(self, x, pool, dtype=torch.bfloat16):
-        return self.ops[1].run(self.ops[0].run(x, dtype=dtype)[0], pool=pool, dtype=dtype)[0]
+    def run(self, x, pool, dtype=torch.bfloat16, exact=False):
+        return self.ops[1].run(self.ops[0].run(x, dtype=dtype, exact=exact)[0], pool=pool, dtype=dtype, exact=exact)[0]
 
 
 class UpTransition(nn.Module):
@@ -406,9 +421,9 @@ class UpTransition(nn.Module):
         self.deep_supervision_head = LUConv(channels, 1, "sigmoid", norm)
         self.norm = norm
 
-    def run(self, x, final=None, dtype=torch.bfloat16):
-        h = self.ops[0].run(x, up=self.up_conv, dtype=dtype)[0]
-        outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final, dtype=dtype)
+    def run(self, x, final=None, dtype=torch.bfloat16, exact=False):
+        h = self.ops[0].run(x, up=self.up_conv, dtype=dtype, exact=exact)[0]
+        outs = self.ops[1].run(h, tail=self.deep_supervision_head, final=final, dtype=dtype, exact=exact)
         a, avg, y1, st1 = outs[0], outs[1], outs[2], outs[3]
         y0 = outs[4] if final is not None else None
         # projection (BatchNorm1d) and prediction (Linear-BN-ReLU-Linear) heads, reference :54-58,67-69:
@@ -432,15 +447,20 @@ class OutputTransition(nn.Module):
 
 class PCRLv23d(nn.Module):
     def __init__(self, n_class=1, act="relu", norm="bn", in_channels=1, low_dim=128, student=False,
-                 precision="bf16"):
+                 precision="fp32"):
         """Same arguments as the reference (:98) plus ``precision``: the storage type of the
-        activations between kernels.  ``"bf16"`` (default): bf16 storage, bf16 tensor-core operands.
-        ``"fp32"``: fp32 storage, TF32 tensor-core operands -- what the reference itself runs on an
-        Ampere-or-newer GPU (torch's default ``cudnn.allow_tf32``).  fp32 accumulation, statistics
-        and parameters in both."""
+        activations between kernels.  ``"fp32"`` (default, = the reference's default): fp32 storage,
+        TF32 tensor-core operands -- what the reference itself runs on an Ampere-or-newer GPU (torch's
+        default ``cudnn.allow_tf32``).  ``"bf16"``: bf16 storage, bf16 tensor-core operands (what
+        ``--amp`` selects, reference train_3d.py:52-53).  ``"fp32x3"``: fp32 storage without the tf32
+        rounding and every tensor-core product evaluated as three TF32 products of split operands
+        (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo): fp32-equivalent arithmetic -- what the reference computes
+        with ``allow_tf32=False`` -- at about a third of the speed; the mode in which parity with the
+        fp32 reference is asserted to 1e-3 (tests/test_step_gpu.py).  fp32 accumulation, statistics
+        and parameters in all three."""
         super().__init__()
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision not in ("bf16", "fp32", "fp32x3"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp32x3'")
         self.precision = precision
         if in_channels != 1:
             raise NotImplementedError("in_channels must be 1 (CT sub-volumes, the reference default)")
@@ -462,14 +482,15 @@ class PCRLv23d(nn.Module):
         if x.dim() != 5 or x.shape[1] != 1 or any(s % 8 for s in x.shape[2:]):
             raise ValueError("expected (B,1,D,H,W) with D,H,W multiples of 8, got %s" % (tuple(x.shape),))
         x = x.float().contiguous()
-        dt = torch.float32 if self.precision == "fp32" else torch.bfloat16
-        h = self.down_tr64.run(x, pool=True, dtype=dt)
-        h = self.down_tr128.run(h, pool=True, dtype=dt)
-        h = self.down_tr256.run(h, pool=True, dtype=dt)
-        h = self.down_tr512.run(h, pool=False, dtype=dt)
-        h, pro_256, pre_256, m256, _ = self.up_tr256.run(h, dtype=dt)
-        h, pro_128, pre_128, m128, _ = self.up_tr128.run(h, dtype=dt)
-        h, pro_64, pre_64, m64, y0 = self.up_tr64.run(h, final=self.out_tr.final_conv, dtype=dt)
+        dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        ex = self.precision == "fp32x3"
+        h = self.down_tr64.run(x, pool=True, dtype=dt, exact=ex)
+        h = self.down_tr128.run(h, pool=True, dtype=dt, exact=ex)
+        h = self.down_tr256.run(h, pool=True, dtype=dt, exact=ex)
+        h = self.down_tr512.run(h, pool=False, dtype=dt, exact=ex)
+        h, pro_256, pre_256, m256, _ = self.up_tr256.run(h, dtype=dt, exact=ex)
+        h, pro_128, pre_128, m128, _ = self.up_tr128.run(h, dtype=dt, exact=ex)
+        h, pro_64, pre_64, m64, y0 = self.up_tr64.run(h, final=self.out_tr.final_conv, dtype=dt, exact=ex)
         middle_masks = []
         if not local:
             middle_masks.append(Fn.upsample_trilinear(m256, 4))

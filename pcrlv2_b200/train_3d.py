@@ -234,7 +234,7 @@ def train_pcrlv2_inner(args, epoch, train_loader, model, optimizer, criterion, c
         loss, loss1, loss2, local_loss = pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch,
                                                           criterion, cosine)
         # ===================backward=====================
-        if epoch > 10 and loss > 1000:   # same test as the reference (:140); ordered to avoid a host sync early on
+        if epoch > 10 and _skip_step(loss):   # reference :140; ordered to avoid a host sync early on
             print('skip the step')
             continue
         optimizer.zero_grad()
@@ -260,6 +260,19 @@ def train_pcrlv2_inner(args, epoch, train_loader, model, optimizer, criterion, c
     return mg_loss_meter.avg, prob_meter.avg
 
 
+def _skip_step(loss):
+    """``loss > 1000`` of reference train_3d.py:140, decided on the GLOBAL-batch loss: under
+    nn.DataParallel the reference has one loss over the whole batch; with one process per GPU every
+    rank must take the same branch (a rank that skipped would leave the others' gradient all-reduce
+    without a partner), so the shard losses are averaged over the ranks first -- equal shards, every
+    term a batch mean, hence exactly the DataParallel loss."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        g = loss.detach().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return bool(g.item() / dist.get_world_size() > 1000)
+    return bool(loss > 1000)
+
+
 def _rank():
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
@@ -279,15 +292,19 @@ def train_pcrlv2_3d(args, data_loader, out_channel=3):
     checkpoint at epoch % 100 == 0 or epoch == 240 with the reference's dict / file name."""
     train_loader = data_loader['train']
     rank, world, dev = init_distributed()
-    model = PCRLv23d().to(dev)
+    # precision follows the reference's switch (train_3d.py:52-53, main.py:39): fp32 storage / TF32
+    # tensor-core operands by default (what the reference's cuDNN convolutions compute under torch's
+    # default allow_tf32), bf16 storage + operands under --amp (apex O1 runs the convolutions in half
+    # precision; bf16 needs no loss scaling)
+    precision = "bf16" if getattr(args, "amp", False) else "fp32"
+    model = PCRLv23d(precision=precision).to(dev)
+    if rank == 0:
+        print("precision: %s (%s)" % (precision, "--amp" if precision == "bf16" else "default; --amp selects bf16"))
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, src=0)
     optimizer = FlatSGD(model.parameters(), lr=args.lr, momentum=float(args.momentum),
                         weight_decay=float(args.weight_decay))
-    if getattr(args, "amp", False) and rank == 0:
-        print("--amp: activations are already bf16 with fp32 accumulation/statistics/parameters; "
-              "no loss scaling is needed")
     criterion = nn.MSELoss().to(dev)
     cosine = nn.CosineSimilarity().to(dev)
     for epoch in range(0, args.epochs + 1):
