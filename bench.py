@@ -198,9 +198,10 @@ def make_batch(B, seed, pinned):
             [t((B, 1) + LOCAL) for _ in range(6)])
 
 
-def measure(args, precision, host, rank, world, dev, full):
-    """Times K device-resident steps at `precision`; with full=True also the end-to-end leg and
-    the instrumented per-kernel step.  Returns a dict (meaningful on every rank; rank 0 prints)."""
+def measure(args, precision, host, rank, world, dev):
+    """One precision mode, every rank: K device-resident steps (the product path = the captured-graph
+    step unless --eager), the end-to-end leg through train_pcrlv2_inner, the eager step beside it, and
+    one instrumented eager step for the per-kernel breakdown.  Returns a dict (rank 0 prints)."""
     import torch.distributed as dist
     from pcrlv2_b200 import _lib
     from pcrlv2_b200 import train_3d as T
@@ -218,17 +219,56 @@ def measure(args, precision, host, rank, world, dev, full):
     crit, cos = torch.nn.MSELoss(), torch.nn.CosineSimilarity()
     resident = [(b[0].to(dev), b[1].to(dev), b[2].to(dev), [v.to(dev) for v in b[4]]) for b in host]
 
-    def device_step(i):
+    def eager_step(i):
         x1, x2, gt, lv = resident[i % nbatches]
         loss, _, _, _ = T.pcrlv2_step_loss(model, x1, x2, gt, lv, 0, crit, cos)
         opt.zero_grad()
         loss.backward()
         opt.step()
 
+    gs = None
+    if not args.eager:
+        gs = T.graphed_step_for(model, opt, crit, cos, resident[0][0], resident[0][3])   # captures here
+
+    def graph_step(i):
+        x1, x2, gt, lv = resident[i % nbatches]
+        gs.load(x1, x2, gt, lv)          # device -> static input buffers of the graph (53.5 MB D2D)
+        gs.run(0)
+
+    device_step = eager_step if gs is None else graph_step
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def host_cost(step_fn):
+        # host time of one step with an EMPTY launch queue (sync before, none inside the bracket):
+        # when it approaches ms_per_step the job is host-bound
+        ts = []
+        for i in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step_fn(i)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        barrier()
+        h = torch.tensor([statistics.median(ts)], device=dev)
+        if world > 1:
+            dist.all_reduce(h, op=dist.ReduceOp.MAX)
+        return h.item()
 
     for i in range(args.warmup):
         device_step(i)
@@ -236,38 +276,16 @@ def measure(args, precision, host, rank, world, dev, full):
     sampler = ClockSampler(dev.index)
     sampler.start()
     _lib.launch_count[0] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        device_step(i)
-    e1.record()
-    barrier()
+    ms_total = timed(device_step, args.steps)
     clocks = sampler.stop()
-    launches = _lib.launch_count[0]
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = ms.item()
-    # host cost of one step: Python + ctypes + launches with an EMPTY launch queue (sync before, no sync
-    # inside the bracket); when this approaches ms_per_step the job is host-bound
-    host = []
-    for i in range(3):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        device_step(i)
-        host.append((time.perf_counter() - t0) * 1e3)
-    barrier()
-    host_ms = torch.tensor([statistics.median(host)], device=dev)
-    if world > 1:
-        dist.all_reduce(host_ms, op=dist.ReduceOp.MAX)
+    launches = gs.launches * args.steps if gs is not None else _lib.launch_count[0]
     out = {"value": world * B * args.steps / (ms_total / 1e3), "ms_per_step": ms_total / args.steps,
-           "gpu_launches": launches, "clocks": clocks, "precision": precision,
-           "host_ms_per_step": host_ms.item()}
-    if not full:
-        return out
+           "gpu_launches": launches, "launches_per_step": launches / args.steps, "clocks": clocks,
+           "precision": precision, "host_ms_per_step": host_cost(device_step),
+           "step": "eager (Python launches)" if gs is None else "CUDA graph replay (one cudaGraphLaunch per step)"}
 
-    # ---- end to end through the public trainer call: host (pinned) -> device copies every step,
-    # loss meters read back every step (train_pcrlv2_inner does .item() + synchronize)
+    # ---- end to end through the public trainer call: pinned host batches -> device copies every step,
+    # loss scalars read back every step
     import types
     targs = types.SimpleNamespace(lr=1e-3, momentum=0.9, weight_decay=1e-4, amp=False, epochs=240)
     k2 = max(3, args.steps // 2)
@@ -276,6 +294,8 @@ def measure(args, precision, host, rank, world, dev, full):
     _stdout = sys.stdout
     sys.stdout = open(os.devnull, "w")
     try:
+        if args.eager:
+            os.environ["PCRL_GRAPH"] = "0"
         t0 = time.perf_counter()
         T.train_pcrlv2_inner(targs, 0, loader, model, opt, crit, cos)
         torch.cuda.synchronize()
@@ -287,9 +307,26 @@ def measure(args, precision, host, rank, world, dev, full):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     h2d = sum(t.numel() * 4 for t in (host[0][0], host[0][1], host[0][2])) + sum(v.numel() * 4 for v in host[0][4])
     out["e2e"] = {"value": world * B * k2 / e2e_t.item(), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                  "d2h_bytes_per_step": 8, "steps": k2}
+                  "d2h_bytes_per_step": 16, "steps": k2}
 
-    # ---- per-kernel roofline: one instrumented step (events around every entry point).  Every
+    # ---- replicas in sync: after all those steps every rank must hold the same parameters (the
+    # multi-GPU correctness evidence: same draws, same all-reduced gradients, same update everywhere)
+    if world > 1:
+        chk = torch.stack([opt._flat_p.double().sum(), (opt._flat_p.double() ** 2).sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        out["replicas_in_sync"] = bool(all(torch.equal(allc[0], c) for c in allc))
+        out["param_checksum"] = [float(v) for v in allc[0]]
+
+    # ---- the eager step beside the graph replay (same kernels, launched from Python)
+    if gs is not None:
+        for i in range(2):
+            eager_step(i)
+        ke = max(3, args.steps // 3)
+        out["eager"] = {"ms_per_step": timed(eager_step, ke) / ke, "host_ms_per_step": host_cost(eager_step),
+                        "steps": ke}
+
+    # ---- per-kernel roofline: one instrumented EAGER step (events around every entry point).  Every
     # rank runs it (the step contains the gradient all-reduce); only rank 0 reports.
     # The weight-gradient kernels normally run on a side stream, concurrently with main-stream
     # kernels; event-bracketed durations would then include the time a kernel waits for SMs held by
@@ -300,7 +337,7 @@ def measure(args, precision, host, rank, world, dev, full):
     os.environ["PCRL_OVERLAP_WGRAD"] = "0"
     _lib.profile[0] = []
     try:
-        device_step(0)
+        eager_step(0)
         torch.cuda.synchronize()
     finally:
         prof, _lib.profile[0] = _lib.profile[0], None
@@ -319,7 +356,71 @@ def measure(args, precision, host, rank, world, dev, full):
             n_, d_, h_, w_, ci, co = ints[-7:-1]       # (..., N, D, H, W, Cin, Cout, dtype)
             d["flops"] += 2.0 * n_ * d_ * h_ * w_ * 27 * ci * co
     out["per"] = per
+    del gs, model, opt, resident
     return out
+
+
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full) of the dominant kernel's
+# largest launch (up_tr64.ops.0 forward at b=32) and its algorithmic bytes: CONSTANTS from the
+# committed capture profiles/r01c_ncu_tensor_kernels.md, not re-measured by a bench run
+NCU_TRAFFIC = {"bf16": (1.0910e9 + 0.5056e9, 1.640e9), "fp32": (2.1829e9 + 1.0389e9, 3.279e9)}
+
+
+def roofline_of(r, precision, peaks, peak_src, dev):
+    """Per-kernel roofline + breakdown of one measured precision mode."""
+    per = r["per"]
+    bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    extra = {}
+    if precision == "bf16":
+        peak = bf16_peak
+        src = peak_src + ", sustained bf16 (cuBLAS)"
+    else:
+        # kind::tf32 runs on the same tcgen05 datapath at K = 8 instead of 16 per instruction: its
+        # hardware rate is half the bf16 rate.  MEASURED_PEAKS.json has no TF32 entry, so the
+        # denominator is DERIVED; cuBLAS's TF32 GEMM is measured live beside it (it sits below the
+        # derived figure on this pool) and the larger of the two is used.
+        cublas_tf32 = measure_tf32_peak(dev)
+        peak = max(0.5 * bf16_peak, cublas_tf32)
+        src = ("DERIVED: max(half of the sustained bf16 peak [" + peak_src + "], cuBLAS TF32 8192^3 GEMM "
+               "measured live in this run for 1 s)")
+        extra = {"cublas_tf32_tflops_live": cublas_tf32, "half_bf16_sustained_tflops": 0.5 * bf16_peak}
+    traffic, algo_bytes = NCU_TRAFFIC[precision]
+    fam = ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_dgrad_unshuffled")
+    kmajor_ms = sum(per[k]["ms"] for k in fam if k in per)
+    kmajor_fl = sum(per[k]["flops"] for k in fam if k in per)
+    n_kmajor = sum(per[k]["n"] for k in fam if k in per)
+    achieved = kmajor_fl / (kmajor_ms / 1e3) / 1e12 if kmajor_ms > 0 else 0.0
+    w = per.get("pcrl_conv3d_k3_wgrad", {"ms": 0.0, "flops": 0.0, "n": 0})
+    conv_ms, conv_fl = kmajor_ms + w["ms"], kmajor_fl + w["flops"]
+    step_ms_prof = sum(d["ms"] for d in per.values())
+    breakdown = {k.replace("pcrl_", ""): {"ms": round(v["ms"], 3), "n": v["n"],
+                                          **({"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1),
+                                              "frac": round(v["flops"] / (v["ms"] / 1e3) / 1e12 / peak, 3)} if v["flops"] else {})}
+                 for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])}
+    fl = flops_per_sample()
+    roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak if peak else None, "traffic": traffic,
+            "traffic_note": ("CONSTANT from profiles/r01c_ncu_tensor_kernels.md (ncu --set full, dram__bytes_read.sum + "
+                             "dram__bytes_write.sum of this kernel's largest launch, up_tr64.ops.0 forward at b=32; "
+                             "algorithmic bytes %.3f GB); not re-measured by this run" % (algo_bytes / 1e9)),
+            **extra,
+            "kernel": "igemm_kmajor_kernel (3x3x3 conv forward + data gradient)",
+            "launches": n_kmajor, "kernel_ms_per_step": kmajor_ms,
+            "timing": "CUDA events around every launch of one serialised eager step (side-stream overlap off)",
+            "share_of_step": kmajor_ms / step_ms_prof if step_ms_prof else None,
+            "wgrad_kernel": {"kernel": "igemm_mnmajor_kernel (3x3x3 weight gradient)", "launches": w["n"],
+                             "achieved": w["flops"] / (w["ms"] / 1e3) / 1e12 if w["ms"] else None,
+                             "frac": w["flops"] / (w["ms"] / 1e3) / 1e12 / peak if w["ms"] and peak else None,
+                             "ms_per_step": w["ms"]},
+            "all_conv3_kernels": {"achieved": conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms else None,
+                                  "frac": conv_fl / (conv_ms / 1e3) / 1e12 / peak if conv_ms and peak else None,
+                                  "ms_per_step": conv_ms},
+            "whole_step": {"tflops": r["value"] / r.get("world", 1) * fl / 1e12,
+                           "frac_of_this_peak": r["value"] / r.get("world", 1) * fl / 1e12 / peak if peak else None,
+                           "frac_of_bf16_burst_peak": (r["value"] / r.get("world", 1) * fl / 1e12 / peaks["bf16_tflops"]
+                                                       if peaks.get("bf16_tflops") else None)},
+            "peak_source": src}
+    return roof, breakdown
 
 
 def run_ours(args):
@@ -333,52 +434,24 @@ def run_ours(args):
     host = [make_batch(B, 1000 * rank + i, True) for i in range(2)]
     main_p = args.precision
     other_p = "bf16" if main_p == "fp32" else "fp32"
-    r = measure(args, main_p, host, rank, world, dev, True)
+    import gc
+    r = measure(args, main_p, host, rank, world, dev)
+    r["world"] = world
+    gc.collect()
     torch.cuda.empty_cache()
     also = None
     if not args.no_also:
-        also = measure(args, other_p, host, rank, world, dev, False)
+        also = measure(args, other_p, host, rank, world, dev)
+        also["world"] = world
+        gc.collect()
         torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    per = r["per"]
     peaks, peak_src = measured_peaks()
-    bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    extra = {}
-    if main_p == "bf16":
-        peak = bf16_peak
-        peak_src += ", sustained bf16"
-    else:
-        # kind::tf32 runs on the same tcgen05 datapath at K = 8 instead of 16 per instruction: its
-        # hardware rate is half the bf16 rate.  cuBLAS's TF32 GEMM is measured live beside it (it sits
-        # below that figure on this pool); the larger of the two is the denominator.
-        cublas_tf32 = measure_tf32_peak(dev)
-        peak = max(0.5 * bf16_peak, cublas_tf32)
-        peak_src = ("max(half of the sustained bf16 peak [" + peak_src + "], cuBLAS TF32 8192^3 GEMM measured "
-                    "live in this run for 1 s)")
-        extra = {"cublas_tf32_tflops_live": cublas_tf32, "half_bf16_sustained_tflops": 0.5 * bf16_peak}
-    # DRAM bytes of the dominant kernel's largest launch (up_tr64.ops.0 forward at b=32) from the
-    # committed ncu --set full capture: equal to its algorithmic bytes (read x once, write y once)
-    traffic = {"bf16": 1.0910e9 + 0.5056e9, "fp32": 2.1829e9 + 1.0389e9}[main_p]
-    traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of this kernel "
-                    "(up_tr64.ops.0 forward, b=32; algorithmic bytes %.3f GB), profiles/r01c_ncu_tensor_kernels.md"
-                    % ({"bf16": 1.640, "fp32": 3.279}[main_p]))
-    fam = ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_dgrad_unshuffled")
-    kmajor_ms = sum(per[k]["ms"] for k in fam if k in per)
-    kmajor_fl = sum(per[k]["flops"] for k in fam if k in per)
-    n_kmajor = sum(per[k]["n"] for k in fam if k in per)
-    achieved = kmajor_fl / (kmajor_ms / 1e3) / 1e12 if kmajor_ms > 0 else 0.0
-    conv_fam = fam + ("pcrl_conv3d_k3_wgrad",)
-    conv_ms = sum(per[k]["ms"] for k in conv_fam if k in per)
-    conv_fl = sum(per[k]["flops"] for k in conv_fam if k in per)
-    step_ms_prof = sum(d["ms"] for d in per.values())
-    breakdown = {k.replace("pcrl_", ""): {"ms": round(v["ms"], 3), "n": v["n"],
-                                          **({"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)} if v["flops"] else {})}
-                 for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])}
-
+    roof, breakdown = roofline_of(r, main_p, peaks, peak_src, dev)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, cms, sample = cpu_oracle_rate(2, 2, 1)
@@ -386,41 +459,49 @@ def run_ours(args):
 
     fl = flops_per_sample()
     value = r["value"]
+    config = {"workload": WORKLOADS[main_p].format(B=B),
+              "global_batch": world * B, "parallelism": f"dp{world}",
+              "l2": "activation working set per step is tens of GB >> 126 MB L2; two input batches alternate",
+              "algorithmic_gflop_per_sample": round(fl / 1e9, 2), "step": r["step"]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if main_p == "bf16" else "tf32",
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[main_p].format(B=B),
-                   "global_batch": world * B, "parallelism": f"dp{world}",
-                   "l2": "activation working set per step is tens of GB >> 126 MB L2; two input batches alternate",
-                   "algorithmic_gflop_per_sample": round(fl / 1e9, 2)},
+        "config": config,
         "overall_tflops": value * fl / 1e12,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "traffic_note": traffic_note, **extra,
-                     "kernel": "igemm_kmajor_kernel (3x3x3 conv forward + data gradient)",
-                     "launches": n_kmajor, "kernel_ms_per_step": kmajor_ms,
-                     "timing": "CUDA events around every launch of one serialised step (side-stream overlap off)",
-                     "share_of_step": kmajor_ms / step_ms_prof if step_ms_prof else None,
-                     "all_conv3_kernels": {"achieved": conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms else None,
-                                           "frac": conv_fl / (conv_ms / 1e3) / 1e12 / peak if conv_ms and peak else None,
-                                           "ms_per_step": conv_ms},
-                     "peak_source": peak_src},
+        "roofline": roof,
         "kernel_breakdown_ms": breakdown,
         "cpu_baseline": cpu,
         "e2e": r["e2e"],
         "gpu_launches": r["gpu_launches"],
-        "launches_per_step": r["gpu_launches"] / args.steps,
+        "launches_per_step": r["launches_per_step"],
         "host_ms_per_step": r["host_ms_per_step"],
+        "eager_step": r.get("eager"),
         "clocks": r["clocks"],
     }
+    if world > 1:
+        line["replicas_in_sync"] = r.get("replicas_in_sync")
+        config["replicas_in_sync"] = r.get("replicas_in_sync")
     if also is not None:
-        line["also"] = {"dtype": "bf16" if other_p == "bf16" else "tf32",
-                        "workload": WORKLOADS[other_p].format(B=B), "value": also["value"], "unit": UNIT,
-                        "ms_per_step": also["ms_per_step"], "host_ms_per_step": also["host_ms_per_step"],
-                        "overall_tflops": also["value"] * fl / 1e12,
-                        "clocks": also["clocks"]}
+        roof2, breakdown2 = roofline_of(also, other_p, peaks, peak_src, dev)
+        second = {"dtype": "bf16" if other_p == "bf16" else "tf32",
+                  "workload": WORKLOADS[other_p].format(B=B), "value": also["value"], "unit": UNIT,
+                  "ms_per_step": also["ms_per_step"], "host_ms_per_step": also["host_ms_per_step"],
+                  "launches_per_step": also["launches_per_step"], "e2e": also["e2e"],
+                  "eager_step": also.get("eager"), "overall_tflops": also["value"] * fl / 1e12,
+                  "replicas_in_sync": also.get("replicas_in_sync"), "clocks": also["clocks"]}
+        line["also"] = {**second, "roofline": roof2, "kernel_breakdown_ms": breakdown2}
+        # the same numbers inside keys the driver's record keeps (it drops unknown top-level keys):
+        # the per-GPU shard of configs[2] and its roofline
+        key = "configs2_bf16_shard" if other_p == "bf16" else "configs1_fp32"
+        config[key] = {k: second[k] for k in ("value", "unit", "ms_per_step", "host_ms_per_step", "overall_tflops",
+                                              "replicas_in_sync")}
+        config[key]["e2e_value"] = also["e2e"]["value"]
+        roof[other_p] = {k: roof2[k] for k in ("achieved", "peak", "frac", "unit", "kernel_ms_per_step", "share_of_step",
+                                               "wgrad_kernel", "all_conv3_kernels", "whole_step", "peak_source")}
+        roof[other_p]["kernel_breakdown_ms"] = breakdown2
+    roof["kernel_breakdown_ms"] = breakdown
     print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -437,6 +518,8 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["bf16", "fp32"],
                     help="activation storage / tensor-core operand type of the headline measurement "
                          "(fp32 = fp32 storage + TF32 MMAs: configs[1]; bf16: configs[2] shard)")
+    ap.add_argument("--eager", action="store_true",
+                    help="time the eager step (Python launches) instead of the captured CUDA graph")
     ap.add_argument("--no-also", action="store_true",
                     help="skip the device-resident measurement at the other precision ('also' key)")
     args = ap.parse_args()

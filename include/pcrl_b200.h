@@ -187,6 +187,21 @@ int pcrl_cosine_mean_fwd_bwd(const float* x, const float* y, float* mean_out, fl
 int pcrl_mse_fwd(const float* p, const float* t, float* out, long long n, void* stream);
 /* dp = g[0] * 2 (p - t) / n, g = upstream gradient (device scalar) */
 int pcrl_mse_bwd(const float* p, const float* t, const float* g, float* dp, long long n, void* stream);
+/* the same MSE terms multiplied by a DEVICE scalar `weight` (beta * [drawn scale == this scale] of the
+ * deep-supervision term, train_3d.py:136-137): lets a captured CUDA graph of the step evaluate all
+ * three scales with the drawn one selected by data */
+int pcrl_mse_scaled_fwd(const float* p, const float* t, const float* weight, float* out, long long n,
+                        void* stream);
+int pcrl_mse_scaled_bwd(const float* p, const float* t, const float* g, const float* weight, float* dp,
+                        long long n, void* stream);
+/* All 1 + 2*n_local cos_loss terms of one step (train_3d.py:86-92,119,124-133) and their gradients
+ * wrt the prediction-head outputs in one launch; the drawn scale of every term is read from device
+ * memory (draws[0]: global term; draws[1+2i], draws[2+2i]: decoder 1 / decoder 2 against local view
+ * i).  ptrs: HOST array of 27 device pointers, scale-major triples in the order pre1, pro1, pre2,
+ * pro2 ([B][C_s]), preL, proL ([n_local*B][C_s]), dpre1, dpre2, dpreL (outputs, fully written);
+ * channels: HOST int[3] (C_s <= 256).  out2[0] += loss2, out2[1] += local_loss. */
+int pcrl_contrastive_fwd_bwd(const void* const* ptrs, const int* channels, int B, int n_local,
+                             const int* draws, float* out2, float eps, void* stream);
 /* torch.sigmoid of the 1-channel output volume (models/pcrlv2_model_3d.py:79,132) and its autograd */
 int pcrl_sigmoid_fwd(const float* x, float* y, long long n, void* stream);
 int pcrl_sigmoid_bwd(const float* y, const float* dy, float* dx, long long n, void* stream);
@@ -215,6 +230,14 @@ int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf,
                   const long long* seg_offsets, const int* seg_active, const int* seg_first,
                   int nseg, float lr, float momentum, float weight_decay, float grad_scale,
                   void* stream);
+
+/* the same update with the scalars in DEVICE memory, hyper = [lr, momentum, weight_decay, grad_scale,
+ * skip_threshold] (utils.py:111-114 changes lr per epoch; a captured graph must not bake it in).
+ * guard (nullable): device scalar = loss summed over the ranks; nothing is updated when
+ * guard[0]*grad_scale > skip_threshold (train_3d.py:140-142, same decision on every rank). */
+int pcrl_sgd_flat_dev(float* params, const float* grads, float* momentum_buf,
+                      const long long* seg_offsets, const int* seg_active, const int* seg_first,
+                      int nseg, const float* hyper, const float* guard, void* stream);
 
 #ifdef __cplusplus
 }

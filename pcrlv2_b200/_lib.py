@@ -52,6 +52,10 @@ SIGNATURES = {
     "pcrl_gemm_tn": [_P, _P, _P, _L, _I, _I, _I, _P],
     "pcrl_sgd_flat": [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _P],
     "pcrl_split3_tf32": [_P, _P, _L, _I, _I, _I, _P],
+    "pcrl_mse_scaled_fwd": [_P, _P, _P, _P, _L, _P],
+    "pcrl_mse_scaled_bwd": [_P, _P, _P, _P, _P, _L, _P],
+    "pcrl_contrastive_fwd_bwd": [_P, _P, _I, _I, _P, _P, _F, _P],
+    "pcrl_sgd_flat_dev": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "pcrl_bn1d_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     "pcrl_bn1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pcrl_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],

@@ -51,8 +51,10 @@ int bn1d_bwd(const float*, const float*, const float*, const float*, const float
 int linear_fwd(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int linear_bwd(const float*, const float*, const float*, float*, float*, float*, int, int, int, cudaStream_t);
 int cosine_mean_fwd_bwd(const float*, const float*, float*, float*, int, int, float, float, cudaStream_t);
-int mse_fwd(const float*, const float*, float*, long long, cudaStream_t);
-int mse_bwd(const float*, const float*, const float*, float*, long long, cudaStream_t);
+int mse_fwd(const float*, const float*, float*, long long, const float*, cudaStream_t);
+int mse_bwd(const float*, const float*, const float*, float*, long long, const float*, cudaStream_t);
+int contrastive_fwd_bwd(const void* const*, const int*, int, int, const int*, float*, float, cudaStream_t);
+int sgd_flat_dev(float*, const float*, float*, const long long*, const int*, const int*, int, const float*, const float*, cudaStream_t);
 int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
 int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int upsample_trilinear_fwd(const float*, float*, int, int, int, int, int, cudaStream_t);
@@ -259,11 +261,25 @@ int pcrl_cosine_mean_fwd_bwd(const float* x, const float* y, float* mean_out, fl
 }
 int pcrl_mse_fwd(const float* p, const float* t, float* out, long long n, void* stream) {
   NONNULL(p); NONNULL(t); NONNULL(out);
-  return mse_fwd(p, t, out, n, ST(stream));
+  return mse_fwd(p, t, out, n, nullptr, ST(stream));
+}
+int pcrl_mse_scaled_fwd(const float* p, const float* t, const float* weight, float* out, long long n, void* stream) {
+  NONNULL(p); NONNULL(t); NONNULL(weight); NONNULL(out);
+  return mse_fwd(p, t, out, n, weight, ST(stream));
 }
 int pcrl_mse_bwd(const float* p, const float* t, const float* g, float* dp, long long n, void* stream) {
   NONNULL(p); NONNULL(t); NONNULL(g); NONNULL(dp);
-  return mse_bwd(p, t, g, dp, n, ST(stream));
+  return mse_bwd(p, t, g, dp, n, nullptr, ST(stream));
+}
+int pcrl_mse_scaled_bwd(const float* p, const float* t, const float* g, const float* weight, float* dp, long long n,
+                        void* stream) {
+  NONNULL(p); NONNULL(t); NONNULL(g); NONNULL(weight); NONNULL(dp);
+  return mse_bwd(p, t, g, dp, n, weight, ST(stream));
+}
+int pcrl_contrastive_fwd_bwd(const void* const* ptrs, const int* channels, int B, int n_local, const int* draws,
+                             float* out2, float eps, void* stream) {
+  NONNULL(ptrs); NONNULL(channels); NONNULL(draws); NONNULL(out2);
+  return contrastive_fwd_bwd(ptrs, channels, B, n_local, draws, out2, eps, ST(stream));
 }
 int pcrl_sigmoid_fwd(const float* x, float* y, long long n, void* stream) {
   NONNULL(x); NONNULL(y);
@@ -293,6 +309,14 @@ int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf, const 
   NONNULL(params); NONNULL(grads); NONNULL(momentum_buf); NONNULL(seg_offsets); NONNULL(seg_active); NONNULL(seg_first);
   return sgd_flat(params, grads, momentum_buf, seg_offsets, seg_active, seg_first, nseg, lr, momentum,
                   weight_decay, grad_scale, ST(stream));
+}
+
+int pcrl_sgd_flat_dev(float* params, const float* grads, float* momentum_buf, const long long* seg_offsets,
+                      const int* seg_active, const int* seg_first, int nseg, const float* hyper,
+                      const float* guard, void* stream) {
+  NONNULL(params); NONNULL(grads); NONNULL(momentum_buf); NONNULL(seg_offsets); NONNULL(seg_active); NONNULL(seg_first);
+  NONNULL(hyper);
+  return sgd_flat_dev(params, grads, momentum_buf, seg_offsets, seg_active, seg_first, nseg, hyper, guard, ST(stream));
 }
 
 }  // extern "C"

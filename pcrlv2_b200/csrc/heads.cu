@@ -291,6 +291,33 @@ sgd_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
   }
 }
 
+// The same update with every scalar read from DEVICE memory (a captured CUDA graph of the step must
+// not bake in the learning rate of one epoch): hyper = [lr, momentum, weight_decay, grad_scale,
+// skip_threshold].  guard (nullable): device scalar holding the (rank-summed) loss; the whole update is
+// skipped when guard[0] * grad_scale > skip_threshold -- the reference's `loss > 1000 and epoch > 10`
+// test (train_3d.py:140), decided identically on every rank.
+__global__ void __launch_bounds__(256)
+sgd_flat_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                    const long long* __restrict__ seg_off, const int* __restrict__ seg_active,
+                    const int* __restrict__ seg_first, int nseg, const float* __restrict__ hyper,
+                    const float* __restrict__ guard) {
+  const float lr = hyper[0], mu = hyper[1], wd = hyper[2], grad_scale = hyper[3];
+  if (guard && guard[0] * grad_scale > hyper[4]) return;
+  for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
+    if (!seg_active[s]) continue;
+    const long long b = seg_off[s], e = seg_off[s + 1];
+    const bool first = seg_first[s] != 0;
+    for (long long i = b + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e;
+         i += (long long)gridDim.x * blockDim.x) {
+      const float pv = p[i];
+      const float d = fmaf(wd, pv, g[i] * grad_scale);
+      const float m = first ? d : fmaf(mu, buf[i], d);
+      buf[i] = m;
+      p[i] = fmaf(-lr, m, pv);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ wrappers
 static inline unsigned blocks_for(long long items, int per_block, int cap) {
   long long b = (items + per_block - 1) / per_block;
@@ -353,6 +380,14 @@ int sgd_flat(float* p, const float* g, float* buf, const long long* seg_off, con
              cudaStream_t s) {
   dim3 grid(64, nseg < 256 ? nseg : 256);
   sgd_flat_kernel<<<grid, 256, 0, s>>>(p, g, buf, seg_off, seg_active, seg_first, nseg, lr, mu, wd, grad_scale);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+int sgd_flat_dev(float* p, const float* g, float* buf, const long long* seg_off, const int* seg_active,
+                 const int* seg_first, int nseg, const float* hyper, const float* guard, cudaStream_t s) {
+  dim3 grid(64, nseg < 256 ? nseg : 256);
+  sgd_flat_dev_kernel<<<grid, 256, 0, s>>>(p, g, buf, seg_off, seg_active, seg_first, nseg, hyper, guard);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

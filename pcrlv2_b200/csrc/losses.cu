@@ -254,10 +254,123 @@ int cosine_mean_fwd_bwd(const float* x, const float* y, float* mean_out, float* 
   return PCRL_OK;
 }
 
+// ------------------------------------------------------------------------------ fused contrastive terms
+// All 1 + 2*n_local cos_loss terms of one training step (train_3d.py:86-92,119,124-133) in ONE launch,
+// with the randomly drawn scale of every term read from DEVICE memory (draws[0] = global term, then
+// for view i: draws[1+2i] = (decoder 1, view i), draws[2+2i] = (decoder 2, view i)), so that a captured
+// CUDA graph of the step is independent of the draws.  One warp per row of a `pre` tensor (the only
+// tensors the reference differentiates through: the projections are detached), which loops over the
+// terms that involve it: the gradient of a row is written once, without atomics.
+//   out[0] += loss2      = -1/2 (mean cos(pre1_s, pro2_s) + mean cos(pre2_s, pro1_s)),  s = draws[0]
+//   out[1] += local_loss = 1/(2 n_local) sum_i [ -1/2 (mean cos(pre1_a, proL_a[i]) + mean cos(preL_a[i], pro1_a))
+//                                               -1/2 (mean cos(pre2_b, proL_b[i]) + mean cos(preL_b[i], pro2_b)) ]
+struct ContrastiveArgs {
+  const float* pre1[3]; const float* pro1[3]; const float* pre2[3]; const float* pro2[3];
+  const float* preL[3]; const float* proL[3];
+  float* dpre1[3]; float* dpre2[3]; float* dpreL[3];
+  int C[3];
+  int B, n_local;
+  const int* draws;
+  float* out;
+  float eps;
+};
+
+__device__ __forceinline__ void cos_term(const float (&xv)[8], float nx, const float* __restrict__ yr, int C, int lane,
+                                         float eps, float k, float (&gacc)[8], float& loss) {
+  float yv[8], dot = 0.f, ny = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = lane + 32 * j;
+    yv[j] = c < C ? yr[c] : 0.f;
+    dot = fmaf(xv[j], yv[j], dot);
+    ny = fmaf(yv[j], yv[j], ny);
+  }
+  dot = warp_sum(dot); ny = warp_sum(ny);
+  const float lx = fmaxf(sqrtf(nx), eps), ly = fmaxf(sqrtf(ny), eps);
+  const float inv = 1.f / (lx * ly);
+  const float cs = dot * inv;
+  const float kx = cs / (lx * lx);
+  loss += cs * k;
+#pragma unroll
+  for (int j = 0; j < 8; j++) gacc[j] = fmaf(k, yv[j] * inv - xv[j] * kx, gacc[j]);
+}
+
+__global__ void __launch_bounds__(256)
+contrastive_kernel(const ContrastiveArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int B = a.B, nl = a.n_local;
+  const int per_scale = B * (2 + nl);
+  if (wid >= 3 * per_scale) return;
+  const int s = wid / per_scale;
+  int r = wid % per_scale;
+  const int C = a.C[s];
+  const float kg = -0.5f / (float)B, kl = -0.5f / (float)B / (float)(2 * nl);
+  const float* xr;
+  float* dr;
+  int grp, b, view = 0;
+  if (r < B) { grp = 0; b = r; xr = a.pre1[s] + (size_t)b * C; dr = a.dpre1[s] + (size_t)b * C; }
+  else if (r < 2 * B) { grp = 1; b = r - B; xr = a.pre2[s] + (size_t)b * C; dr = a.dpre2[s] + (size_t)b * C; }
+  else { grp = 2; r -= 2 * B; view = r / B; b = r % B; xr = a.preL[s] + (size_t)r * C; dr = a.dpreL[s] + (size_t)r * C; }
+  float xv[8], gacc[8], nx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = lane + 32 * j;
+    xv[j] = c < C ? xr[c] : 0.f;
+    gacc[j] = 0.f;
+    nx = fmaf(xv[j], xv[j], nx);
+  }
+  nx = warp_sum(nx);
+  float lg = 0.f, ll = 0.f;
+  if (grp == 0) {
+    if (a.draws[0] == s) cos_term(xv, nx, a.pro2[s] + (size_t)b * C, C, lane, a.eps, kg, gacc, lg);
+    for (int i = 0; i < nl; i++)
+      if (a.draws[1 + 2 * i] == s) cos_term(xv, nx, a.proL[s] + ((size_t)i * B + b) * C, C, lane, a.eps, kl, gacc, ll);
+  } else if (grp == 1) {
+    if (a.draws[0] == s) cos_term(xv, nx, a.pro1[s] + (size_t)b * C, C, lane, a.eps, kg, gacc, lg);
+    for (int i = 0; i < nl; i++)
+      if (a.draws[2 + 2 * i] == s) cos_term(xv, nx, a.proL[s] + ((size_t)i * B + b) * C, C, lane, a.eps, kl, gacc, ll);
+  } else {
+    if (a.draws[1 + 2 * view] == s) cos_term(xv, nx, a.pro1[s] + (size_t)b * C, C, lane, a.eps, kl, gacc, ll);
+    if (a.draws[2 + 2 * view] == s) cos_term(xv, nx, a.pro2[s] + (size_t)b * C, C, lane, a.eps, kl, gacc, ll);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = lane + 32 * j;
+    if (c < C) dr[c] = gacc[j];
+  }
+  if (lane == 0) {
+    if (lg != 0.f) atomicAdd(&a.out[0], lg);
+    if (ll != 0.f) atomicAdd(&a.out[1], ll);
+  }
+}
+
+// ptrs: 27 device pointers in the order pre1[3], pro1[3], pre2[3], pro2[3], preL[3], proL[3], dpre1[3],
+// dpre2[3], dpreL[3] (scale index 0..2 = up_tr256, up_tr128, up_tr64)
+int contrastive_fwd_bwd(const void* const* ptrs, const int* C3, int B, int n_local, const int* draws,
+                        float* out2, float eps, cudaStream_t s) {
+  PCRL_REQUIRE(B >= 1 && n_local >= 1, "contrastive: bad dims");
+  ContrastiveArgs a;
+  for (int i = 0; i < 3; i++) {
+    PCRL_REQUIRE(C3[i] >= 1 && C3[i] <= 256, "contrastive: C=%d must be in 1..256", C3[i]);
+    a.C[i] = C3[i];
+    a.pre1[i] = (const float*)ptrs[0 + i]; a.pro1[i] = (const float*)ptrs[3 + i];
+    a.pre2[i] = (const float*)ptrs[6 + i]; a.pro2[i] = (const float*)ptrs[9 + i];
+    a.preL[i] = (const float*)ptrs[12 + i]; a.proL[i] = (const float*)ptrs[15 + i];
+    a.dpre1[i] = (float*)ptrs[18 + i]; a.dpre2[i] = (float*)ptrs[21 + i]; a.dpreL[i] = (float*)ptrs[24 + i];
+  }
+  for (int i = 0; i < 27; i++) PCRL_REQUIRE(ptrs[i] != nullptr, "contrastive: pointer %d is NULL", i);
+  a.B = B; a.n_local = n_local; a.draws = draws; a.out = out2; a.eps = eps;
+  const int warps = 3 * B * (2 + n_local);
+  contrastive_kernel<<<(warps + 7) / 8, 256, 0, s>>>(a);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
 // ------------------------------------------------------------------------------ MSE
 __global__ void __launch_bounds__(256)
 mse_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t, float* __restrict__ out, long long n,
-               float inv_n) {
+               float inv_n, const float* __restrict__ wgt) {
   __shared__ float red[8];
   float s = 0.f;
   const long long n4 = n >> 2;
@@ -279,14 +392,14 @@ mse_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t, float* 
     s = red[threadIdx.x];
 #pragma unroll
     for (int k = 4; k >= 1; k >>= 1) s += __shfl_xor_sync(0xffu, s, k);
-    if (threadIdx.x == 0) atomicAdd(out, s * inv_n);
+    if (threadIdx.x == 0) atomicAdd(out, s * inv_n * (wgt ? wgt[0] : 1.f));
   }
 }
 
 __global__ void __launch_bounds__(256)
 mse_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ g,
-               float* __restrict__ dp, long long n, float two_over_n) {
-  const float k = g[0] * two_over_n;
+               float* __restrict__ dp, long long n, float two_over_n, const float* __restrict__ wgt) {
+  const float k = g[0] * two_over_n * (wgt ? wgt[0] : 1.f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dp[i] = k * (p[i] - t[i]);
 }
@@ -298,17 +411,18 @@ static inline int blocks_for(long long n, int per_block, int cap) {
   return (int)b;
 }
 
-int mse_fwd(const float* p, const float* t, float* out, long long n, cudaStream_t s) {
+// wgt (nullable): device scalar multiplying the term (beta * one-hot of the drawn deep-supervision scale)
+int mse_fwd(const float* p, const float* t, float* out, long long n, const float* wgt, cudaStream_t s) {
   PCRL_REQUIRE(n >= 1, "mse_fwd: empty input");
   PCRL_REQUIRE((((uintptr_t)p | (uintptr_t)t) & 15) == 0, "mse_fwd: inputs must be 16-byte aligned");
-  mse_fwd_kernel<<<blocks_for(n, 1024 * 4, num_sms() * 4), 256, 0, s>>>(p, t, out, n, 1.f / (float)n);
+  mse_fwd_kernel<<<blocks_for(n, 1024 * 4, num_sms() * 4), 256, 0, s>>>(p, t, out, n, 1.f / (float)n, wgt);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
 
-int mse_bwd(const float* p, const float* t, const float* g, float* dp, long long n, cudaStream_t s) {
+int mse_bwd(const float* p, const float* t, const float* g, float* dp, long long n, const float* wgt, cudaStream_t s) {
   PCRL_REQUIRE(n >= 1, "mse_bwd: empty input");
-  mse_bwd_kernel<<<blocks_for(n, 1024, num_sms() * 8), 256, 0, s>>>(p, t, g, dp, n, 2.f / (float)n);
+  mse_bwd_kernel<<<blocks_for(n, 1024, num_sms() * 8), 256, 0, s>>>(p, t, g, dp, n, 2.f / (float)n, wgt);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

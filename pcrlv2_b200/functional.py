@@ -82,21 +82,70 @@ def cosine_mean(x, y, eps=1e-8, coef=1.0):
 
 class _MSEFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, p, t):
+    def forward(ctx, p, t, weight):
         p, t = p.contiguous(), t.contiguous()
-        ctx.save_for_backward(p, t)
-        return K.mse_fwd(p, t)
+        ctx.save_for_backward(p, t, weight)
+        return K.mse_fwd(p, t, weight)
 
     @staticmethod
     def backward(ctx, g):
-        p, t = ctx.saved_tensors
-        return K.mse_bwd(p, t, g.contiguous().float()), None
+        p, t, weight = ctx.saved_tensors
+        return K.mse_bwd(p, t, g.contiguous().float(), weight), None, None
 
 
-def mse_loss(pred, target):
+def mse_loss(pred, target, weight=None):
+    """nn.MSELoss()(pred, target) [* weight: a 1-element device tensor read by the kernels, so a
+    captured graph can switch the term on / off and scale it by data]."""
     if target.requires_grad:
         raise NotImplementedError("mse_loss: the target is a constant on this path")
-    return _MSEFn.apply(pred, target.to(pred.dtype))
+    return _MSEFn.apply(pred, target.to(pred.dtype), weight)
+
+
+class _ContrastiveFn(torch.autograd.Function):
+    """loss2 + local_loss of one step (reference train_3d.py:119,124-133) from the 18 projection /
+    prediction tensors, one launch forward+gradient (csrc/losses.cu:contrastive_kernel).
+
+    ``drawn`` (host tuple of the scales that occur in the draws, or None): with it the gradients of
+    the prediction tensors of scales NO term drew are returned as ``None`` -- the reference's graph
+    does not reach those heads at all and SGD then skips their parameters (SURVEY note N3).  ``None``
+    (captured-graph mode): every gradient is returned (zeros where nothing was drawn) and the caller
+    supplies the reached-parameter mask itself."""
+
+    @staticmethod
+    def forward(ctx, draws, drawn, *tensors):
+        pre1, pro1, pre2, pro2, pre_l, pro_l = (list(tensors[3 * i:3 * i + 3]) for i in range(6))
+        out, grads = K.contrastive_fwd_bwd([t.contiguous() for t in pre1], [t.detach().contiguous() for t in pro1],
+                                           [t.contiguous() for t in pre2], [t.detach().contiguous() for t in pro2],
+                                           [t.contiguous() for t in pre_l], [t.detach().contiguous() for t in pro_l],
+                                           draws)
+        ctx.drawn = drawn
+        ctx.save_for_backward(*(grads[0] + grads[1] + grads[2]))
+        parts = out.detach().clone()
+        ctx.mark_non_differentiable(parts)
+        return out.sum(), parts
+
+    @staticmethod
+    def backward(ctx, g, _gparts):
+        saved = ctx.saved_tensors
+        dpre1, dpre2, dpre_l = saved[0:3], saved[3:6], saved[6:9]
+
+        def sel(group):
+            return [None if (ctx.drawn is not None and s not in ctx.drawn) else group[s] * g for s in range(3)]
+        none3 = [None, None, None]
+        return (None, None, *sel(dpre1), *none3, *sel(dpre2), *none3, *sel(dpre_l), *none3)
+
+
+def contrastive_losses(dec1, dec2, dec_local, draws, drawn=None):
+    """dec*: [[pro, pre] x 3 scales] as returned by the model (local: rows = n_local * B, view-major).
+    Returns (loss2 + local_loss, parts [2] = (loss2, local_loss))."""
+    def pre(dec):
+        # a scale that no term drew must not enter the autograd graph at all: the reference never
+        # touches its prediction head, so its parameters keep grad None (custom Functions would
+        # otherwise be run with materialised zero gradients and mark those parameters as reached)
+        return [d[1] if (drawn is None or s in drawn) else d[1].detach() for s, d in enumerate(dec)]
+    args = (pre(dec1) + [d[0] for d in dec1] + pre(dec2) + [d[0] for d in dec2]
+            + pre(dec_local) + [d[0] for d in dec_local])
+    return _ContrastiveFn.apply(draws, drawn, *args)
 
 
 class _SigmoidFn(torch.autograd.Function):

@@ -409,6 +409,12 @@ def gemm_tn(a, b, out=None):
     return out
 
 
+def sgd_flat_dev(params, grads, bufs, seg_off, seg_active, seg_first, hyper, guard=None):
+    """sgd_flat with [lr, momentum, weight_decay, grad_scale, skip_threshold] in device memory."""
+    _lib.call("pcrl_sgd_flat_dev", params, grads, bufs, seg_off, seg_active, seg_first, seg_active.numel(),
+              hyper, guard)
+
+
 def sgd_flat(params, grads, bufs, seg_off, seg_active, seg_first, lr, momentum, weight_decay,
              grad_scale=1.0):
     nseg = seg_active.numel()
@@ -469,16 +475,41 @@ def cosine_mean_fwd_bwd(x, y, eps=1e-8, coef=1.0, need_dx=True):
     return out, dx
 
 
-def mse_fwd(p, t):
+def mse_fwd(p, t, weight=None):
+    """mean((p - t)^2) [* weight[0], a device scalar]."""
     out = torch.zeros((), dtype=torch.float32, device=p.device)
-    _lib.call("pcrl_mse_fwd", _f32c(p), _f32c(t), out, p.numel())
+    if weight is None:
+        _lib.call("pcrl_mse_fwd", _f32c(p), _f32c(t), out, p.numel())
+    else:
+        _lib.call("pcrl_mse_scaled_fwd", _f32c(p), _f32c(t), _f32c(weight), out, p.numel())
     return out
 
 
-def mse_bwd(p, t, g):
+def mse_bwd(p, t, g, weight=None):
     dp = torch.empty_like(p)
-    _lib.call("pcrl_mse_bwd", p, t, _f32c(g), dp, p.numel())
+    if weight is None:
+        _lib.call("pcrl_mse_bwd", p, t, _f32c(g), dp, p.numel())
+    else:
+        _lib.call("pcrl_mse_scaled_bwd", p, t, _f32c(g), _f32c(weight), dp, p.numel())
     return dp
+
+
+def contrastive_fwd_bwd(pre1, pro1, pre2, pro2, pre_l, pro_l, draws, eps=1e-8):
+    """The 1 + 2*n_local cos_loss terms of a step and their gradients in one launch.
+    pre1/pro1/pre2/pro2: 3 tensors [B, C_s] each; pre_l/pro_l: 3 tensors [n_local*B, C_s];
+    draws: int32 device tensor [1 + 2*n_local].  Returns (out [2] = (loss2, local_loss),
+    (dpre1[3], dpre2[3], dpre_l[3]))."""
+    import ctypes
+    b = pre1[0].shape[0]
+    n_local = pre_l[0].shape[0] // b
+    assert draws.dtype == torch.int32 and draws.is_cuda and draws.numel() >= 1 + 2 * n_local
+    ins = [_f32c(t) for grp in (pre1, pro1, pre2, pro2, pre_l, pro_l) for t in grp]
+    grads = [torch.empty_like(t) for grp in (pre1, pre2, pre_l) for t in grp]
+    ptrs = (ctypes.c_void_p * 27)(*[t.data_ptr() for t in ins + grads])
+    chans = (ctypes.c_int * 3)(*[int(t.shape[1]) for t in pre1])
+    out = torch.zeros(2, dtype=torch.float32, device=draws.device)
+    _lib.call("pcrl_contrastive_fwd_bwd", ptrs, chans, b, n_local, draws, out, float(eps))
+    return out, (grads[0:3], grads[3:6], grads[6:9])
 
 
 def sigmoid_fwd(x):

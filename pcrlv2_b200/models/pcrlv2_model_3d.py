@@ -54,6 +54,7 @@ import os as _os
 
 _SIDE = {}            # device index -> side stream
 _JOIN_PENDING = [None]    # id of the autograd graph task that already queued the join callback
+_EXPLICIT_JOIN = [False]  # captured-graph step: the caller joins the side stream itself (FlatSGD.step_static)
 
 
 def _side_stream(device):
@@ -96,7 +97,7 @@ def _wgrad_overlapped(dy, x, weight, flat, exact=False):
     # one join per backward(): keyed on the running graph task, so a backward that raised before its
     # callback ran cannot leave the flag stuck for the next one
     task = torch._C._current_graph_task_id()
-    if _JOIN_PENDING[0] != task:
+    if not _EXPLICIT_JOIN[0] and _JOIN_PENDING[0] != task:
         _JOIN_PENDING[0] = task
         torch.autograd.Variable._execution_engine.queue_callback(join_side_streams)
 

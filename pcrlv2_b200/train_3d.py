@@ -71,8 +71,12 @@ class FlatSGD(torch.optim.Optimizer):
         for p in ps:
             offs.append(offs[-1] + (p.numel() + 3) // 4 * 4)   # 16-byte aligned segments
         total = offs[-1]
+        self._total = total
         self._flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self._flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        # 4 tail floats: slot [total] carries the step's loss through the SAME all-reduce as the
+        # gradients, so that every rank takes the reference's "loss > 1000" skip decision
+        # (train_3d.py:140) on the global-batch loss without a second collective (captured-graph step)
+        self._flat_g = torch.zeros(total + 4, dtype=torch.float32, device=dev)
         self._flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for p, o in zip(ps, offs):
@@ -85,6 +89,10 @@ class FlatSGD(torch.optim.Optimizer):
         self._seg_off = torch.tensor(offs, dtype=torch.long, device=dev)
         self._touched = [False] * len(ps)
         self._has_buf = [False] * len(ps)
+        # segment flags of the fused kernel: persistent device tensors fed from one pinned host block
+        # (row 0 = active, row 1 = first) with a single asynchronous copy per step
+        self._flags_host = torch.zeros((2, len(ps)), dtype=torch.int32).pin_memory()
+        self._flags_dev = torch.zeros((2, len(ps)), dtype=torch.int32, device=dev)
         for i, p in enumerate(ps):
             p.register_hook(self._make_hook(i))
             # lets the convolution backward accumulate its weight gradient straight into the flat
@@ -109,6 +117,8 @@ class FlatSGD(torch.optim.Optimizer):
         # the gradient views must stay attached to the flat buffer: "none" is represented by the
         # untouched flag, not by dropping the tensor
         self._flat_g.zero_()
+        if torch.cuda.is_current_stream_capturing():
+            return      # the views were attached before the capture; host flags come from the draws
         for i, p in enumerate(self._ps):
             self._touched[i] = False
             o = self._offs[i]
@@ -121,18 +131,68 @@ class FlatSGD(torch.optim.Optimizer):
         scale = 1.0
         join_side_streams()   # weight gradients still in flight on the side stream (no-op after backward())
         if self._distributed:
-            scale = allreduce_flat_gradients(self._flat_g, self._pg)
-        dev = self._flat_p.device
-        active = torch.tensor([1 if t else 0 for t in self._touched], dtype=torch.int32).to(dev, non_blocking=True)
-        first = torch.tensor([0 if b else 1 for b in self._has_buf], dtype=torch.int32).to(dev, non_blocking=True)
-        K.sgd_flat(self._flat_p, self._flat_g, self._flat_m, self._seg_off, active, first,
+            scale = allreduce_flat_gradients(self._flat_g[:self._total], self._pg)
+        self.upload_flags(self._touched)
+        K.sgd_flat(self._flat_p, self._flat_g, self._flat_m, self._seg_off, self._flags_dev[0], self._flags_dev[1],
                    group["lr"], group["momentum"], group["weight_decay"], scale)
+        self.mark_stepped(self._touched)
+
+    def upload_flags(self, touched):
+        """(active, first) flags of every segment -> device (pinned staging, one async copy)."""
+        # the previous copy out of the pinned block must have been consumed before it is rewritten
+        ev = getattr(self, "_flags_event", None)
+        if ev is not None:
+            ev.synchronize()
+        fh = self._flags_host
+        fh[0] = torch.tensor([1 if t else 0 for t in touched], dtype=torch.int32)
+        fh[1] = torch.tensor([0 if b else 1 for b in self._has_buf], dtype=torch.int32)
+        self._flags_dev.copy_(fh, non_blocking=True)
+        self._flags_event = torch.cuda.Event()
+        self._flags_event.record()
+
+    def mark_stepped(self, touched):
+        """Host bookkeeping after an update: reached parameters now own a momentum buffer."""
         for i, p in enumerate(self._ps):
-            if self._touched[i] and not self._has_buf[i]:
+            if touched[i] and not self._has_buf[i]:
                 self._has_buf[i] = True
                 o = self._offs[i]
                 self.state[p]["momentum_buffer"] = self._flat_m[o:o + p.numel()].view_as(p)
         bump_param_epoch()
+
+    @torch.no_grad()
+    def step_static(self, hyper, loss):
+        """The update as it is captured into a CUDA graph: hyper-parameters ([lr, momentum, weight_decay,
+        grad_scale, skip_threshold]) and segment flags are read from device memory at replay time, the
+        loss rides in the tail of the flat gradient buffer through the all-reduce and gates the update."""
+        join_side_streams()
+        self._flat_g[self._total:self._total + 1].copy_(loss.detach().reshape(1))
+        if self._distributed:
+            dist.all_reduce(self._flat_g, op=dist.ReduceOp.SUM, group=self._pg)
+        K.sgd_flat_dev(self._flat_p, self._flat_g, self._flat_m, self._seg_off, self._flags_dev[0],
+                       self._flags_dev[1], hyper, self._flat_g[self._total:])
+
+    def reached_from_draws(self, model, draws):
+        """Which parameters the reference's autograd graph reaches for a given list of scale draws
+        (SURVEY note N3), without running autograd: everything except (a) the deep-supervision heads
+        of the scales != draws[0] (only middle_masks1[index2] enters the loss, train_3d.py:137) and (b)
+        the projection BatchNorm1d + prediction head of a scale that no cos_loss term drew."""
+        names = getattr(self, "_names", None)
+        if names is None:
+            by_id = {id(p): n for n, p in model.named_parameters()}
+            names = self._names = [by_id[id(p)] for p in self._ps]
+        stage = {"up_tr256": 0, "up_tr128": 1, "up_tr64": 2}
+        drawn = set(int(d) for d in draws)
+        out = []
+        for n in names:
+            top, _, rest = n.partition(".")
+            ok = True
+            if top in stage:
+                if rest.startswith("deep_supervision_head."):
+                    ok = stage[top] == int(draws[0])
+                elif rest.startswith("bn.") or rest.startswith("predictor_head."):
+                    ok = stage[top] in drawn
+            out.append(ok)
+        return out
 
     def load_state_dict(self, state_dict):
         """Accepts the ``optimizer`` entry of a reference checkpoint (torch.optim.SGD.state_dict(),
@@ -177,41 +237,254 @@ def cos_loss(cosine, output1, output2):
 
 
 def _is_plain_cosine(cosine):
-    return type(cosine) is nn.CosineSimilarity and cosine.dim == 1
+    return type(cosine) is nn.CosineSimilarity and cosine.dim == 1 and cosine.eps == 1e-8
+
+
+def _is_plain_mse(criterion):
+    return type(criterion) is nn.MSELoss and criterion.reduction == "mean"
 
 
 def _mse(criterion, pred, target):
     """criterion(pred, target); nn.MSELoss() (the reference's criterion, train_3d.py:56) runs on the
     fused squared-error kernels."""
-    if type(criterion) is nn.MSELoss and criterion.reduction == "mean" and pred.is_cuda \
-            and pred.dtype == torch.float32 and pred.shape == target.shape:
+    if _is_plain_mse(criterion) and pred.is_cuda and pred.dtype == torch.float32 and pred.shape == target.shape:
         return Fn.mse_loss(pred, target)
     return criterion(pred, target)
 
 
-def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine):
+def draw_scales(n_views, n_scales=3):
+    """The 1 + 2*n_views ``random.randint`` draws of one iteration in the reference's order
+    (train_3d.py:87 called from :119 and, per local view, :129-130): index2, then for every view the
+    draw of (decoder 1, view) and of (decoder 2, view).  Consumes Python's global RNG exactly like
+    the reference's 13 cos_loss calls."""
+    return [random.randint(0, n_scales - 1) for _ in range(1 + 2 * n_views)]
+
+
+def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine, static=None):
     """Forward part of one iteration, reference train_3d.py:116-138.
-    Returns (loss, loss1, loss2, local_loss)."""
+    Returns (loss, loss1, loss2, local_loss).
+
+    With the reference's own criterion / similarity (nn.MSELoss, nn.CosineSimilarity) the 13
+    cos_loss terms are ONE kernel (csrc/losses.cu:contrastive_kernel) that reads the drawn scales
+    from device memory; any other callable is evaluated term by term as the reference does.
+    ``static`` (a _StaticCtl, captured-graph mode): the draws and beta come from device buffers that
+    the host refreshes before every replay, and the deep-supervision term is evaluated for all
+    three scales with the drawn one selected by a device-side weight."""
     bsz = x1.size(0)
+    fused = (_is_plain_cosine(cosine) and x1.is_cuda) or static is not None
     mask1, decoder_outputs1, middle_masks1 = model(x1)
     mask2, decoder_outputs2, _ = model(x2)
-    loss2, index2 = cos_loss(cosine, decoder_outputs1, decoder_outputs2)
-    local_loss = 0.0
+    if not fused:
+        loss2, index2 = cos_loss(cosine, decoder_outputs1, decoder_outputs2)
     local_input = torch.cat(local_views, dim=0)
     _, local_views_outputs, _ = model(local_input, local=True)
-    local_views_outputs = [torch.stack(t) for t in local_views_outputs]
-    for i in range(len(local_views)):
-        local_views_outputs_tmp = [t[:, bsz * i: bsz * (i + 1)] for t in local_views_outputs]
-        loss_local_1, _ = cos_loss(cosine, decoder_outputs1, local_views_outputs_tmp)
-        loss_local_2, _ = cos_loss(cosine, decoder_outputs2, local_views_outputs_tmp)
-        local_loss += loss_local_1
-        local_loss += loss_local_2
-    local_loss = local_loss / (2 * len(local_views))
+    if fused:
+        if static is None:
+            draws = draw_scales(len(local_views))
+            index2 = draws[0]
+            draws_dev = torch.tensor(draws, dtype=torch.int32, device=x1.device)
+            closs, parts = Fn.contrastive_losses(decoder_outputs1, decoder_outputs2, local_views_outputs,
+                                                 draws_dev, tuple(sorted(set(draws))))
+        else:
+            closs, parts = Fn.contrastive_losses(decoder_outputs1, decoder_outputs2, local_views_outputs,
+                                                 static.draws, None)
+        loss2, local_loss = parts[0], parts[1]
+    else:
+        local_loss = 0.0
+        local_views_outputs = [torch.stack(t) for t in local_views_outputs]
+        for i in range(len(local_views)):
+            local_views_outputs_tmp = [t[:, bsz * i: bsz * (i + 1)] for t in local_views_outputs]
+            loss_local_1, _ = cos_loss(cosine, decoder_outputs1, local_views_outputs_tmp)
+            loss_local_2, _ = cos_loss(cosine, decoder_outputs2, local_views_outputs_tmp)
+            local_loss += loss_local_1
+            local_loss += loss_local_2
+        local_loss = local_loss / (2 * len(local_views))
+        closs = loss2 + local_loss
     loss1 = _mse(criterion, mask1, gt)
-    beta = 0.5 * (1. + math.cos(math.pi * epoch / 240))
-    loss4 = beta * _mse(criterion, middle_masks1[index2], gt)
-    loss = loss1 + loss2 + loss4 + local_loss
+    if static is not None:
+        # beta * MSE(middle_masks1[index2], gt) for a data-dependent index2: all three scales, each
+        # multiplied by static.w4[s] = beta * [index2 == s] inside the kernels
+        loss4 = (Fn.mse_loss(middle_masks1[0], gt, static.w4[0:1]) + Fn.mse_loss(middle_masks1[1], gt, static.w4[1:2])
+                 + Fn.mse_loss(middle_masks1[2], gt, static.w4[2:3]))
+    else:
+        beta = 0.5 * (1. + math.cos(math.pi * epoch / 240))
+        loss4 = beta * _mse(criterion, middle_masks1[index2], gt)
+    loss = loss1 + closs + loss4
     return loss, loss1, loss2, local_loss
+
+
+class _StaticCtl:
+    """Device-resident control block of a captured step: draws int32[16], w4 float32[4] (beta * one-hot
+    of the drawn deep-supervision scale), hyper float32[8] ([lr, momentum, weight_decay, grad_scale,
+    skip_threshold]); one pinned host mirror, one asynchronous copy per step."""
+
+    def __init__(self, dev):
+        self.host = torch.zeros(28, dtype=torch.int32).pin_memory()
+        self.dev = torch.zeros(28, dtype=torch.int32, device=dev)
+        self.draws = self.dev[0:16]
+        self.w4 = self.dev[16:20].view(torch.float32)
+        self.hyper = self.dev[20:28].view(torch.float32)
+        self._h_draws = self.host[0:16]
+        self._h_w4 = self.host[16:20].view(torch.float32)
+        self._h_hyper = self.host[20:28].view(torch.float32)
+        self._event = None
+
+    def upload(self, draws, beta, lr, momentum, weight_decay, grad_scale, skip_threshold):
+        if self._event is not None:
+            self._event.synchronize()          # the previous copy has left the pinned block
+        self._h_draws.zero_()
+        self._h_draws[:len(draws)] = torch.tensor(draws, dtype=torch.int32)
+        self._h_w4.zero_()
+        self._h_w4[draws[0]] = beta
+        self._h_hyper[:5] = torch.tensor([lr, momentum, weight_decay, grad_scale, skip_threshold], dtype=torch.float32)
+        self.dev.copy_(self.host, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+
+
+class GraphedStep:
+    """One training iteration (reference train_3d.py:109-151: three forwards, the four loss terms,
+    backward, gradient all-reduce, SGD) captured ONCE into a CUDA graph and replayed per step.
+
+    Why: the eager step issues ~600 kernel launches through Python/ctypes per ~60-100 ms of GPU work;
+    with eight ranks on one host that Python time, not the GPU, set the bf16 8-GPU step time (round-1
+    SCALE: 0.81 efficiency).  A replay costs the host one cudaGraphLaunch plus two small pinned copies.
+
+    Everything that varies from step to step is DATA of the graph, refreshed by the host before the
+    replay: the input batch (static device buffers), the 13 scale draws and beta (``_StaticCtl``), the
+    learning rate / skip threshold (device hyper-parameters of ``sgd_flat_dev``) and the per-parameter
+    "reached by autograd" flags of SGD (``FlatSGD.reached_from_draws``: unreached parameters are
+    skipped entirely, SURVEY note N3).  The graph itself always evaluates every contrastive /
+    deep-supervision branch; branches the draws did not select contribute exact zeros.
+
+    State semantics are the eager step's: parameters, momentum, BatchNorm running statistics and
+    ``num_batches_tracked`` are updated in place by the captured kernels.  Results are bit-compatible
+    with the eager path up to the order of floating-point atomics (tests/test_graph_gpu.py)."""
+
+    def __init__(self, model, optimizer, bsz, vol, local, n_local, warmup=1):
+        if not isinstance(optimizer, FlatSGD):
+            raise TypeError("GraphedStep needs a FlatSGD optimizer")
+        dev = optimizer._flat_p.device
+        self.model, self.opt, self.key = model, optimizer, (bsz, tuple(vol), tuple(local), n_local)
+        self.x1 = torch.zeros((bsz, 1) + tuple(vol), device=dev)
+        self.x2 = torch.zeros_like(self.x1)
+        self.gt = torch.zeros_like(self.x1)
+        self.local = torch.zeros((n_local * bsz, 1) + tuple(local), device=dev)
+        self.ctl = _StaticCtl(dev)
+        self.out = torch.zeros(4, device=dev)          # loss, loss1, loss2, local_loss of the last replay
+        self.n_local, self.bsz = n_local, bsz
+        self.graph = None
+        self.launches = 0
+        self._capture(warmup)
+
+    # -- the step as it is captured
+    def _static_step(self):
+        bump_param_epoch()     # the tensor-core operand copies of the weights are re-packed INSIDE the graph
+        crit, cos = nn.MSELoss(), nn.CosineSimilarity()
+        views = [self.local[i * self.bsz:(i + 1) * self.bsz] for i in range(self.n_local)]
+        loss, loss1, loss2, local_loss = pcrlv2_step_loss(self.model, self.x1, self.x2, self.gt, views, 0,
+                                                          crit, cos, static=self.ctl)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step_static(self.ctl.hyper, loss)
+        self.out.copy_(torch.stack([loss.detach(), loss1.detach(), loss2.detach(), local_loss.detach()]))
+
+    def _capture(self, warmup):
+        from . import _lib
+        from .models import pcrlv2_model_3d as M
+        model, opt = self.model, self.opt
+        # the warm-up iterations run for real (they initialise lazily created CUDA state: kernel
+        # attributes, the TMA driver entry point, NCCL communicators, the allocator's pools); the
+        # training state they touch is put back afterwards
+        saved = {"p": opt._flat_p.clone(), "m": opt._flat_m.clone(),
+                 "buf": [b.detach().clone() for b in model.buffers()], "rng": random.getstate()}
+        group = opt.param_groups[0]
+        self.ctl.upload([0] * (1 + 2 * self.n_local), 1.0, 0.0, group["momentum"], 0.0, 1.0, float("inf"))
+        opt.upload_flags([True] * len(opt._ps))
+        M._EXPLICIT_JOIN[0] = True       # the side stream is joined by step_static, not by an engine callback
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self._static_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count[0]
+            try:
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                    self._static_step()
+            except RuntimeError as e:
+                raise RuntimeError(
+                    "capturing the training step into a CUDA graph failed (%s).  The usual cause: an autograd "
+                    "graph of an EARLIER eager iteration is still alive (a loss tensor kept in a variable), "
+                    "which pins the parameters' AccumulateGrad nodes to the default stream; drop those "
+                    "references before the first captured step, or set PCRL_GRAPH=0 to keep the eager step."
+                    % str(e).splitlines()[0]) from e
+            self.launches = _lib.launch_count[0] - n0
+        finally:
+            M._EXPLICIT_JOIN[0] = False
+        with torch.no_grad():
+            opt._flat_p.copy_(saved["p"])
+            opt._flat_m.copy_(saved["m"])
+            for b, v in zip(model.buffers(), saved["buf"]):
+                b.copy_(v)
+        random.setstate(saved["rng"])
+        bump_param_epoch()
+        torch.cuda.synchronize()
+
+    def load(self, x1, x2, gt, local_views):
+        """Stage one batch into the static input buffers (host or device tensors, asynchronous)."""
+        self.x1.copy_(x1, non_blocking=True)
+        self.x2.copy_(x2, non_blocking=True)
+        self.gt.copy_(gt, non_blocking=True)
+        b = self.bsz
+        for i, v in enumerate(local_views):
+            self.local[i * b:(i + 1) * b].copy_(v, non_blocking=True)
+
+    def run(self, epoch, skip_guard=True):
+        """Draw the scales (Python's ``random``, the reference's order), refresh the control data and
+        replay.  Returns the device tensor [loss, loss1, loss2, local_loss] (no host sync here)."""
+        opt = self.opt
+        group = opt.param_groups[0]
+        draws = draw_scales(self.n_local)
+        beta = 0.5 * (1. + math.cos(math.pi * epoch / 240))
+        world = dist.get_world_size(opt._pg) if opt._distributed else 1
+        thr = 1000.0 if (skip_guard and epoch > 10) else float("inf")
+        self.ctl.upload(draws, beta, group["lr"], group["momentum"], group["weight_decay"], 1.0 / world, thr)
+        reached = opt.reached_from_draws(self.model, draws)
+        opt.upload_flags(reached)
+        self.graph.replay()
+        self.last_reached, self.last_draws = reached, draws
+        self.pending = thr != float("inf")     # the skip guard may fire: the caller reports the outcome
+        if not self.pending:
+            self.finish(False)
+        return self.out
+
+    def finish(self, skipped):
+        """Host bookkeeping of the replayed update (momentum-buffer ownership, packed-weight cache)."""
+        self.pending = False
+        if not skipped:
+            self.opt._touched = list(self.last_reached)
+            self.opt.mark_stepped(self.last_reached)
+
+
+def graphed_step_for(model, optimizer, criterion, cosine, x1, local_views):
+    """The cached GraphedStep of (model, optimizer) for this batch geometry, or None when the step
+    cannot be captured (foreign optimizer / criterion / similarity, PCRL_GRAPH=0)."""
+    if os.environ.get("PCRL_GRAPH", "1") == "0":
+        return None
+    if not (isinstance(model, PCRLv23d) and isinstance(optimizer, FlatSGD) and _is_plain_mse(criterion)
+            and _is_plain_cosine(cosine) and model.training):
+        return None
+    key = (x1.shape[0], tuple(x1.shape[2:]), tuple(local_views[0].shape[2:]), len(local_views))
+    cache = optimizer.__dict__.setdefault("_graphed", {})
+    gs = cache.get(key)
+    if gs is None:
+        cache.clear()          # one geometry at a time: a captured graph pins its activation memory
+        gs = cache[key] = GraphedStep(model, optimizer, key[0], key[1], key[2], key[3])
+    return gs
 
 
 def train_pcrlv2_inner(args, epoch, train_loader, model, optimizer, criterion, cosine):
@@ -227,23 +500,40 @@ def train_pcrlv2_inner(args, epoch, train_loader, model, optimizer, criterion, c
     for idx, (input1, input2, gt, gt2, local_views) in enumerate(train_loader):
         data_time.update(time.time() - end)
         bsz = input1.size(0)
-        x1 = input1.float().to(dev, non_blocking=True)
-        x2 = input2.float().to(dev, non_blocking=True)
-        gt = gt.float().to(dev, non_blocking=True)
-        local_views = [v.float().to(dev, non_blocking=True) for v in local_views]
-        loss, loss1, loss2, local_loss = pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch,
-                                                          criterion, cosine)
-        # ===================backward=====================
-        if epoch > 10 and _skip_step(loss):   # reference :140; ordered to avoid a host sync early on
-            print('skip the step')
-            continue
-        optimizer.zero_grad()
-        loss.backward()
-        optimizer.step()
+        gs = graphed_step_for(model, optimizer, criterion, cosine, input1, local_views)
+        if gs is not None:
+            # captured step: inputs go straight into the graph's static buffers, one replay, one
+            # read-back of the four loss scalars (the reference reads three .item()s per iteration)
+            gs.load(input1.float(), input2.float(), gt.float(), [v.float() for v in local_views])
+            vals = gs.run(epoch).tolist()
+            world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+            skipped = epoch > 10 and (optimizer._flat_g[optimizer._total].item() / world if world > 1 else vals[0]) > 1000
+            if gs.pending:
+                gs.finish(skipped)
+            if skipped:
+                print('skip the step')
+                continue
+            loss1_v, loss2_v, local_v = vals[1], vals[2], vals[3]
+        else:
+            x1 = input1.float().to(dev, non_blocking=True)
+            x2 = input2.float().to(dev, non_blocking=True)
+            gt = gt.float().to(dev, non_blocking=True)
+            local_views = [v.float().to(dev, non_blocking=True) for v in local_views]
+            loss, loss1, loss2, local_loss = pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch,
+                                                              criterion, cosine)
+            # ===================backward=====================
+            if epoch > 10 and _skip_step(loss):   # reference :140; ordered to avoid a host sync early on
+                print('skip the step')
+                continue
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            loss1_v, loss2_v = loss1.item(), loss2.item()
+            local_v = local_loss.item() if torch.is_tensor(local_loss) else float(local_loss)
         # ===================meters=====================
-        mg_loss_meter.update(loss1.item(), bsz)
-        loss_meter.update(loss2.item(), bsz)
-        prob_meter.update(local_loss.item() if torch.is_tensor(local_loss) else float(local_loss), bsz)
+        mg_loss_meter.update(loss1_v, bsz)
+        loss_meter.update(loss2_v, bsz)
+        prob_meter.update(local_v, bsz)
         torch.cuda.synchronize()
         batch_time.update(time.time() - end)
         end = time.time()

@@ -1,0 +1,126 @@
+"""Two-GPU data-parallel equivalence (one process per GPU over NCCL; skipped on a single-GPU box).
+
+The reference shards a batch over GPUs with nn.DataParallel (train_3d.py:54): every replica
+normalises with the BatchNorm statistics of ITS shard and the replicas' gradients are summed into one
+parameter set.  Here every rank runs the step on its shard and the flat gradient buffer is
+all-reduced.  Checked on rank 0 against a single process that evaluates the two shards one after the
+other (each with its own BatchNorm statistics) and averages the two gradients:
+  * the all-reduced, 1/world-scaled gradient equals that average (up to atomics noise);
+  * after the update every rank holds bit-identical parameters, in the eager step and in the
+    captured-graph step; both steps agree with each other.
+Evidence of a run on 2 x B200: profiles/r02_ddp2_pytest.log."""
+import os
+import random
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pcrlv2_oracle as orc  # noqa: E402
+
+
+def _worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from pcrlv2_b200.models import PCRLv23d
+    from pcrlv2_b200 import train_3d as T
+    dev = torch.device("cuda", rank)
+    sd0 = orc.init_state(0)
+    full = orc.synthetic_batch(2 * world, seed=9, vol=(32, 32, 16))
+
+    def shard(r):
+        sl = slice(2 * r, 2 * r + 2)
+        return full[0][sl], full[1][sl], full[2][sl], [v[sl] for v in full[3]]
+
+    def fresh():
+        m = PCRLv23d(precision="fp32")
+        m.load_state_dict(orc.clone_state(sd0))
+        return m.to(dev).train()
+
+    crit, cos = torch.nn.MSELoss(), torch.nn.CosineSimilarity()
+    log = []
+
+    def rl2(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+    # ---- eager data-parallel step
+    m = fresh()
+    opt = T.FlatSGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+    assert opt._distributed
+    x1, x2, gt, lv = [t.to(dev) if torch.is_tensor(t) else [v.to(dev) for v in t] for t in shard(rank)]
+    random.seed(3)
+    loss, *_ = T.pcrlv2_step_loss(m, x1, x2, gt, lv, 0, crit, cos)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    g_dp = opt._flat_g[:opt._total].clone() / world
+    p_dp = opt._flat_p.clone()
+    gathered = [torch.zeros_like(p_dp) for _ in range(world)]
+    dist.all_gather(gathered, p_dp)
+    assert all(torch.equal(gathered[0], t) for t in gathered), "replicas diverged after the eager step"
+
+    # ---- single-process restatement on rank 0: shard by shard, own BatchNorm statistics each
+    if rank == 0:
+        gs_sum = None
+        for r in range(world):
+            ms = fresh()
+            os_ = T.FlatSGD(ms.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4, distributed=False)
+            a1, a2, agt, alv = [t.to(dev) if torch.is_tensor(t) else [v.to(dev) for v in t] for t in shard(r)]
+            random.seed(3)
+            l_, *_ = T.pcrlv2_step_loss(ms, a1, a2, agt, alv, 0, crit, cos)
+            os_.zero_grad()
+            l_.backward()
+            T.join_side_streams()
+            g = os_._flat_g[:os_._total].clone()
+            gs_sum = g if gs_sum is None else gs_sum + g
+        e = rl2(g_dp, gs_sum / world)
+        log.append(f"all-reduced gradient vs average of per-shard gradients: rel-L2 {e:.3e}")
+        assert e < 2e-2, e       # atomics noise through the BatchNorm backward at batch 2 is ~4e-3
+
+    # ---- captured-graph data-parallel steps: replicas stay in sync, result agrees with the eager step
+    m2 = fresh()
+    opt2 = T.FlatSGD(m2.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+    s = shard(rank)
+    args = types.SimpleNamespace(lr=1e-2, momentum=0.9, weight_decay=1e-4, amp=False, epochs=240)
+    random.seed(3)
+    T.train_pcrlv2_inner(args, 0, [(s[0], s[1], s[2], s[2], s[3])], m2, opt2, crit, cos)
+    assert opt2.__dict__.get("_graphed"), "the trainer did not take the captured-graph step"
+    p_g = opt2._flat_p.clone()
+    dist.all_gather(gathered, p_g)
+    assert all(torch.equal(gathered[0], t) for t in gathered), "replicas diverged after the graph step"
+    i0 = torch.cat([sd0[n].flatten() for n, _ in m.named_parameters()]).to(dev)
+    # flat buffers pad segments to 16 bytes: compare parameter by parameter
+    du_e = torch.cat([p.detach().flatten() for p in opt._ps]) - i0
+    du_g = torch.cat([p.detach().flatten() for p in opt2._ps]) - i0
+    e = rl2(du_g, du_e)
+    log.append(f"rank {rank}: update of the graph step vs the eager step rel-L2 {e:.3e}")
+    assert e < 2e-2, e
+    # a second replay with another batch keeps them in sync as well
+    s2 = orc.synthetic_batch(2 * world, seed=10, vol=(32, 32, 16))
+    sl = slice(2 * rank, 2 * rank + 2)
+    T.train_pcrlv2_inner(args, 0, [(s2[0][sl], s2[1][sl], s2[2][sl], s2[2][sl], [v[sl] for v in s2[3]])], m2, opt2, crit, cos)
+    dist.all_gather(gathered, opt2._flat_p.clone())
+    assert all(torch.equal(gathered[0], t) for t in gathered)
+    dist.barrier()
+    if rank == 0:
+        open(out_path, "w").write("ok\n" + "\n".join(log))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_data_parallel_equivalence(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "ddp.txt")
+    port = 29600 + (os.getpid() % 1000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    text = open(out).read()
+    print(text)
+    assert text.startswith("ok")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    open(os.path.join(root, "gpurun_out", "ddp2_equivalence.txt"), "w").write(text)
