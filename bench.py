@@ -32,7 +32,7 @@ VOL = (64, 64, 32)
 LOCAL = (16, 16, 16)
 
 
-def flops_per_sample(vol=VOL, local=LOCAL, n_local=6):
+def flops_per_sample(vol=None, local=None, n_local=6):
     """Algorithmic FLOPs (2*MACs of every conv / convT / linear) of one sample's step
     (SURVEY 8d): forward F(V) scales with the voxel count; backward = 2x forward minus the data
     gradient of the Cin=1 stem."""
@@ -46,6 +46,7 @@ def flops_per_sample(vol=VOL, local=LOCAL, n_local=6):
         f += sum(2.0 * (v / s) * ci * co * 8 for ci, co, s in [(512, 512, 512), (256, 256, 64), (128, 128, 8)])
         f += sum(2.0 * (c * 2 * c) * 2 for c in (256, 128, 64))                           # predictor
         return f
+    vol, local = vol or VOL, local or LOCAL
     vg = vol[0] * vol[1] * vol[2]
     vl = local[0] * local[1] * local[2]
     f_fwd = 2 * fwd(vg) + n_local * fwd(vl)
@@ -135,6 +136,18 @@ def measure_tf32_peak(dev, seconds=1.0):
         return 2.0 * n ** 3 * total_it / (total_ms / 1e3) / 1e12
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def set_workload(name):
+    """configs[1]/[2] geometry (default) or configs[3]: 128x128x64 crops with 32^3 local views
+    (the reference leaves the local size of that config open; 32^3 keeps the 1/32 voxel ratio)."""
+    global VOL, LOCAL
+    if name == "large":
+        VOL, LOCAL = (128, 128, 64), (32, 32, 32)
+        for k in list(WORKLOADS):
+            WORKLOADS[k] = ("LUNA 3D pretrain 128x128x64 crops + 6x32^3 local views, b={B}/GPU, %s (configs[3]: "
+                            "128x128x64 b=8 bf16 on 1xB200, the large-volume regime)" %
+                            ("bf16" if k == "bf16" else "fp32 storage / TF32 operands"))
 
 
 WORKLOADS = {
@@ -229,6 +242,7 @@ def measure(args, precision, host, rank, world, dev):
     gs = None
     if not args.eager:
         gs = T.graphed_step_for(model, opt, crit, cos, resident[0][0], resident[0][3])   # captures here
+        gs.capture_all()        # the graphs of all three index2 draws, before anything is timed
 
     def graph_step(i):
         x1, x2, gt, lv = resident[i % nbatches]
@@ -385,6 +399,8 @@ def roofline_of(r, precision, peaks, peak_src, dev):
                "measured live in this run for 1 s)")
         extra = {"cublas_tf32_tflops_live": cublas_tf32, "half_bf16_sustained_tflops": 0.5 * bf16_peak}
     traffic, algo_bytes = NCU_TRAFFIC[precision]
+    if VOL != (64, 64, 32):
+        traffic = None                      # the committed ncu capture is of the 64x64x32 workload
     fam = ("pcrl_conv3d_k3_fprop", "pcrl_conv3d_k3_dgrad", "pcrl_conv3d_k3_dgrad_unshuffled")
     kmajor_ms = sum(per[k]["ms"] for k in fam if k in per)
     kmajor_fl = sum(per[k]["flops"] for k in fam if k in per)
@@ -464,7 +480,8 @@ def run_ours(args):
               "l2": "activation working set per step is tens of GB >> 126 MB L2; two input batches alternate",
               "algorithmic_gflop_per_sample": round(fl / 1e9, 2), "step": r["step"]}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if args.workload == "luna64" else "LUNA 128x128x64 pretrain volumes/sec (configs[3])",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if main_p == "bf16" else "tf32",
         "data": "synthetic",
@@ -513,7 +530,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default 32; 8 for --workload large)")
+    ap.add_argument("--workload", default="luna64", choices=["luna64", "large"],
+                    help="luna64: 64x64x32 crops (configs[1]/[2], the headline); large: configs[3], 128x128x64 "
+                         "crops, b=8, bf16 -- its line is recorded under profiles/, it is not the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["bf16", "fp32"],
                     help="activation storage / tensor-core operand type of the headline measurement "
@@ -523,6 +543,11 @@ def main():
     ap.add_argument("--no-also", action="store_true",
                     help="skip the device-resident measurement at the other precision ('also' key)")
     args = ap.parse_args()
+    set_workload(args.workload)
+    if args.batch is None:
+        args.batch = 8 if args.workload == "large" else 32
+    if args.workload == "large" and "--precision" not in sys.argv:
+        args.precision = "bf16"
     # stdout carries exactly ONE line (the JSON): anything libraries print there while the job
     # runs (e.g. NCCL's version banner) is sent to stderr instead
     sys.stdout.flush()

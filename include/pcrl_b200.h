@@ -40,6 +40,9 @@ extern "C" {
 #define PCRL_ACT_ELU 2
 #define PCRL_ACT_SIGMOID 3
 #define PCRL_ACT_NONE 4
+/* nn.LeakyReLU(0.01): not offered by the reference's LUConv (:20-27); BASELINE.json:north_star names the
+ * Conv3d+InstanceNorm+LeakyReLU block, so it is available as act='leakyrelu' (an extension) */
+#define PCRL_ACT_LEAKYRELU 5
 
 const char* pcrl_last_error(void);
 int pcrl_version(void);

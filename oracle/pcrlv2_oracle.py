@@ -159,6 +159,8 @@ def _act(x, sd, prefix, act):
         return F.elu(x)
     if act == "sigmoid":
         return torch.sigmoid(x)
+    if act == "leakyrelu":      # not in the reference (extension named by north_star): nn.LeakyReLU(0.01)
+        return F.leaky_relu(x, 0.01)
     raise ValueError(f"activation type {act} is not supported")
 
 

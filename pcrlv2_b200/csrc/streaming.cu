@@ -10,7 +10,7 @@
 
 namespace pcrl {
 
-enum { ACT_RELU = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_SIGMOID = 3, ACT_NONE = 4 };
+enum { ACT_RELU = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_SIGMOID = 3, ACT_NONE = 4, ACT_LEAKY = 5 };
 
 // ---- 8-channel vector access, templated on the storage type (bf16: 16 bytes, fp32: 32 bytes)
 typedef __nv_bfloat16 bf16_t;
@@ -103,6 +103,7 @@ __device__ __forceinline__ float act_fwd(float z, int act, float slope) {
     case ACT_PRELU: return z > 0.f ? z : slope * z;
     case ACT_ELU: return z > 0.f ? z : expm1f(z);
     case ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    case ACT_LEAKY: return z > 0.f ? z : 0.01f * z;
     default: return z;
   }
 }
@@ -113,6 +114,7 @@ __device__ __forceinline__ float act_bwd(float z, int act, float slope) {
     case ACT_PRELU: return z > 0.f ? 1.f : slope;
     case ACT_ELU: return z > 0.f ? 1.f : expf(z);
     case ACT_SIGMOID: { float s = 1.f / (1.f + expf(-z)); return s * (1.f - s); }
+    case ACT_LEAKY: return z > 0.f ? 1.f : 0.01f;
     default: return 1.f;
   }
 }

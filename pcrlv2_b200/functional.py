@@ -143,8 +143,9 @@ def contrastive_losses(dec1, dec2, dec_local, draws, drawn=None):
         # touches its prediction head, so its parameters keep grad None (custom Functions would
         # otherwise be run with materialised zero gradients and mark those parameters as reached)
         return [d[1] if (drawn is None or s in drawn) else d[1].detach() for s, d in enumerate(dec)]
-    args = (pre(dec1) + [d[0] for d in dec1] + pre(dec2) + [d[0] for d in dec2]
-            + pre(dec_local) + [d[0] for d in dec_local])
+    def pro(dec):      # the reference detaches the projections (train_3d.py:90-91)
+        return [d[0].detach() for d in dec]
+    args = pre(dec1) + pro(dec1) + pre(dec2) + pro(dec2) + pre(dec_local) + pro(dec_local)
     return _ContrastiveFn.apply(draws, drawn, *args)
 
 

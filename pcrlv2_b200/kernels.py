@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-ACT = {"relu": 0, "prelu": 1, "elu": 2, "sigmoid": 3, "none": 4}
+ACT = {"relu": 0, "prelu": 1, "elu": 2, "sigmoid": 3, "none": 4, "leakyrelu": 5}
 BF16 = torch.bfloat16
 F32 = torch.float32
 # storage types of activations / tensor-core operands (include/pcrl_b200.h: PCRL_DTYPE_*)

@@ -356,6 +356,10 @@ class LUConv(nn.Module):
             self.activation = nn.ELU(inplace=True)
         elif act == "sigmoid":
             self.activation = nn.Sigmoid()
+        elif act == "leakyrelu":
+            # extension: the reference's LUConv has no LeakyReLU branch (:20-27); north_star names the
+            # Conv3d+InstanceNorm+LeakyReLU block (use with norm='in')
+            self.activation = nn.LeakyReLU(0.01, inplace=True)
         else:
             raise ValueError("activation type {} is not supported".format(act))
         self.act, self.norm = act, norm

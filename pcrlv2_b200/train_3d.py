@@ -302,10 +302,11 @@ def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine, s
         closs = loss2 + local_loss
     loss1 = _mse(criterion, mask1, gt)
     if static is not None:
-        # beta * MSE(middle_masks1[index2], gt) for a data-dependent index2: all three scales, each
-        # multiplied by static.w4[s] = beta * [index2 == s] inside the kernels
-        loss4 = (Fn.mse_loss(middle_masks1[0], gt, static.w4[0:1]) + Fn.mse_loss(middle_masks1[1], gt, static.w4[1:2])
-                 + Fn.mse_loss(middle_masks1[2], gt, static.w4[2:3]))
+        # beta * MSE(middle_masks1[index2], gt): beta is data (static.w4[index2]); index2 itself selects
+        # one of three captured graphs (GraphedStep), so that the backward of the two deep-supervision
+        # heads the draw did NOT select is not run at all -- as in the reference (SURVEY note N2/N3)
+        k = static.index2
+        loss4 = Fn.mse_loss(middle_masks1[k], gt, static.w4[k:k + 1])
     else:
         beta = 0.5 * (1. + math.cos(math.pi * epoch / 240))
         loss4 = beta * _mse(criterion, middle_masks1[index2], gt)
@@ -328,6 +329,7 @@ class _StaticCtl:
         self._h_w4 = self.host[16:20].view(torch.float32)
         self._h_hyper = self.host[20:28].view(torch.float32)
         self._event = None
+        self.index2 = 0          # host constant of the graph being captured (see GraphedStep)
 
     def upload(self, draws, beta, lr, momentum, weight_decay, grad_scale, skip_threshold):
         if self._event is not None:
@@ -354,8 +356,11 @@ class GraphedStep:
     replay: the input batch (static device buffers), the 13 scale draws and beta (``_StaticCtl``), the
     learning rate / skip threshold (device hyper-parameters of ``sgd_flat_dev``) and the per-parameter
     "reached by autograd" flags of SGD (``FlatSGD.reached_from_draws``: unreached parameters are
-    skipped entirely, SURVEY note N3).  The graph itself always evaluates every contrastive /
-    deep-supervision branch; branches the draws did not select contribute exact zeros.
+    skipped entirely, SURVEY note N3).  A graph always evaluates the contrastive terms of all three
+    scales (one small kernel; terms the draws did not select contribute exact zeros).  The one draw
+    that changes the amount of work -- index2, which deep-supervision mask enters the loss -- selects
+    one of THREE graphs, captured lazily on first use into one shared memory pool (they never run
+    concurrently and hand nothing to each other but the static output buffer).
 
     State semantics are the eager step's: parameters, momentum, BatchNorm running statistics and
     ``num_batches_tracked`` are updated in place by the captured kernels.  Results are bit-compatible
@@ -373,9 +378,11 @@ class GraphedStep:
         self.ctl = _StaticCtl(dev)
         self.out = torch.zeros(4, device=dev)          # loss, loss1, loss2, local_loss of the last replay
         self.n_local, self.bsz = n_local, bsz
-        self.graph = None
+        self.graphs = {}                 # index2 -> CUDAGraph
+        self.pool = None
         self.launches = 0
-        self._capture(warmup)
+        self._warmup = warmup
+        self._capture(0)
 
     # -- the step as it is captured
     def _static_step(self):
@@ -389,8 +396,10 @@ class GraphedStep:
         self.opt.step_static(self.ctl.hyper, loss)
         self.out.copy_(torch.stack([loss.detach(), loss1.detach(), loss2.detach(), local_loss.detach()]))
 
-    def _capture(self, warmup):
+    def _capture(self, index2):
         from . import _lib
+        warmup = self._warmup if not self.graphs else 1
+        self.ctl.index2 = index2
         from .models import pcrlv2_model_3d as M
         model, opt = self.model, self.opt
         # the warm-up iterations run for real (they initialise lazily created CUDA state: kernel
@@ -399,7 +408,7 @@ class GraphedStep:
         saved = {"p": opt._flat_p.clone(), "m": opt._flat_m.clone(),
                  "buf": [b.detach().clone() for b in model.buffers()], "rng": random.getstate()}
         group = opt.param_groups[0]
-        self.ctl.upload([0] * (1 + 2 * self.n_local), 1.0, 0.0, group["momentum"], 0.0, 1.0, float("inf"))
+        self.ctl.upload([index2] * (1 + 2 * self.n_local), 1.0, 0.0, group["momentum"], 0.0, 1.0, float("inf"))
         opt.upload_flags([True] * len(opt._ps))
         M._EXPLICIT_JOIN[0] = True       # the side stream is joined by step_static, not by an engine callback
         try:
@@ -410,10 +419,10 @@ class GraphedStep:
                     self._static_step()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
+            graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count[0]
             try:
-                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                with torch.cuda.graph(graph, pool=self.pool, capture_error_mode="thread_local"):
                     self._static_step()
             except RuntimeError as e:
                 raise RuntimeError(
@@ -423,6 +432,9 @@ class GraphedStep:
                     "references before the first captured step, or set PCRL_GRAPH=0 to keep the eager step."
                     % str(e).splitlines()[0]) from e
             self.launches = _lib.launch_count[0] - n0
+            self.graphs[index2] = graph
+            if self.pool is None:
+                self.pool = graph.pool()
         finally:
             M._EXPLICIT_JOIN[0] = False
         with torch.no_grad():
@@ -433,6 +445,13 @@ class GraphedStep:
         random.setstate(saved["rng"])
         bump_param_epoch()
         torch.cuda.synchronize()
+
+    def capture_all(self):
+        """Capture the graphs of all three index2 values now (otherwise: lazily on first use)."""
+        for k in range(3):
+            if k not in self.graphs:
+                self._capture(k)
+        return self
 
     def load(self, x1, x2, gt, local_views):
         """Stage one batch into the static input buffers (host or device tensors, asynchronous)."""
@@ -449,13 +468,15 @@ class GraphedStep:
         opt = self.opt
         group = opt.param_groups[0]
         draws = draw_scales(self.n_local)
+        if draws[0] not in self.graphs:
+            self._capture(draws[0])
         beta = 0.5 * (1. + math.cos(math.pi * epoch / 240))
         world = dist.get_world_size(opt._pg) if opt._distributed else 1
         thr = 1000.0 if (skip_guard and epoch > 10) else float("inf")
         self.ctl.upload(draws, beta, group["lr"], group["momentum"], group["weight_decay"], 1.0 / world, thr)
         reached = opt.reached_from_draws(self.model, draws)
         opt.upload_flags(reached)
-        self.graph.replay()
+        self.graphs[draws[0]].replay()
         self.last_reached, self.last_draws = reached, draws
         self.pending = thr != float("inf")     # the skip guard may fire: the caller reports the outcome
         if not self.pending:

@@ -99,13 +99,13 @@ def test_graphed_step_matches_eager_step(precision):
     me3, oe3, _, mg_e3, _ = run_trainer(precision, False, n=3)
     mg3, og3, _, mg_g3, _ = run_trainer(precision, True, n=3)
     log(f"[graph {precision}] 3 steps: mg eager {mg_e3:.7f} graph {mg_g3:.7f}")
-    assert abs(mg_g3 - mg_e3) < 2e-3 * abs(mg_e3)
+    assert abs(mg_g3 - mg_e3) < 1e-2 * abs(mg_e3)
     assert oe3._has_buf == og3._has_buf
     for (k, a), (_, b) in zip(me3.state_dict().items(), mg3.state_dict().items()):
         if k.endswith("num_batches_tracked"):
             assert int(a) == int(b) == 9, k
     gs = next(iter(og3._graphed.values()))
-    assert gs.launches > 100
+    assert gs.launches > 100 and 1 <= len(gs.graphs) <= 3
 
 
 def test_reached_parameters_rule_matches_autograd():

@@ -342,6 +342,31 @@ def test_instance_norm_whole_model_backward(precision):
     _check_grads(m, ograds, f"in {precision}", {"fp32x3": 4e-2, "fp32": 0.25}[precision])
 
 
+def test_instance_norm_leaky_relu_block():
+    """north_star's "Conv3d + InstanceNorm + LeakyReLU" block: norm='in', act='leakyrelu' (LeakyReLU is an
+    extension -- the reference's LUConv offers relu / prelu / elu / sigmoid only), forward and every
+    parameter gradient against the oracle's F.instance_norm + F.leaky_relu(0.01) restatement."""
+    sd0 = orc.init_state(0, norm="in", act="leakyrelu")
+    m = PCRLv23d(norm="in", act="leakyrelu", precision="fp32x3")
+    m.load_state_dict(orc.clone_state(sd0))
+    m = m.cuda().train()
+    x1, _, gt, _ = orc.synthetic_batch(2, seed=8, vol=(32, 32, 16))
+    sd = orc.clone_state(sd0)
+    keys = [k for k in sd if orc.is_param(k)]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    o_out, _, o_masks = orc.forward(sd, x1, False, True, "leakyrelu", "in")
+    o_loss = F.mse_loss(o_out, gt) + F.mse_loss(o_masks[1], gt)
+    ograds = dict(zip(keys, torch.autograd.grad(o_loss, [sd[k] for k in keys], allow_unused=True)))
+    out, _, masks = m(x1.cuda())
+    loss = F.mse_loss(out, gt.cuda()) + F.mse_loss(masks[1], gt.cuda())
+    loss.backward()
+    e = rl2(out, o_out)
+    log(f"[in+leakyrelu fp32x3] out rel-L2 {e:.3e}; loss {loss.item():.7f} vs {o_loss.item():.7f}")
+    assert e < 1e-3 and abs(loss.item() - o_loss.item()) < 2e-6
+    _check_grads(m, ograds, "in+leakyrelu fp32x3", 4e-2)
+
+
 @pytest.mark.parametrize("precision", ["fp32x3", "fp32", "bf16"])
 def test_eval_mode_forward_and_backward(precision):
     """model.eval(): BatchNorm normalises with the running statistics (constants of the graph), so
