@@ -157,6 +157,12 @@ int pcrl_im2col27(const float* x, void* out, int N, int D, int H, int W, int dty
  * 1 = fp32, 2 = fp32 transposed (C^T[cols][rows], ldc = rows). */
 int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
                  int cols, int ldc, int out_fp32, int dtype, void* stream);
+/* C[rows][cols] = A * B^T stored in the operand type, plus stats [cols][2] fp64 += per-column (sum, sum of
+ * squares) of the stored C.  With A = pcrl_im2col27(x) and B = the (32, 27 -> 32) stem filter this is the
+ * Conv3d(1 -> 32) stem (models/pcrlv2_model_3d.py:114) with the statistics of its BatchNorm, on the tensor
+ * cores: the SIMT stem kernel runs at 15 % of the HBM rate, this pair of launches at the copy rate. */
+int pcrl_gemm_nt_stats(const void* a, const void* b, void* c, double* stats, long long rows, int K,
+                       int cols, int dtype, void* stream);
 /* C[P][Q] (fp32) += A[rows][P]^T * B[rows][Q] */
 int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, int dtype,
                  void* stream);

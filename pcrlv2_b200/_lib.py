@@ -49,6 +49,7 @@ SIGNATURES = {
     "pcrl_chan1_sigmoid_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _L, _P],
     "pcrl_im2col27": [_P, _P, _I, _I, _I, _I, _I, _P],
     "pcrl_gemm_nt": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P],
+    "pcrl_gemm_nt_stats": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "pcrl_gemm_tn": [_P, _P, _P, _L, _I, _I, _I, _P],
     "pcrl_sgd_flat": [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _P],
     "pcrl_split3_tf32": [_P, _P, _L, _I, _I, _I, _P],

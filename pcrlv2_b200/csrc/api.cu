@@ -23,7 +23,7 @@ EncodeTiledFn get_encode_tiled() {
 
 // launchers defined in igemm_kmajor.cu / igemm_mnmajor.cu / streaming.cu / heads.cu
 int conv3d_k3_igemm(const void*, const void*, void*, double*, int, int, int, int, int, int, int, int, cudaStream_t, int, int);
-int gemm_nt_igemm(const void*, const void*, void*, const float*, long long, int, int, int, int, int, int, int, int, int, cudaStream_t, int);
+int gemm_nt_igemm(const void*, const void*, void*, const float*, long long, int, int, int, int, int, int, int, int, int, cudaStream_t, int, double*);
 int conv3d_k3_wgrad_igemm(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t, int);
 int gemm_tn_igemm(const void*, const void*, float*, long long, int, int, cudaStream_t, int);
 int pack_conv3_weights(const float*, void*, void*, int, int, int, cudaStream_t);
@@ -133,7 +133,7 @@ int pcrl_convT3d_k2s2_fprop(const void* x, const void* wf, const float* bias, vo
   NONNULL(x); NONNULL(wf); NONNULL(y_fine); CHECK_DTYPE(dtype);
   const long long rows = (long long)N * D * (H + 1) * W;
   int rc = gemm_nt_igemm(x, wf, y_fine, bias, rows, Cin, 8 * Cout, Cout, dtype != PCRL_DTYPE_BF16, /*OUT_CONVT*/ 2,
-                         D, H, W, Cout, ST(stream), dtype);
+                         D, H, W, Cout, ST(stream), dtype, nullptr);
   if (rc) return rc;
   return zero_pad_rows(y_fine, (long long)N * 2 * D, 2 * H + 1, (long long)2 * W * Cout * esz(dtype), ST(stream));
 }
@@ -150,7 +150,7 @@ int pcrl_convT3d_k2s2_bwd(const void* g_fine, const void* x, const void* wd, voi
   if (dx) {
     NONNULL(wd);
     rc = gemm_nt_igemm(scratch, wd, dx, nullptr, rows, 8 * Cout, Cin, Cin, dtype != PCRL_DTYPE_BF16, /*OUT_ROWS*/ 1,
-                       0, 0, 0, 0, ST(stream), dtype);
+                       0, 0, 0, 0, ST(stream), dtype, nullptr);
     if (rc) return rc;
   }
   if (dw_packed) {
@@ -225,7 +225,13 @@ int pcrl_gemm_nt(const void* a, const void* b, void* c, const float* bias, long 
                  int cols, int ldc, int out_fp32, int dtype, void* stream) {
   NONNULL(a); NONNULL(b); NONNULL(c); CHECK_DTYPE(dtype);
   return gemm_nt_igemm(a, b, c, bias, rows, K, cols, ldc, out_fp32 != 0, out_fp32 == 2 ? /*OUT_ROWS_T*/ 3 : /*OUT_ROWS*/ 1,
-                       0, 0, 0, 0, ST(stream), dtype);
+                       0, 0, 0, 0, ST(stream), dtype, nullptr);
+}
+int pcrl_gemm_nt_stats(const void* a, const void* b, void* c, double* stats, long long rows, int K, int cols,
+                       int dtype, void* stream) {
+  NONNULL(a); NONNULL(b); NONNULL(c); NONNULL(stats); CHECK_DTYPE(dtype);
+  return gemm_nt_igemm(a, b, c, nullptr, rows, K, cols, cols, dtype != PCRL_DTYPE_BF16, /*OUT_ROWS*/ 1, 0, 0, 0, 0,
+                       ST(stream), dtype, stats);
 }
 int pcrl_gemm_tn(const void* a, const void* b, float* c, long long rows, int P, int Q, int dtype, void* stream) {
   NONNULL(a); NONNULL(b); NONNULL(c); CHECK_DTYPE(dtype);

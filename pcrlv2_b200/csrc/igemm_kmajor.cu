@@ -647,7 +647,7 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
 // (tap, cout) columns of a ConvTranspose3d(k=2,s=2) to the fine H-padded NDHWC tensor.
 int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long long rows, int K,
                   int cols, int ldc, int out_fp32, int out_mode, int ct_D, int ct_H, int ct_W,
-                  int ct_cout, cudaStream_t stream, int dtype) {
+                  int ct_cout, cudaStream_t stream, int dtype, double* stats) {
   const int tf32 = dtype != PCRL_DTYPE_BF16;
   if (tf32) {
     PCRL_REQUIRE(K % 32 == 0, "gemm_nt (fp32): K=%d must be a multiple of 32", K);
@@ -679,6 +679,7 @@ int gemm_nt_igemm(const void* a, const void* b, void* c, const float* bias, long
   p.cout_total = (out_mode == OUT_CONVT) ? ct_cout : cols;
   p.ct_D = ct_D; p.ct_H = ct_H; p.ct_W = ct_W;
   p.has_bias = bias != nullptr; p.bias = bias; p.out = c; p.exact_out = dtype == PCRL_DTYPE_F32X;
+  p.has_stats = stats != nullptr; p.stats = stats; p.stats_per_sample = 0;   // column sums / sums of squares
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
   uint64_t str[1] = {(uint64_t)K * elt};
   uint32_t box[2] = {(uint32_t)p.kc, 128};

@@ -400,9 +400,31 @@ __device__ __forceinline__ float act_d(float z, int act, float slope) {
   return act_bwd(z, act, slope);
 }
 
+// Per-channel constants of the norm/act kernels live in SHARED memory, not in registers: a thread owns
+// 8 channels, and 5-6 constant arrays of 8 floats each pushed the two-pass backward kernel to 154-255
+// registers = ONE resident block per SM (ncu, profiles/r02g_ncu_norm_act.md: 12 % warps active, 2.3 TB/s
+// in bf16).  They are fetched per use with volatile shared loads (the compiler would otherwise hoist them
+// back into registers); with two rows in flight per thread the kernels fit 3 blocks per SM.
+__device__ __forceinline__ void ldc8(const float* p, float (&f)[8]) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(a + 16));
+}
+// slots 3 / 4 hold (invstd, mean*invstd) in the statistics pass and (gs, c1) in the apply pass: 7 slots keep
+// the largest layer (C = 512) under the 48 KB default dynamic shared memory limit
+enum { K_SC = 0, K_SH = 1, K_SL = 2, K_IS = 3, K_MIS = 4, K_GS = 3, K_C1 = 4, K_GA = 5, K_C2 = 6, K_COUNT = 7 };
+// Layout of one constant array in shared memory: [C/8][12] floats -- the 8 values of a channel group plus 4
+// floats of padding.  With a plain [C] array the 32-byte reads of the 8 channel groups of a quarter-warp
+// sit 32 bytes apart and collide pairwise in the banks (ncu: 4e7 bank conflicts per launch, short-scoreboard
+// the top stall); a 48-byte pitch makes both 16-byte halves conflict-free.
+#define CPITCH 12
+__device__ __forceinline__ int cidx(int k, int c, int C8) { return (k * C8 + (c >> 3)) * CPITCH + (c & 7); }
+
 template <typename T, bool POOL, int ACT>
-__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParams<T> p) {
-  extern __shared__ float red[];  // [blockDim.x][8] when avg_sum
+__global__ void __launch_bounds__(256, POOL ? 2 : 3) norm_act_fwd_kernel(const NormActFwdParams<T> p) {
+  extern __shared__ float smem_f[];
+  float* cst = smem_f;                     // [3][C]: scale, shift, prelu slope
+  float* red = smem_f + 3 * (p.C >> 3) * CPITCH;   // [blockDim.x][8] when avg_sum
   const int n = blockIdx.y;
   const int C8 = p.C >> 3;
   const int H1 = p.H + 1;
@@ -411,33 +433,47 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
   const int cws = cw / p.wseg, Rv = R * p.wseg;   // segment width, virtual (row, segment) count
   const RowMap m = make_row_map(cws, C8);
   const bool lane_ok = m.t_row < m.rows_per_iter && m.chunks == 1;
-  float asum[8], sc[8], sh[8], sl[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) asum[i] = 0.f;
   {
-    const size_t o = (p.per_sample ? (size_t)n * p.C : 0) + m.c8 * 8;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      sc[i] = p.scale[o + i];
-      sh[i] = p.shift[o + i];
-      sl[i] = p.prelu ? p.prelu[m.c8 * 8 + i] : 0.f;
+    const size_t o = p.per_sample ? (size_t)n * p.C : 0;
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      cst[cidx(K_SC, c, C8)] = p.scale[o + c];
+      cst[cidx(K_SH, c, C8)] = p.shift[o + c];
+      cst[cidx(K_SL, c, C8)] = p.prelu ? p.prelu[c] : 0.f;
     }
   }
+  __syncthreads();
+  const float* my = cst + m.c8 * CPITCH;
+  const int KS = C8 * CPITCH;                  // floats between two constant arrays
+  float asum[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) asum[i] = 0.f;
   constexpr int U = POOL ? 1 : 4;
   const size_t row_elems = (size_t)p.W * p.C;            // elements of one fine row
-  for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < Rv; row0 += gridDim.x * m.rows_per_iter * U) {
+  const size_t base = (size_t)n * R * row_elems + m.c8 * 8;      // non-POOL: + row*row_elems + w*C
+  // Row bookkeeping without integer division in the loop (rows no wider than a block, wseg == 1: every
+  // 64x64x32 shape): row % period and row / period of the thread's first row are advanced incrementally;
+  // the generic path divides (the divisions were ~2/3 of the instructions issued per row)
+  const int rpi = m.rows_per_iter, stride = gridDim.x * rpi * U, period = POOL ? ch + 1 : H1;
+  const bool w1 = p.wseg == 1;
+  int rem0 = (blockIdx.x * rpi * U + m.t_row) % period, quo0 = (blockIdx.x * rpi * U + m.t_row) / period;
+  const int d_rem = stride % period, d_quo = stride / period, u_rem = rpi % period;
+  for (int row0 = blockIdx.x * rpi * U; row0 < Rv;
+       row0 += stride, rem0 += d_rem, quo0 += d_quo + (rem0 >= period ? 1 : 0), rem0 -= (rem0 >= period ? period : 0)) {
     if (!POOL) {
+      int rem = rem0;
       V8<T> yv[U];
       int kind[U];
       size_t off[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int vrow = row0 + u * m.rows_per_iter + m.t_row;
-        const int row = vrow / p.wseg, w = (vrow % p.wseg) * cws + m.w;
+        const int vrow = row0 + u * rpi + m.t_row;
+        int row, w, hp;
+        if (w1) { row = vrow; w = m.w; hp = rem; rem += u_rem; rem -= (rem >= H1 ? H1 : 0); }
+        else { row = vrow / p.wseg; w = (vrow % p.wseg) * cws + m.w; hp = row % H1; }
         kind[u] = 0;
         if (lane_ok && vrow < Rv) {
-          off[u] = ((size_t)n * R + row) * row_elems + (size_t)w * p.C + m.c8 * 8;
-          kind[u] = (row % H1) == 0 ? 1 : 2;
+          off[u] = base + (size_t)row * row_elems + (size_t)w * p.C;
+          kind[u] = hp == 0 ? 1 : 2;
           if (kind[u] == 2) yv[u] = ld8(p.y + off[u]);
         }
       }
@@ -446,10 +482,13 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
         if (kind[u] == 1) {
           if (p.a_out) z8(p.a_out + off[u]);
         } else if (kind[u] == 2) {
-          float v[8];
+          float v[8], sc[8], sh[8], sl[8];
           up8(yv[u], v);
+          ldc8(my + K_SC * KS, sc);
+          ldc8(my + K_SH * KS, sh);
+          if (ACT != ACT_RELU) ldc8(my + K_SL * KS, sl);
 #pragma unroll
-          for (int q = 0; q < 8; q++) v[q] = act_f<ACT>(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
+          for (int q = 0; q < 8; q++) v[q] = act_f<ACT>(fmaf(v[q], sc[q], sh[q]), p.act, ACT != ACT_RELU ? sl[q] : 0.f);
           rnd8(T(), v);  // average the stored (rounded) activations
           if (p.a_out) st8(p.a_out + off[u], v);
           if (p.avg_sum) {
@@ -461,8 +500,9 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
     } else {
       const int vrow = row0 + m.t_row;
       if (!(lane_ok && vrow < Rv)) continue;
-      const int row = vrow / p.wseg, w = (vrow % p.wseg) * cws + m.w;
-      const int hp = row % (ch + 1), d = row / (ch + 1);
+      int row, w, hp, d;
+      if (w1) { row = vrow; w = m.w; hp = rem0; d = quo0; }
+      else { row = vrow / p.wseg; w = (vrow % p.wseg) * cws + m.w; hp = row % (ch + 1); d = row / (ch + 1); }
       const size_t pooled_off = (((size_t)n * R + row) * cw + w) * p.C + m.c8 * 8;
       if (hp == 0) {  // pad rows of the outputs
         if (p.pool_out) z8(p.pool_out + pooled_off);
@@ -480,7 +520,10 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
         yv[pos] = ld8(
             p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * p.C + m.c8 * 8);
       }
-      float mx[8];
+      float mx[8], sc[8], sh[8], sl[8];
+      ldc8(my + K_SC * KS, sc);
+      ldc8(my + K_SH * KS, sh);
+      if (ACT != ACT_RELU) ldc8(my + K_SL * KS, sl);
 #pragma unroll
       for (int i = 0; i < 8; i++) mx[i] = -INFINITY;
 #pragma unroll
@@ -490,7 +533,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
         up8(yv[pos], v);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          v[q] = act_f<ACT>(fmaf(v[q], sc[q], sh[q]), p.act, sl[q]);
+          v[q] = act_f<ACT>(fmaf(v[q], sc[q], sh[q]), p.act, ACT != ACT_RELU ? sl[q] : 0.f);
           mx[q] = fmaxf(mx[q], v[q]);
         }
         if (p.a_out)
@@ -520,9 +563,9 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwdParam
 
 // ------------------------------------------------------------------------------ norm + act backward
 // Upstream gradient wrt a = act(z), z = y*scale + shift:
-//   g1: H-padded bf16, full resolution, or (POOL) the gradient wrt the 2x2x2 max-pooled tensor,
+//   g1: H-padded, full resolution, or (POOL) the gradient wrt the 2x2x2 max-pooled tensor,
 //       routed to the first maximum of each cell (torch's MaxPool3d tie rule);
-//   g2: optional second full-resolution gradient (bf16), added;
+//   g2: optional second full-resolution gradient, added (G2: compile-time, only the tail layers have it);
 //   gavg: optional [N][C] fp32 gradient wrt the global average pool; adds gavg/(D*H*W).
 // pass 1 accumulates per (group, channel): sum dz, sum dz*xhat (and sum dA*min(z,0) for PReLU);
 // pass 2 writes dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), pad rows zero.
@@ -538,61 +581,82 @@ struct NormActBwdParams {
   int wseg;          // a row of W voxels is processed as wseg segments (rows wider than one block)
 };
 
-template <typename T, bool POOL, bool APPLY, int ACT>
-__global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParams<T> p) {
-  extern __shared__ float red[];  // pass 1: [blockDim.x][24]
+template <typename T, bool POOL, bool APPLY, int ACT, bool G2>
+__global__ void __launch_bounds__(256, POOL ? 2 : 3) norm_act_bwd_kernel(const NormActBwdParams<T> p) {
+  extern __shared__ float smem_f[];
+  float* cst = smem_f;                       // [K_COUNT][C]
+  float* red = smem_f + K_COUNT * (p.C >> 3) * CPITCH;       // pass 1: [blockDim.x][24]
   const int n = blockIdx.y;
-  const int C8 = p.C >> 3;
+  const int C = p.C, C8 = p.C >> 3;
   const int H1 = p.H + 1;
   const int cd = POOL ? p.D / 2 : p.D, ch = POOL ? p.H / 2 : p.H, cw = POOL ? p.W / 2 : p.W;
   const int R = cd * (ch + 1);
   const int cws = cw / p.wseg, Rv = R * p.wseg;   // segment width, virtual (row, segment) count
   const RowMap m = make_row_map(cws, C8);
   const bool lane_ok = m.t_row < m.rows_per_iter && m.chunks == 1;
-  const size_t so = (p.per_sample ? (size_t)n * p.C : 0) + m.c8 * 8;
-  // x_hat = y*is - mis ; z = y*sc + sh ; apply: dy = gs*dz - c1 - y*c2   (constants folded)
-  float sc[8], sh[8], sl[8], is[8], mis[8], c1[8], c2[8], gs[8], ga[8];
-  const float inv_vol = 1.f / ((float)p.D * p.H * p.W);
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    sc[i] = p.scale[so + i];
-    sh[i] = p.shift[so + i];
-    is[i] = p.invstd[so + i];
-    mis[i] = p.mean[so + i] * is[i];
-    sl[i] = p.prelu ? p.prelu[m.c8 * 8 + i] : 0.f;
-    ga[i] = p.gavg ? p.gavg[(size_t)n * p.C + m.c8 * 8 + i] * inv_vol : 0.f;
-    gs[i] = c1[i] = c2[i] = 0.f;
-    if (APPLY) {
-      const double* s = p.sums + (so + i) * 3;
-      const float k1 = (float)(s[0] / p.count), k2 = (float)(s[1] / p.count);
-      gs[i] = p.gamma[m.c8 * 8 + i] * is[i];
-      // gs*(dz - k1 - xh*k2) with xh = y*is - mis
-      c1[i] = gs[i] * (k1 - mis[i] * k2);
-      c2[i] = gs[i] * k2 * is[i];
+  // x_hat = y*is - mis ; z = y*sc + sh ; apply: dy = gs*dz - c1 - y*c2   (constants folded, one value per
+  // channel computed by one thread)
+  {
+    const size_t o = p.per_sample ? (size_t)n * C : 0;
+    const float inv_vol = 1.f / ((float)p.D * p.H * p.W);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float is = p.invstd[o + c], mis = p.mean[o + c] * is;
+      cst[cidx(K_SC, c, C8)] = p.scale[o + c];
+      cst[cidx(K_SH, c, C8)] = p.shift[o + c];
+      cst[cidx(K_SL, c, C8)] = p.prelu ? p.prelu[c] : 0.f;
+      if (!APPLY) {
+        cst[cidx(K_IS, c, C8)] = is;
+        cst[cidx(K_MIS, c, C8)] = mis;
+      }
+      cst[cidx(K_GA, c, C8)] = p.gavg ? p.gavg[(size_t)n * C + c] * inv_vol : 0.f;
+      if (APPLY) {
+        const double* sm = p.sums + (o + c) * 3;
+        const float k1 = (float)(sm[0] / p.count), k2 = (float)(sm[1] / p.count);
+        const float gs = p.gamma[c] * is;
+        cst[cidx(K_GS, c, C8)] = gs;
+        cst[cidx(K_C1, c, C8)] = gs * (k1 - mis * k2);      // gs*(dz - k1 - xh*k2) with xh = y*is - mis
+        cst[cidx(K_C2, c, C8)] = gs * k2 * is;
+      }
     }
   }
+  __syncthreads();
+  const float* my = cst + m.c8 * CPITCH;
+  const int KS = C8 * CPITCH;                  // floats between two constant arrays
+  const bool has_ga = p.gavg != nullptr;
   float a0[8], a1[8], a2[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) a0[i] = a1[i] = a2[i] = 0.f;
-  constexpr int U = POOL ? 1 : 4;
-  const size_t row_elems = (size_t)p.W * p.C;
-  for (int row0 = blockIdx.x * m.rows_per_iter * U; row0 < Rv; row0 += gridDim.x * m.rows_per_iter * U) {
+  constexpr int U = POOL ? 1 : (sizeof(T) == 2 ? 4 : 2);     // see norm_act_fwd_kernel
+  const size_t row_elems = (size_t)p.W * C;
+  const size_t base = (size_t)n * R * row_elems + m.c8 * 8;      // non-POOL: + row*row_elems + w*C
+  // Row bookkeeping without integer division in the loop (rows no wider than a block, wseg == 1: every
+  // 64x64x32 shape): row % period and row / period of the thread's first row are advanced incrementally;
+  // the generic path divides (the divisions were ~2/3 of the instructions issued per row)
+  const int rpi = m.rows_per_iter, stride = gridDim.x * rpi * U, period = POOL ? ch + 1 : H1;
+  const bool w1 = p.wseg == 1;
+  int rem0 = (blockIdx.x * rpi * U + m.t_row) % period, quo0 = (blockIdx.x * rpi * U + m.t_row) / period;
+  const int d_rem = stride % period, d_quo = stride / period, u_rem = rpi % period;
+  for (int row0 = blockIdx.x * rpi * U; row0 < Rv;
+       row0 += stride, rem0 += d_rem, quo0 += d_quo + (rem0 >= period ? 1 : 0), rem0 -= (rem0 >= period ? period : 0)) {
     if (!POOL) {
+      int rem = rem0;
       V8<T> yq[U], g1q[U], g2q[U];
       int kind[U];
       size_t off[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int vrow = row0 + u * m.rows_per_iter + m.t_row;
-        const int row = vrow / p.wseg, w = (vrow % p.wseg) * cws + m.w;
+        const int vrow = row0 + u * rpi + m.t_row;
+        int row, w, hp;
+        if (w1) { row = vrow; w = m.w; hp = rem; rem += u_rem; rem -= (rem >= H1 ? H1 : 0); }
+        else { row = vrow / p.wseg; w = (vrow % p.wseg) * cws + m.w; hp = row % H1; }
         kind[u] = 0;
         if (lane_ok && vrow < Rv) {
-          off[u] = ((size_t)n * R + row) * row_elems + (size_t)w * p.C + m.c8 * 8;
-          kind[u] = (row % H1) == 0 ? 1 : 2;
+          off[u] = base + (size_t)row * row_elems + (size_t)w * C;
+          kind[u] = hp == 0 ? 1 : 2;
           if (kind[u] == 2) {
             yq[u] = ld8(p.y + off[u]);
             if (p.g1) g1q[u] = ld8(p.g1 + off[u]);
-            if (p.g2) g2q[u] = ld8(p.g2 + off[u]);
+            if (G2) g2q[u] = ld8(p.g2 + off[u]);
           }
         }
       }
@@ -601,50 +665,90 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
         if (kind[u] == 1) {
           if (APPLY) z8(p.dy + off[u]);
         } else if (kind[u] == 2) {
-          float yv[8], g1v[8], g2v[8], out[8];
+          float yv[8], da[8], t[8], z[8];
           up8(yq[u], yv);
-          if (p.g1) up8(g1q[u], g1v);
-          if (p.g2) up8(g2q[u], g2v);
+          if (has_ga) ldc8(my + K_GA * KS, da);
+          else {
 #pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const float z = fmaf(yv[q], sc[q], sh[q]);
-            float da = ga[q];
-            if (p.g1) da += g1v[q];
-            if (p.g2) da += g2v[q];
-            const float dz = da * act_d<ACT>(z, p.act, sl[q]);
-            if (APPLY) {
-              out[q] = fmaf(gs[q], dz, -fmaf(yv[q], c2[q], c1[q]));
-            } else {
-              a0[q] += dz;
-              a1[q] = fmaf(dz, fmaf(yv[q], is[q], -mis[q]), a1[q]);
-              if (ACT != ACT_RELU) a2[q] += da * fminf(z, 0.f);
+            for (int q = 0; q < 8; q++) da[q] = 0.f;
+          }
+          if (p.g1) {
+            up8(g1q[u], t);
+#pragma unroll
+            for (int q = 0; q < 8; q++) da[q] += t[q];
+          }
+          if (G2) {
+            up8(g2q[u], t);
+#pragma unroll
+            for (int q = 0; q < 8; q++) da[q] += t[q];
+          }
+          {
+            float sc[8], sh[8];
+            ldc8(my + K_SC * KS, sc);
+            ldc8(my + K_SH * KS, sh);
+#pragma unroll
+            for (int q = 0; q < 8; q++) z[q] = fmaf(yv[q], sc[q], sh[q]);
+          }
+          if (ACT != ACT_RELU) {
+            ldc8(my + K_SL * KS, t);
+            if (!APPLY) {
+#pragma unroll
+              for (int q = 0; q < 8; q++) a2[q] += da[q] * fminf(z[q], 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) da[q] *= act_bwd(z[q], p.act, t[q]);      // da now holds dz
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) da[q] = z[q] > 0.f ? da[q] : 0.f;
+          }
+          if (APPLY) {
+            float gs[8], c1[8], c2[8];
+            ldc8(my + K_GS * KS, gs);
+            ldc8(my + K_C1 * KS, c1);
+            ldc8(my + K_C2 * KS, c2);
+#pragma unroll
+            for (int q = 0; q < 8; q++) z[q] = fmaf(gs[q], da[q], -fmaf(yv[q], c2[q], c1[q]));
+            st8(p.dy + off[u], z);
+          } else {
+            float is[8], mis[8];
+            ldc8(my + K_IS * KS, is);
+            ldc8(my + K_MIS * KS, mis);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              a0[q] += da[q];
+              a1[q] = fmaf(da[q], fmaf(yv[q], is[q], -mis[q]), a1[q]);
             }
           }
-          if (APPLY) st8(p.dy + off[u], out);
         }
       }
     } else {
       const int vrow = row0 + m.t_row;
       if (!(lane_ok && vrow < Rv)) continue;
-      const int row = vrow / p.wseg, w = (vrow % p.wseg) * cws + m.w;
-      const int hp = row % (ch + 1), d = row / (ch + 1);
+      int row, w, hp, d;
+      if (w1) { row = vrow; w = m.w; hp = rem0; d = quo0; }
+      else { row = vrow / p.wseg; w = (vrow % p.wseg) * cws + m.w; hp = row % (ch + 1); d = row / (ch + 1); }
       if (hp == 0) {
         if (APPLY)
           for (int i = 0; i < 2; i++)
             for (int k = 0; k < 2; k++)
-              z8(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * w + k) * p.C + m.c8 * 8);
+              z8(p.dy + ((((size_t)n * p.D + 2 * d + i) * H1) * p.W + 2 * w + k) * C + m.c8 * 8);
         continue;
       }
       const int h = hp - 1;
       float gp[8];
-      up8(ld8(p.g1 + (((size_t)n * R + row) * cw + w) * p.C + m.c8 * 8), gp);
+      up8(ld8(p.g1 + (((size_t)n * R + row) * cw + w) * C + m.c8 * 8), gp);
       V8<T> yq[8];
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
         yq[pos] = ld8(
-            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * p.C + m.c8 * 8);
+            p.y + ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * C + m.c8 * 8);
       }
+      float sc[8], sh[8], sl[8], ga[8];
+      ldc8(my + K_SC * KS, sc);
+      ldc8(my + K_SH * KS, sh);
+      if (ACT != ACT_RELU) ldc8(my + K_SL * KS, sl);
+      if (has_ga) ldc8(my + K_GA * KS, ga);
       int arg[8];
       float mx[8];
 #pragma unroll
@@ -656,32 +760,45 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           // same fp32 values and scan order as the forward pass: the first maximum wins
-          const float a = act_f<ACT>(fmaf(yv[q], sc[q], sh[q]), p.act, sl[q]);
+          const float a = act_f<ACT>(fmaf(yv[q], sc[q], sh[q]), p.act, ACT != ACT_RELU ? sl[q] : 0.f);
           if (a > mx[q]) { mx[q] = a; arg[q] = pos; }
         }
       }
 #pragma unroll
       for (int pos = 0; pos < 8; pos++) {
         const int i = pos >> 2, j = (pos >> 1) & 1, k = pos & 1;
-        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * p.C + m.c8 * 8;
-        float yv[8], g2v[8], out[8];
-        up8(yq[pos], yv);
-        if (p.g2) up8(ld8(p.g2 + off), g2v);
+        const size_t off = ((((size_t)n * p.D + 2 * d + i) * H1 + 2 * h + j + 1) * p.W + 2 * w + k) * C + m.c8 * 8;
+        float yv[8], g2v[8], out[8], dzv[8];
+        // y is re-read here (an L1 / L2 hit: this thread loaded the same 8 vectors a moment ago) instead of
+        // keeping all eight positions live across both loops, which spilled at 2 blocks per SM
+        up8(ld8(p.y + off), yv);
+        if (G2) up8(ld8(p.g2 + off), g2v);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const float z = fmaf(yv[q], sc[q], sh[q]);
-          float da = (arg[q] == pos ? gp[q] : 0.f) + ga[q];
-          if (p.g2) da += g2v[q];
-          const float dz = da * act_d<ACT>(z, p.act, sl[q]);
-          if (APPLY) {
-            out[q] = fmaf(gs[q], dz, -fmaf(yv[q], c2[q], c1[q]));
-          } else {
-            a0[q] += dz;
-            a1[q] = fmaf(dz, fmaf(yv[q], is[q], -mis[q]), a1[q]);
-            if (ACT != ACT_RELU) a2[q] += da * fminf(z, 0.f);
+          float da = (arg[q] == pos ? gp[q] : 0.f) + (has_ga ? ga[q] : 0.f);
+          if (G2) da += g2v[q];
+          dzv[q] = da * act_d<ACT>(z, p.act, ACT != ACT_RELU ? sl[q] : 0.f);
+          if (!APPLY && ACT != ACT_RELU) a2[q] += da * fminf(z, 0.f);
+        }
+        if (APPLY) {
+          float gs[8], c1[8], c2[8];
+          ldc8(my + K_GS * KS, gs);
+          ldc8(my + K_C1 * KS, c1);
+          ldc8(my + K_C2 * KS, c2);
+#pragma unroll
+          for (int q = 0; q < 8; q++) out[q] = fmaf(gs[q], dzv[q], -fmaf(yv[q], c2[q], c1[q]));
+          st8(p.dy + off, out);
+        } else {
+          float is[8], mis[8];
+          ldc8(my + K_IS * KS, is);
+          ldc8(my + K_MIS * KS, mis);
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            a0[q] += dzv[q];
+            a1[q] = fmaf(dzv[q], fmaf(yv[q], is[q], -mis[q]), a1[q]);
           }
         }
-        if (APPLY) st8(p.dy + off, out);
       }
     }
   }
@@ -701,7 +818,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormActBwdParam
       for (int j = grp; j < blockDim.x; j += C8)
 #pragma unroll
         for (int q = 0; q < 8; q++) t[q] += red[j * 24 + which * 8 + q];
-      const size_t o = (p.per_sample ? (size_t)n * p.C : 0) + grp * 8;
+      const size_t o = (p.per_sample ? (size_t)n * C : 0) + grp * 8;
 #pragma unroll
       for (int q = 0; q < 8; q++) atomicAdd(&p.sums[(o + q) * 3 + which], (double)t[q]);
     }
@@ -919,7 +1036,7 @@ static int norm_act_fwd_t(const void* y, const float* scale, const float* shift,
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(bx, N);
-  const size_t smem = avg_sum ? (size_t)256 * 8 * 4 : 0;
+  const size_t smem = (size_t)3 * (C / 8) * CPITCH * 4 + (avg_sum ? (size_t)256 * 8 * 4 : 0);
   const bool relu = act == ACT_RELU;
   if (pool) {
     if (relu) norm_act_fwd_kernel<T, true, ACT_RELU><<<grid, 256, smem, s>>>(p);
@@ -955,7 +1072,7 @@ static int norm_act_bwd_t(const void* y, const void* g1, const void* g2, const f
   const int cw = pool ? W / 2 : W;
   NormActBwdParams<T> p{(const T*)y, (const T*)g1, (const T*)g2, gavg, scale, shift, mean, invstd, gamma,
                         prelu, sums, (T*)dy, count, per_sample, act, N, D, H, W, C, row_segments(cw, C / 8)};
-  const int items = (cw / p.wseg) * (C / 8), rpi = 256 / items, U = pool ? 1 : 4;
+  const int items = (cw / p.wseg) * (C / 8), rpi = 256 / items, U = pool ? 1 : (sizeof(T) == 2 ? 4 : 2);
   const int R = (pool ? (D / 2) * (H / 2 + 1) : D * (H + 1)) * p.wseg;
   int bx = (R + rpi * U - 1) / (rpi * U);
   const int cap = (num_sms() * 8 + N - 1) / N;
@@ -963,19 +1080,27 @@ static int norm_act_bwd_t(const void* y, const void* g1, const void* g2, const f
   if (bx < 1) bx = 1;
   dim3 grid(bx, N);
   const bool relu = act == ACT_RELU;
-#define PCRL_LAUNCH_BWD(POOLV, APPLYV, SMEM)                                                 \
-  do {                                                                                       \
-    if (relu) norm_act_bwd_kernel<T, POOLV, APPLYV, ACT_RELU><<<grid, 256, SMEM, s>>>(p);    \
-    else norm_act_bwd_kernel<T, POOLV, APPLYV, -1><<<grid, 256, SMEM, s>>>(p);               \
+  const bool has_g2 = g2 != nullptr;
+  const size_t csm = (size_t)K_COUNT * (C / 8) * CPITCH * 4;
+#define PCRL_LAUNCH_BWD2(POOLV, APPLYV, SMEM, G2V)                                                \
+  do {                                                                                            \
+    if (relu) norm_act_bwd_kernel<T, POOLV, APPLYV, ACT_RELU, G2V><<<grid, 256, SMEM, s>>>(p);    \
+    else norm_act_bwd_kernel<T, POOLV, APPLYV, -1, G2V><<<grid, 256, SMEM, s>>>(p);               \
+  } while (0)
+#define PCRL_LAUNCH_BWD(POOLV, APPLYV, SMEM)                    \
+  do {                                                          \
+    if (has_g2) PCRL_LAUNCH_BWD2(POOLV, APPLYV, SMEM, true);    \
+    else PCRL_LAUNCH_BWD2(POOLV, APPLYV, SMEM, false);          \
   } while (0)
   if (pass == 0) {
-    const size_t smem = (size_t)256 * 24 * 4;
+    const size_t smem = csm + (size_t)256 * 24 * 4;
     if (pool) PCRL_LAUNCH_BWD(true, false, smem);
     else PCRL_LAUNCH_BWD(false, false, smem);
   } else {
-    if (pool) PCRL_LAUNCH_BWD(true, true, 0);
-    else PCRL_LAUNCH_BWD(false, true, 0);
+    if (pool) PCRL_LAUNCH_BWD(true, true, csm);
+    else PCRL_LAUNCH_BWD(false, true, csm);
   }
+#undef PCRL_LAUNCH_BWD2
 #undef PCRL_LAUNCH_BWD
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;

@@ -365,16 +365,41 @@ def chan1_sigmoid_bwd(y, mask, dmask, mean, invstd, gamma, per_sample, batch_sta
     return dy, sums
 
 
-def stem_conv_wgrad_gemm(dyp, x, exact=False):
-    """Stem weight gradient on the tensor cores: im2col of the 1-channel input to [rows,32]
-    (27 taps), rows paired into 64-wide operands, dW = sum of the diagonal 32x32 blocks of
-    gemm_tn(dY, X27)."""
-    _chk(dyp), _chk(x, torch.float32)
+def im2col27(x, dtype, exact=False):
+    """x (N,1,D,H,W) fp32 -> X27 [rows, 32] in ``dtype`` (H-padded row order, X27[u][tap] = x[u + tap])."""
+    _chk(x, torch.float32)
     n, _, d, h, w = x.shape
-    rows = n * d * (h + 1) * w
-    x27 = torch.empty((rows, 32), dtype=dyp.dtype, device=x.device)
-    _lib.call("pcrl_im2col27", x, x27, n, d, h, w, _dt(dyp, exact))
-    out = torch.zeros((64, 64), dtype=torch.float32, device=x.device)
+    x27 = torch.empty((n * d * (h + 1) * w, 32), dtype=dtype, device=x.device)
+    _lib.call("pcrl_im2col27", x, x27, n, d, h, w, _code(dtype, exact))
+    return x27
+
+
+def stem_pack_weights(w, dtype):
+    """(32,1,3,3,3) fp32 -> [32 out, 32 taps] GEMM operand (taps 27..31 zero), rounded to the operand type."""
+    w32 = torch.nn.functional.pad(w.detach().reshape(32, 27), (0, 5)).contiguous()
+    if dtype == torch.float32:      # cvt.rna.tf32 (round to nearest, ties away) of the magnitude bits
+        return ((w32.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return w32.to(dtype)
+
+
+def stem_conv_fprop_gemm(x27, wst, dims, stats):
+    """Conv3d(1 -> 32) as X27 * Wst^T on the tensor cores with the BatchNorm statistics in the epilogue.
+    Returns the H-padded activation [N,D,H+1,W,32] (pad rows are zero because X27's are)."""
+    n, d, h, w = dims
+    y = torch.empty((n, d, h + 1, w, 32), dtype=x27.dtype, device=x27.device)
+    _lib.call("pcrl_gemm_nt_stats", x27, wst, y, stats, x27.shape[0], 32, 32, _dt(x27))
+    return y
+
+
+def stem_conv_wgrad_gemm(dyp, x, exact=False, x27=None):
+    """Stem weight gradient on the tensor cores: im2col of the 1-channel input to [rows,32]
+    (27 taps; ``x27``: the one the forward pass already made), rows paired into 64-wide operands,
+    dW = sum of the diagonal 32x32 blocks of gemm_tn(dY, X27)."""
+    _chk(dyp)
+    rows = dyp.numel() // 32
+    if x27 is None:
+        x27 = im2col27(x, dyp.dtype, exact)
+    out = torch.zeros((64, 64), dtype=torch.float32, device=dyp.device)
     if exact:
         _lib.call("pcrl_gemm_tn", split3(dyp.reshape(rows // 2, 64), 1, stack=True),
                   split3(x27.reshape(rows // 2, 64), 0, stack=True), out, 3 * (rows // 2), 64, 64, F32X)

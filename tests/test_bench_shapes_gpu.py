@@ -60,3 +60,29 @@ def test_conv3_fprop_dgrad_wgrad_at_bench_shapes(shape, dtype):
     if cout % 64 == 0:
         gpk = K.conv3d_k3_wgrad(dyp, xp)
         assert rel(K.unpack_conv3_wgrad(gpk), wt.grad) < 3e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(32, 64, 64, 32), (192, 16, 16, 16), (3, 8, 24, 8)], ids=lambda s: "x".join(map(str, s)))
+def test_stem_as_im2col_gemm(shape, dtype):
+    """Conv3d(1 -> 32) as im2col27 + K = 32 tensor-core GEMM with the statistics epilogue (the path
+    LUConv takes in train mode with BatchNorm) against torch's fp32 convolution on operand-representable
+    inputs; the kept X27 feeds the weight gradient."""
+    n, d, h, w = shape
+    torch.manual_seed(11)
+    x = rep(torch.randn(n, 1, d, h, w, device=DEV), dtype)
+    wt = rep(torch.randn(32, 1, 3, 3, 3, device=DEV) / 27 ** 0.5, dtype).requires_grad_(True)
+    ref = F.conv3d(x, wt, padding=1)
+    x27 = K.im2col27(x, dtype)
+    stats = torch.zeros(1, 32, 2, dtype=torch.float64, device=DEV)
+    y = K.stem_conv_fprop_gemm(x27, K.stem_pack_weights(wt, dtype), (n, d, h, w), stats)
+    got = K.unpad_ndhwc(y)
+    assert rel(got, ref) < (3e-4 if dtype == torch.float32 else 1.2e-2)
+    assert y[:, :, 0].abs().max().item() == 0                       # pad rows are produced zero
+    assert rel(stats[0, :, 0], got.double().sum(dim=(0, 2, 3, 4))) < 1e-4 or \
+        (stats[0, :, 0] - got.double().sum(dim=(0, 2, 3, 4))).abs().max() < 1e-2
+    assert rel(stats[0, :, 1], (got.double() ** 2).sum(dim=(0, 2, 3, 4))) < 1e-5
+    dy = rep(torch.randn_like(ref), dtype)
+    ref.backward(dy)
+    dw = K.stem_conv_wgrad_gemm(K.pad_ndhwc(dy, dtype), None, x27=x27)
+    assert rel(dw, wt.grad) < 3e-4

@@ -121,6 +121,13 @@ def _worker(rank, world, port, out_path):
     dist.barrier()
     if rank == 0:
         open(out_path, "w").write("ok\n" + "\n".join(log))
+    # captured graphs hold NCCL operations: release them before the communicator is torn down
+    # (destroy_process_group otherwise waits forever)
+    import gc
+    opt2._graphed.clear()
+    del m2, opt2
+    gc.collect()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 
