@@ -240,6 +240,35 @@ int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf,
                   int nseg, float lr, float momentum, float weight_decay, float grad_scale,
                   void* stream);
 
+/* ---- GPU-side input staging: the per-item torchio transforms of data.py:73-89 /
+ * datasets/lunaDataset.py:28-81 as batched kernels over [B][D][H][W] fp32 volumes.  Random parameters are
+ * drawn by the host and passed in (device arrays of B entries). ------------------------------------- */
+/* torchio RandomFlip: bit 0 / 1 / 2 of axis_mask[b] mirrors axis D / H / W */
+int pcrl_aug_flip(const float* x, float* y, const int* axis_mask, int B, int D, int H, int W, void* stream);
+/* torchio RandomBlur = scipy.ndimage.gaussian_filter per axis: radius int(4 sigma + 0.5), fp64 weights and
+ * accumulation, boundary 'reflect'; sigma[b*sigma_stride + axis]; axis 0 / 1 / 2 = D / H / W; out of place */
+int pcrl_aug_blur_axis(const float* x, float* y, const float* sigma, int sigma_stride, int axis, int B,
+                       int D, int H, int W, void* stream);
+/* torchio RandomNoise then RandomGamma: t = x + noise_std[b] * n, y = sign(t) |t|^exp(log_gamma[b]); n from
+ * `noise` [B][vol] when given, else from a counter-based generator keyed by (seed, b, voxel) */
+int pcrl_aug_noise_gamma(const float* x, float* y, const float* noise, const float* noise_std,
+                         const float* log_gamma, unsigned long long seed, int B, int vol, void* stream);
+/* torchio RandomSwap(patch_size, num_iterations): corners [B][iters][6] = first / second patch origin (d,h,w);
+ * swaps are applied in order, in place */
+int pcrl_aug_swap(float* x, const int* corners, int iters, int pd, int ph, int pw, int B, int D, int H,
+                  int W, void* stream);
+/* torchio ZNormalization: (x - mean) / std per volume (Bessel-corrected std) */
+int pcrl_aug_znorm(const float* x, float* y, int B, int vol, void* stream);
+
+/* ---- offline crop generator pieces ---------------------------------------------- */
+/* HU window of luna_preprocess.py:133-135: y = (clip(x, hu_min, hu_max) - hu_min) / (hu_max - hu_min), fp64 inside */
+int pcrl_hu_window(const float* x, float* y, long long n, double hu_min, double hu_max, void* stream);
+/* the voxel loops of luna_preprocess.py:217-236: crop [X][Y][z_pitch] (z fastest, z_pitch >= Z + len_depth - 1);
+ * per voxel (i, j, d < Z) the first k < len_depth with crop[i][j][d+k] >= threshold gives t_img = that value and
+ * d_img = 1 - k / (len_depth - 1) (none: t_img = 0, d_img = 0); *sum += sum(d_img) (the lung test of :243-247) */
+int pcrl_depth_scan(const float* crop, float* t_img, float* d_img, double* sum, int X, int Y, int Z,
+                    int z_pitch, int len_depth, float threshold, void* stream);
+
 /* the same update with the scalars in DEVICE memory, hyper = [lr, momentum, weight_decay, grad_scale,
  * skip_threshold] (utils.py:111-114 changes lr per epoch; a captured graph must not bake it in).
  * guard (nullable): device scalar = loss summed over the ranks; nothing is updated when

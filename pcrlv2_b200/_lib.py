@@ -57,6 +57,13 @@ SIGNATURES = {
     "pcrl_mse_scaled_bwd": [_P, _P, _P, _P, _P, _L, _P],
     "pcrl_contrastive_fwd_bwd": [_P, _P, _I, _I, _P, _P, _F, _P],
     "pcrl_sgd_flat_dev": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+    "pcrl_aug_flip": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "pcrl_aug_blur_axis": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_aug_noise_gamma": [_P, _P, _P, _P, _P, ctypes.c_ulonglong, _I, _I, _P],
+    "pcrl_aug_swap": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_aug_znorm": [_P, _P, _I, _I, _P],
+    "pcrl_hu_window": [_P, _P, _L, _D, _D, _P],
+    "pcrl_depth_scan": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "pcrl_bn1d_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     "pcrl_bn1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pcrl_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],

@@ -60,6 +60,15 @@ int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int upsample_trilinear_fwd(const float*, float*, int, int, int, int, int, cudaStream_t);
 int upsample_trilinear_bwd(const float*, float*, int, int, int, int, int, cudaStream_t);
 
+// augment.cu
+int aug_flip(const float*, float*, const int*, int, int, int, int, cudaStream_t);
+int aug_blur_axis(const float*, float*, const float*, int, int, int, int, int, int, cudaStream_t);
+int aug_noise_gamma(const float*, float*, const float*, const float*, const float*, unsigned long long, int, int, cudaStream_t);
+int aug_swap(float*, const int*, int, int, int, int, int, int, int, int, cudaStream_t);
+int aug_znorm(const float*, float*, int, int, cudaStream_t);
+int hu_window(const float*, float*, long long, double, double, cudaStream_t);
+int depth_scan(const float*, float*, float*, double*, int, int, int, int, int, float, cudaStream_t);
+
 }  // namespace pcrl
 
 using namespace pcrl;
@@ -315,6 +324,40 @@ int pcrl_sgd_flat(float* params, const float* grads, float* momentum_buf, const 
   NONNULL(params); NONNULL(grads); NONNULL(momentum_buf); NONNULL(seg_offsets); NONNULL(seg_active); NONNULL(seg_first);
   return sgd_flat(params, grads, momentum_buf, seg_offsets, seg_active, seg_first, nseg, lr, momentum,
                   weight_decay, grad_scale, ST(stream));
+}
+
+int pcrl_aug_flip(const float* x, float* y, const int* axis_mask, int B, int D, int H, int W, void* stream) {
+  NONNULL(x); NONNULL(y); NONNULL(axis_mask);
+  return aug_flip(x, y, axis_mask, B, D, H, W, ST(stream));
+}
+int pcrl_aug_blur_axis(const float* x, float* y, const float* sigma, int sigma_stride, int axis, int B, int D,
+                       int H, int W, void* stream) {
+  NONNULL(x); NONNULL(y); NONNULL(sigma);
+  return aug_blur_axis(x, y, sigma, sigma_stride, axis, B, D, H, W, ST(stream));
+}
+int pcrl_aug_noise_gamma(const float* x, float* y, const float* noise, const float* noise_std,
+                         const float* log_gamma, unsigned long long seed, int B, int vol, void* stream) {
+  NONNULL(x); NONNULL(y); NONNULL(noise_std); NONNULL(log_gamma);
+  return aug_noise_gamma(x, y, noise, noise_std, log_gamma, seed, B, vol, ST(stream));
+}
+int pcrl_aug_swap(float* x, const int* corners, int iters, int pd, int ph, int pw, int B, int D, int H, int W,
+                  void* stream) {
+  NONNULL(x); NONNULL(corners);
+  return aug_swap(x, corners, iters, pd, ph, pw, B, D, H, W, ST(stream));
+}
+int pcrl_aug_znorm(const float* x, float* y, int B, int vol, void* stream) {
+  NONNULL(x); NONNULL(y);
+  return aug_znorm(x, y, B, vol, ST(stream));
+}
+
+int pcrl_hu_window(const float* x, float* y, long long n, double hu_min, double hu_max, void* stream) {
+  NONNULL(x); NONNULL(y);
+  return hu_window(x, y, n, hu_min, hu_max, ST(stream));
+}
+int pcrl_depth_scan(const float* crop, float* t_img, float* d_img, double* sum, int X, int Y, int Z, int z_pitch,
+                    int len_depth, float threshold, void* stream) {
+  NONNULL(crop); NONNULL(t_img); NONNULL(d_img); NONNULL(sum);
+  return depth_scan(crop, t_img, d_img, sum, X, Y, Z, z_pitch, len_depth, threshold, ST(stream));
 }
 
 int pcrl_sgd_flat_dev(float* params, const float* grads, float* momentum_buf, const long long* seg_offsets,

@@ -211,3 +211,37 @@ def test_b16_trainer_fixture_within_the_references_own_fp32_noise():
     # the floors themselves: the trunk's two-step update is only reproducible to a few % in fp32
     assert 5e-3 < float(g["floor.down_tr64.ops.0.conv1.weight"]) < 0.2
     assert float(g["floor.out_tr.final_conv.weight"]) < 1e-3
+
+
+def test_staging_and_crop_oracles_known_answers():
+    """oracle/augment_oracle.py and oracle/preprocess_oracle.py (restatements of the torchio transforms of
+    data.py:73-89 and of luna_preprocess.py:213-241, 295-320): closed-form checks, no GPU."""
+    from oracle import augment_oracle as ao
+    from oracle import preprocess_oracle as po
+    g = np.random.default_rng(1)
+    x = g.random((16, 12, 8)).astype(np.float32)
+    assert np.array_equal(ao.flip(ao.flip(x, 5), 5), x) and np.array_equal(ao.flip(x, 1), x[::-1])
+    z = ao.znorm(x)
+    assert abs(z.mean()) < 1e-6 and abs(z.std(ddof=1) - 1) < 1e-6
+    assert np.array_equal(ao.blur(x, [0, 0, 0]), x)
+    one = np.zeros((9, 9, 9), np.float32)
+    one[4, 4, 4] = 1
+    b = ao.blur(one, [1.0, 0, 0])
+    w0 = 1.0 / (1.0 + 2.0 * sum(np.exp(-0.5 * k * k) for k in range(1, 5)))           # normalised, radius int(4 * 1 + 0.5)
+    assert abs(b.sum() - 1) < 1e-6 and abs(b[4, 4, 4] - w0) < 1e-6
+    # swap: disjoint patches exchange content; overlapping ones end with the SECOND patch at the first location
+    y = ao.swap(x, [[0, 0, 0, 8, 4, 4]], (8, 4, 4))
+    assert np.array_equal(y[:8, :4, :4], x[8:, 4:8, 4:8]) and np.array_equal(y[8:, 4:8, 4:8], x[:8, :4, :4])
+    y = ao.swap(x, [[0, 0, 0, 4, 2, 2]], (8, 4, 4))
+    assert np.array_equal(y[:8, :4, :4], x[4:12, 2:6, 2:6])
+    t = ao.noise_gamma(np.array([-0.25, 0.25], np.float32), np.zeros(2, np.float32), 0.1, np.log(2.0))
+    assert np.allclose(t, [-0.0625, 0.0625])
+    for c in ao.sample_swap_corners(random.Random(0), x.shape, (8, 4, 4), 50):
+        assert all(0 <= v for v in c) and c[0] + 8 <= 16 and c[3] + 8 <= 16 and c[:3] != c[3:]
+    crop = g.random((6, 5, 4 + 3)).astype(np.float32)
+    tl, dl = po.depth_scan_loops(crop, 4)
+    tv, dv = po.depth_scan(crop, 4)
+    assert np.array_equal(tl.astype(np.float32), tv.astype(np.float32)) and np.array_equal(dl, dv)
+    assert set(np.unique(dl)) <= {0.0, 0.5, 1.0}
+    assert po.cal_iou((0, 2, 0, 2, 0, 2), (1, 3, 1, 3, 1, 3)) == 1 / 15
+    assert np.array_equal(po.hu_window(np.array([-2000.0, -1000.0, 0.0, 1000.0, 3000.0])), [0, 0, 0.5, 1, 1])
