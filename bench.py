@@ -339,6 +339,10 @@ def measure(args, precision, host, rank, world, dev):
         ke = max(3, args.steps // 3)
         out["eager"] = {"ms_per_step": timed(eager_step, ke) / ke, "host_ms_per_step": host_cost(eager_step),
                         "steps": ke}
+        # the graph step again, right after the eager one (same thermal / power state): what an A/B of
+        # the two step kinds should be read from
+        graph_step(0)
+        out["eager"]["graph_ms_per_step_measured_right_after"] = timed(graph_step, ke) / ke
 
     # ---- per-kernel roofline: one instrumented EAGER step (events around every entry point).  Every
     # rank runs it (the step contains the gradient all-reduce); only rank 0 reports.

@@ -371,11 +371,14 @@ def test_side_stream_weight_gradients_match(monkeypatch):
     parameters, same update as the in-line path (PCRL_OVERLAP_WGRAD=0).  The restoration terms are
     used (well conditioned at batch 2; the contrastive terms are chaotic there: BatchNorm1d over two
     rows), and the run-to-run noise of the in-line path (atomics) calibrates the comparison."""
-    x1, _, gt, _ = orc.synthetic_batch(2, seed=9, vol=(32, 32, 16))
+    # batch 8, fp32 storage: at batch 2 in bf16 the run-to-run noise of ONE path through the BatchNorm
+    # backward is heavy-tailed (4e-3 .. 9e-2 rel-L2 over repeated runs, tools/diag_overlap.py), which made a
+    # one-sample noise calibration flaky
+    x1, _, gt, _ = orc.synthetic_batch(8, seed=9, vol=(32, 32, 16))
     runs = []
-    for mode in ("1", "0", "0"):
+    for mode in ("1", "0", "0", "0"):
         monkeypatch.setenv("PCRL_OVERLAP_WGRAD", mode)
-        m, _ = build("bn")
+        m, _ = build("bn", precision="fp32")
         opt = T.FlatSGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
         out, _, masks = m(x1.cuda())
         loss = torch.nn.functional.mse_loss(out, gt.cuda()) + torch.nn.functional.mse_loss(masks[1], gt.cuda())
@@ -385,17 +388,17 @@ def test_side_stream_weight_gradients_match(monkeypatch):
         touched = list(opt._touched)
         opt.step()
         runs.append((g, touched, opt._flat_p.clone(), loss.item()))
-    (g1, t1, p1, l1), (g0, t0, p0, l0), (gb, tb, pb, lb) = runs
+    (g1, t1, p1, l1), (g0, t0, p0, l0), (gb, tb, pb, lb), (gc, _, pc, _) = runs
     assert t1 == t0 == tb
     # fp64 / fp32 atomics make two runs of the SAME path differ (loss ~3e-6, gradients ~4e-3 rel-L2
     # at batch 2 through the BatchNorm backward): the bounds sit well above that noise and far below
     # what a lost or doubled weight gradient would cause (rel-L2 ~ 1)
     assert abs(l1 - l0) < 1e-4
-    noise = rl2(gb, g0)
+    noise = max(rl2(gb, g0), rl2(gc, g0), rl2(gc, gb))
     diff = rl2(g1, g0)
     log(f"[side-stream wgrad] flat gradient rel-L2 overlapped vs in-line {diff:.3e}; in-line run-to-run {noise:.3e}")
     assert diff < max(5 * noise, 3e-2)
-    assert rl2(p1, p0) < max(5 * rl2(pb, p0), 1e-5)
+    assert rl2(p1, p0) < max(5 * max(rl2(pb, p0), rl2(pc, p0)), 1e-5)
 
 
 def test_checkpoint_round_trip_with_torch_sgd():
