@@ -50,6 +50,7 @@ struct IgemmParams {
   int tiles_per_group, groups, col_chunks, nsamples;
   long long total_tiles;
   int ni;                     // MMA issuer warps in use (1 or 2)
+  int roll, tiles_per_plane;  // rolling plane window (igemm_roll_kernel): tiles of one plane
   long long tiles_per_chunk, total_steps;
   int seg_len;                // rows of one segment that belong to this tile family
   long long rows_total;       // PLAIN: number of A rows
@@ -108,6 +109,91 @@ __device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, long long 
   c.t_local = t * p.m_cta;
   c.f0 = g * p.P * p.PL + c.t_local;
   return c;
+}
+
+// Epilogue of one (128-row block, output plane): nc accumulator columns of the 32 rows this warp owns
+// (taddr = TMEM address of column 0 for this warp's lanes) -> bias, store at element offset `off`
+// (rows of a warp are a row pitch apart), per-channel sum / sum of squares into stat_s.
+__device__ __forceinline__ void epilogue_store(const IgemmParams& p, uint32_t taddr, long long off, bool valid,
+                                               int co0, float* stat_s, int lane) {
+  for (int c = 0; c < p.nc; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c, v);
+    tmem_ld_wait();
+    float y[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) y[i] = __uint_as_float(v[i]);
+    if (p.has_bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) y[i] += __ldg(&p.bias[co0 + c + i]);
+    }
+    if (p.out_mode == OUT_ROWS_T) {
+      if (valid) {
+        float* o = reinterpret_cast<float*>(p.out) + off;
+#pragma unroll
+        for (int i = 0; i < 32; i++) o[(size_t)(co0 + c + i) * p.ldc] = y[i];
+      }
+    } else if (p.out_fp32) {
+      if ((p.out_mode == OUT_CONVT || p.out_mode == OUT_UNSHUFFLE) && !p.exact_out) {
+        // these outputs are tensor-core operands of the next kernel: store tf32-rounded
+#pragma unroll
+        for (int i = 0; i < 32; i++) y[i] = rna_tf32(y[i]);
+      }
+      if (valid) {
+        // 256-bit stores: a lane's 32 B fill a whole sector per instruction (the rows of a
+        // warp are a row pitch apart, so nothing else coalesces)
+        float* o = reinterpret_cast<float*>(p.out) + off + c;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          st_global_v8(o + 8 * i, __float_as_uint(y[8 * i]), __float_as_uint(y[8 * i + 1]),
+                       __float_as_uint(y[8 * i + 2]), __float_as_uint(y[8 * i + 3]),
+                       __float_as_uint(y[8 * i + 4]), __float_as_uint(y[8 * i + 5]),
+                       __float_as_uint(y[8 * i + 6]), __float_as_uint(y[8 * i + 7]));
+      }
+    } else {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        // statistics are taken over exactly the values that are stored
+        y[2 * i] = __low2float(h);
+        y[2 * i + 1] = __high2float(h);
+      }
+      if (valid) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+          st_global_v8(o + 16 * i, pk[8 * i], pk[8 * i + 1], pk[8 * i + 2], pk[8 * i + 3],
+                       pk[8 * i + 4], pk[8 * i + 5], pk[8 * i + 6], pk[8 * i + 7]);
+      }
+    }
+    if (p.has_stats) {
+      float s1[32], s2[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const float t = valid ? y[i] : 0.f;
+        s1[i] = t;
+        s2[i] = t * t;
+      }
+      // transpose-reduce: after the loop lane L holds the column-(c+L) total in s[0]
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+          const float send1 = up ? s1[i] : s1[i + s];
+          const float keep1 = up ? s1[i + s] : s1[i];
+          s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, s);
+          const float send2 = up ? s2[i] : s2[i + s];
+          const float keep2 = up ? s2[i + s] : s2[i];
+          s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, s);
+        }
+      }
+      atomicAdd(&stat_s[c + lane], s1[0]);
+      atomicAdd(&stat_s[p.nc + c + lane], s2[0]);
+    }
+  }
 }
 
 template <int TF32>
@@ -388,84 +474,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
             const long long fd = 2 * d + i, fh = 2 * (hp - 1) + j + 1, fw = 2 * w + k;
             off = (((nn * (2 * p.ct_D) + fd) * (2 * p.ct_H + 1) + fh) * (2 * p.ct_W) + fw) * p.ldc + co0;
           }
-          for (int c = 0; c < p.nc; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(acc + ((uint32_t)(quad * 32) << 16) + (mt * p.P + pp) * p.nc + c, v);
-            tmem_ld_wait();
-            float y[32];
-#pragma unroll
-            for (int i = 0; i < 32; i++) y[i] = __uint_as_float(v[i]);
-            if (p.has_bias) {
-#pragma unroll
-              for (int i = 0; i < 32; i++) y[i] += __ldg(&p.bias[co0 + c + i]);
-            }
-            if (p.out_mode == OUT_ROWS_T) {
-              if (valid) {
-                float* o = reinterpret_cast<float*>(p.out) + off;
-#pragma unroll
-                for (int i = 0; i < 32; i++) o[(size_t)(co0 + c + i) * p.ldc] = y[i];
-              }
-            } else if (p.out_fp32) {
-              if ((p.out_mode == OUT_CONVT || p.out_mode == OUT_UNSHUFFLE) && !p.exact_out) {
-                // these outputs are tensor-core operands of the next kernel: store tf32-rounded
-#pragma unroll
-                for (int i = 0; i < 32; i++) y[i] = rna_tf32(y[i]);
-              }
-              if (valid) {
-                // 256-bit stores: a lane's 32 B fill a whole sector per instruction (the rows of a
-                // warp are a row pitch apart, so nothing else coalesces)
-                float* o = reinterpret_cast<float*>(p.out) + off + c;
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                  st_global_v8(o + 8 * i, __float_as_uint(y[8 * i]), __float_as_uint(y[8 * i + 1]),
-                               __float_as_uint(y[8 * i + 2]), __float_as_uint(y[8 * i + 3]),
-                               __float_as_uint(y[8 * i + 4]), __float_as_uint(y[8 * i + 5]),
-                               __float_as_uint(y[8 * i + 6]), __float_as_uint(y[8 * i + 7]));
-              }
-            } else {
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 16; i++) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
-                pk[i] = *reinterpret_cast<uint32_t*>(&h);
-                // statistics are taken over exactly the values that are stored
-                y[2 * i] = __low2float(h);
-                y[2 * i + 1] = __high2float(h);
-              }
-              if (valid) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c;
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-                  st_global_v8(o + 16 * i, pk[8 * i], pk[8 * i + 1], pk[8 * i + 2], pk[8 * i + 3],
-                               pk[8 * i + 4], pk[8 * i + 5], pk[8 * i + 6], pk[8 * i + 7]);
-              }
-            }
-            if (p.has_stats) {
-              float s1[32], s2[32];
-#pragma unroll
-              for (int i = 0; i < 32; i++) {
-                const float t = valid ? y[i] : 0.f;
-                s1[i] = t;
-                s2[i] = t * t;
-              }
-              // transpose-reduce: after the loop lane L holds the column-(c+L) total in s[0]
-#pragma unroll
-              for (int s = 16; s >= 1; s >>= 1) {
-                const bool up = (lane & s) != 0;
-#pragma unroll
-                for (int i = 0; i < s; i++) {
-                  const float send1 = up ? s1[i] : s1[i + s];
-                  const float keep1 = up ? s1[i + s] : s1[i];
-                  s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, s);
-                  const float send2 = up ? s2[i] : s2[i + s];
-                  const float keep2 = up ? s2[i + s] : s2[i];
-                  s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, s);
-                }
-              }
-              atomicAdd(&stat_s[c + lane], s1[0]);
-              atomicAdd(&stat_s[p.nc + c + lane], s2[0]);
-            }
-          }
+          epilogue_store(p, acc + ((uint32_t)(quad * 32) << 16) + (mt * p.P + pp) * p.nc, off, valid, co0, stat_s, lane);
         }
       }
       // accumulator buffer drained: hand it back to the MMA warp
@@ -483,6 +492,264 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constan
       }
     }
     if (warp == 2) { TSTORE(6, twf); TSTORE(7, TNOW() - tstart); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// ROLLING PLANE WINDOW variant of the convolution kernel, for the layers whose column chunk is narrow
+// (nc <= 64: every full-resolution 64-channel layer, i.e. most of the FLOPs).
+//
+// Why: a tcgen05.mma occupies the pipe for >= ~68 clk whatever its width N <= 128 (tools/umma_probe), so an
+// N = 64 MMA runs at less than half rate.  The kernel above therefore stacks the <= 3 output planes that one
+// input plane feeds along N, but with tiles of P = 2 output planes the first and last input plane of every
+// tile feed ONE plane each (N = 64): per tile 74 + 68 + 68 + 74 clk for 6 x 34 clk of math = 72 % -- the
+// measured tensor-pipe activity of those layers (68-71 %, profiles/r01c_ncu_tensor_kernels.md).
+// Here a CTA owns a 256-row window of the plane and walks through ALL D planes: input plane q is loaded once
+// (not (P+2)/P times) and feeds output planes q-1, q, q+1 in ONE N = 3*nc MMA per tap; the accumulators of
+// four consecutive output planes live in a TMEM ring (4 slots x nc columns per 128-row block), plane q-1 is
+// handed to the epilogue as soon as input plane q is done, and its slot is reused four planes later -- the
+// epilogue of plane p overlaps the MMAs of planes p+1.. without a second accumulator buffer.
+// When the three active slots wrap around the ring (2 of 4 positions) the MMA is split in two.
+// Requirements: D % 4 == 0, nc <= 64, a plane of at least 512 flat rows.
+template <int TF32>
+__global__ void __launch_bounds__(256, 1)
+igemm_roll_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb2,
+                  const __grid_constant__ CUtensorMap tb3, const IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_s = smem;
+  uint8_t* b_s = a_s + (size_t)p.sa * p.slab_bytes;
+  uint64_t* bars = (uint64_t*)(b_s + (size_t)p.sb * p.b_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + p.sa;
+  uint64_t* b_full = a_empty + p.sa;
+  uint64_t* b_empty = b_full + p.sb;
+  uint64_t* acc_full = b_empty + p.sb;     // [4]: one per ring slot
+  uint64_t* acc_empty = acc_full + 4;      // [4]
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 4);
+  float* stat_s = (float*)(tmem_slot + 2);  // [2][nc]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.sa; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], (uint32_t)p.ni); }
+    for (int i = 0; i < p.sb; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], (uint32_t)p.ni); }
+    for (int i = 0; i < 4; i++) { mbar_init(&acc_full[i], (uint32_t)p.ni); mbar_init(&acc_empty[i], 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&ta);
+    tma_prefetch_desc(&tb3);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (p.has_stats)
+    for (int i = threadIdx.x; i < 2 * p.nc; i += blockDim.x) stat_s[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const long long first_step = (long long)blockIdx.x, step_stride = (long long)gridDim.x;
+  const uint32_t tmem = *tmem_slot;
+  const int D = p.D, upt = p.D >> 2;                // uses of every ring slot per tile
+  const int blk_cols = 4 * p.nc;                    // accumulator columns of one 128-row block (4 slots)
+  const long long tiles_per_chunk = (long long)p.tiles_per_plane * p.nsamples;
+
+  if (warp == 0) {
+    // =============================== activation slabs: input plane q of this window, once per k-block
+    int sa = 0, pa = 0;
+    const uint32_t a_tx = (uint32_t)(p.nh_box * p.Wp * p.row_bytes);
+    for (long long step = first_step; step < p.total_steps; step += step_stride) {
+      const long long tile = step % tiles_per_chunk;
+      const int t_local = (int)(tile % p.tiles_per_plane) * p.m_cta, n = (int)(tile / p.tiles_per_plane);
+      const int mr_first = floordiv(t_local - p.Wp - 1, p.Wp);
+      for (int q = 0; q < D; q++)
+        for (int kb = 0; kb < p.kblocks; kb++) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&a_full[sa], a_tx);
+            tma_load_4d(a_s + (size_t)sa * p.slab_bytes, &ta, &a_full[sa], kb * p.kc, -1, mr_first + q * p.H1, n);
+          }
+          __syncwarp();
+          if (++sa == p.sa) { sa = 0; pa ^= 1; }
+        }
+    }
+  } else if (warp == 6) {
+    // =============================== filter tiles: per (input plane, k-block, (dy,dx) tap) the 2 or 3 dz taps
+    int sb = 0, pb = 0;
+    for (long long step = first_step; step < p.total_steps; step += step_stride) {
+      const int col0 = (int)(step / tiles_per_chunk) * p.nc;
+      for (int q = 0; q < D; q++) {
+        const int lo = max(0, q - 1), hi = min(D - 1, q + 1), cnt = hi - lo + 1, dzr_lo = lo - (q - 1);
+        const CUtensorMap* tb = cnt == 2 ? &tb2 : &tb3;
+        const uint32_t b_tx = (uint32_t)(cnt * p.nc * p.row_bytes);
+        for (int kb = 0; kb < p.kblocks; kb++)
+          for (int j = 0; j < 9; j++) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[sb], b_tx);
+              tma_load_3d(b_s + (size_t)sb * p.b_bytes, tb, &b_full[sb], kb * p.kc, col0, j * 3 + dzr_lo);
+            }
+            __syncwarp();
+            if (++sb == p.sb) { sb = 0; pb ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1 || warp == 7) {
+    // =============================== MMA issuers: issuer iw owns 128-row block iw of the window
+    const int iw = (warp == 1) ? 0 : 1;
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    const uint32_t layout = (p.row_bytes == 128) ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint64_t desc_hi = make_smem_desc(0, 16, 8 * p.row_bytes, layout);
+    const int ksteps = (p.row_bytes == 128) ? 4 : 2;
+    const uint32_t fmt = TF32 ? 2u : 1u;
+    const uint32_t idesc1 = make_idesc(fmt, 128, (uint32_t)p.nc, 0, 0);
+    const uint32_t idesc2 = make_idesc(fmt, 128, (uint32_t)(2 * p.nc), 0, 0);
+    const uint32_t idesc3 = make_idesc(fmt, 128, (uint32_t)(3 * p.nc), 0, 0);
+    const uint32_t rb16 = (uint32_t)p.row_bytes >> 4;
+    const uint32_t mt16 = 128u * rb16, slab16 = (uint32_t)p.slab_bytes >> 4, bst16 = (uint32_t)p.b_bytes >> 4;
+    const uint32_t nc16 = (uint32_t)p.nc * rb16;           // descriptor units of one plane's filter rows
+    const uint64_t a_desc0 = desc_hi | (uint64_t)((smem_u32(a_s) >> 4) & 0x3FFF);
+    const uint64_t b_desc0 = desc_hi | (uint64_t)((smem_u32(b_s) >> 4) & 0x3FFF);
+    const uint32_t dblk = tmem + (uint32_t)(iw * blk_cols);
+    int it = 0;
+    for (long long step = first_step; step < p.total_steps && iw < p.ni; step += step_stride, it++) {
+      const long long tile = step % tiles_per_chunk;
+      const int t_local = (int)(tile % p.tiles_per_plane) * p.m_cta;
+      const int tap0_rows = t_local - floordiv(t_local - p.Wp - 1, p.Wp) * p.Wp - p.Wp - 1;
+      for (int q = 0; q < D; q++) {
+        const int lo = max(0, q - 1), hi = min(D - 1, q + 1), cnt = hi - lo + 1;
+        // output planes touched for the first time by this input plane: their ring slot must have been drained
+        const bool has_new = (q == 0) || (q + 1 <= D - 1);
+        if (q == 0) {
+          mbar_wait(&acc_empty[0], ((it * upt) & 1) ^ 1);
+          mbar_wait(&acc_empty[1], ((it * upt) & 1) ^ 1);
+        } else if (q + 1 <= D - 1) {
+          mbar_wait(&acc_empty[(q + 1) & 3], ((it * upt + ((q + 1) >> 2)) & 1) ^ 1);
+        }
+        tc_fence_after();
+        const int s_lo = lo & 3;
+        const int n1 = min(cnt, 4 - s_lo);                 // planes before the ring wraps
+        const uint32_t id_a = n1 == 1 ? idesc1 : (n1 == 2 ? idesc2 : idesc3);
+        const uint32_t id_b = (cnt - n1) == 1 ? idesc1 : idesc2;
+        const uint32_t d_a = dblk + (uint32_t)(s_lo * p.nc);
+        for (int kb = 0; kb < p.kblocks; kb++) {
+          mbar_wait(&a_full[sa], pa);
+          uint64_t ad = a_desc0 + (uint32_t)sa * slab16 + (uint32_t)tap0_rows * rb16 + (uint32_t)iw * mt16;
+          int c3 = 0;
+          for (int j = 0; j < 9; j++) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t bd = b_desc0 + (uint32_t)sb * bst16;
+            if (elect_one()) {
+              if (has_new && kb == 0 && j == 0) {
+                // first tap of an input plane that opens new output planes: plane by plane, the new ones
+                // are overwritten by their first k-step
+                for (int r = 0; r < cnt; r++) {
+                  const int pl = lo + r;
+                  const bool is_new = (q == 0) || (pl == q + 1);
+                  const uint32_t d = dblk + (uint32_t)((pl & 3) * p.nc);
+                  for (int ks = 0; ks < ksteps; ks++)
+                    umma_any<TF32>(d, ad + 2 * ks, bd + (uint32_t)r * nc16 + 2 * ks, idesc1, (ks > 0 || !is_new) ? 1u : 0u);
+                }
+              } else {
+                umma_any<TF32>(d_a, ad, bd, id_a, 1u);
+                umma_any<TF32>(d_a, ad + 2, bd + 2, id_a, 1u);
+                if (ksteps == 4) {
+                  umma_any<TF32>(d_a, ad + 4, bd + 4, id_a, 1u);
+                  umma_any<TF32>(d_a, ad + 6, bd + 6, id_a, 1u);
+                }
+                if (n1 < cnt) {                            // wrapped part: ring slots 0..
+                  const uint64_t bd2 = bd + (uint32_t)n1 * nc16;
+                  umma_any<TF32>(dblk, ad, bd2, id_b, 1u);
+                  umma_any<TF32>(dblk, ad + 2, bd2 + 2, id_b, 1u);
+                  if (ksteps == 4) {
+                    umma_any<TF32>(dblk, ad + 4, bd2 + 4, id_b, 1u);
+                    umma_any<TF32>(dblk, ad + 6, bd2 + 6, id_b, 1u);
+                  }
+                }
+              }
+              umma_commit(&b_empty[sb]);
+            }
+            __syncwarp();
+            if (++sb == p.sb) { sb = 0; pb ^= 1; }
+            if (++c3 == 3) { c3 = 0; ad += (uint32_t)(p.Wp - 2) * rb16; }
+            else ad += rb16;
+          }
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
+          if (++sa == p.sa) { sa = 0; pa ^= 1; }
+        }
+        // input plane q done: output plane q-1 is complete (and plane D-1 after the last input plane)
+        if (elect_one()) {
+          if (q >= 1) umma_commit(&acc_full[(q - 1) & 3]);
+          if (q == D - 1) umma_commit(&acc_full[(D - 1) & 3]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 2 && warp <= 5) {
+    // =============================== epilogue warps (warp w owns TMEM lanes 32*(w%4) .. +31)
+    const int quad = warp & 3;
+    int it = 0;
+    int cur_col0 = -1, cur_n = -1;
+    const int et = threadIdx.x - 64;
+    for (long long step = first_step; step < p.total_steps; step += step_stride, it++) {
+      const long long tile = step % tiles_per_chunk;
+      const int col0 = (int)(step / tiles_per_chunk) * p.nc;
+      const int t_local = (int)(tile % p.tiles_per_plane) * p.m_cta, n = (int)(tile / p.tiles_per_plane);
+      if (p.has_stats && (col0 != cur_col0 || (p.stats_per_sample && n != cur_n))) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (cur_col0 >= 0) {
+          double* st = p.stats + (p.stats_per_sample ? (size_t)cur_n * p.cout_total * 2 : 0);
+          for (int i = et; i < p.nc; i += 128) {
+            atomicAdd(&st[(size_t)(cur_col0 + i) * 2 + 0], (double)stat_s[i]);
+            atomicAdd(&st[(size_t)(cur_col0 + i) * 2 + 1], (double)stat_s[p.nc + i]);
+            stat_s[i] = 0.f;
+            stat_s[p.nc + i] = 0.f;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_col0 = col0;
+        cur_n = n;
+      }
+      for (int pl = 0; pl < D; pl++) {
+        const int slot = pl & 3;
+        mbar_wait(&acc_full[slot], (it * upt + (pl >> 2)) & 1);
+        tc_fence_after();
+        for (int mt = 0; mt < p.mt; mt++) {
+          const int lrow = mt * 128 + quad * 32 + lane;
+          const int f = pl * p.PL + t_local + lrow;
+          const int mr = f / p.Wp, wq = f - mr * p.Wp;
+          const int hp = mr % p.H1;
+          const bool valid = (wq >= 1) && (mr < p.MR) && (hp >= 1) && (t_local + lrow < p.PL);
+          long long off;
+          if (p.out_mode == OUT_FLAT) {
+            off = (((long long)n * p.MR + mr) * p.W + (wq - 1)) * p.ldc + col0;
+          } else {   // OUT_UNSHUFFLE: coarse-major [coarse H-padded row][tap][C]
+            const int d2 = mr / p.H1, h2 = hp - 1, w2 = wq - 1;
+            const int t = ((d2 & 1) << 2) | ((h2 & 1) << 1) | (w2 & 1);
+            const long long crow = (((long long)n * p.ct_D + (d2 >> 1)) * (p.ct_H + 1) + (h2 >> 1) + 1) * p.ct_W + (w2 >> 1);
+            off = (crow * 8 + t) * p.ldc + col0;
+          }
+          epilogue_store(p, tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * blk_cols + slot * p.nc), off, valid,
+                         col0, stat_s, lane);
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[slot]);
+      }
+    }
+    if (p.has_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (cur_col0 >= 0) {
+        double* st = p.stats + (p.stats_per_sample ? (size_t)cur_n * p.cout_total * 2 : 0);
+        for (int i = et; i < p.nc; i += 128) {
+          atomicAdd(&st[(size_t)(cur_col0 + i) * 2 + 0], (double)stat_s[i]);
+          atomicAdd(&st[(size_t)(cur_col0 + i) * 2 + 1], (double)stat_s[p.nc + i]);
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -507,6 +774,36 @@ struct IgemmLaunch {
   IgemmParams p;
   CUtensorMap ta, tb[3];
 };
+
+static int launch_roll(IgemmLaunch& L, cudaStream_t stream) {
+  IgemmParams& p = L.p;
+  p.tmem_cols = pow2_cols(p.mt * 4 * p.nc);
+  p.b_bytes = ((3 * p.nc * p.row_bytes + 1023) / 1024) * 1024;
+  const size_t budget = 212 * 1024;
+  p.sa = 2;
+  p.sb = 2;
+  if ((size_t)p.sa * p.slab_bytes + (size_t)p.sb * p.b_bytes > budget)
+    return fail(PCRL_ERR_ARG, "igemm (rolling): tile does not fit shared memory (slab %d B, b %d B)", p.slab_bytes, p.b_bytes);
+  while ((size_t)p.sa * p.slab_bytes + (size_t)(p.sb + 1) * p.b_bytes <= budget && p.sb < 6) p.sb++;
+  if ((size_t)(p.sa + 1) * p.slab_bytes + (size_t)p.sb * p.b_bytes <= budget) p.sa++;
+  while ((size_t)p.sa * p.slab_bytes + (size_t)(p.sb + 1) * p.b_bytes <= budget && p.sb < 10) p.sb++;
+  const size_t smem = (size_t)p.sa * p.slab_bytes + (size_t)p.sb * p.b_bytes +
+                      (2 * p.sa + 2 * p.sb + 8) * 8 + 16 + 2 * p.nc * 4 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_roll_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_roll_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  p.ni = 2;
+  p.total_steps = (long long)p.tiles_per_plane * p.nsamples * p.col_chunks;
+  long long grid = num_sms();
+  if (p.total_steps < grid) grid = p.total_steps;
+  if (p.tf32) igemm_roll_kernel<1><<<(unsigned)grid, 256, smem, stream>>>(L.ta, L.tb[1], L.tb[2], p);
+  else igemm_roll_kernel<0><<<(unsigned)grid, 256, smem, stream>>>(L.ta, L.tb[1], L.tb[2], p);
+  PCRL_CHECK_CUDA(cudaGetLastError());
+  return PCRL_OK;
+}
 
 static int finish_and_launch(IgemmLaunch& L, cudaStream_t stream) {
   IgemmParams& p = L.p;
@@ -603,6 +900,8 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
     p.P = (p.nc == 64) ? 2 : 4;
     while (p.P > 1 && D % p.P) p.P >>= 1;
   }
+  // rolling plane window (igemm_roll_kernel) for the narrow-column layers with large planes
+  p.roll = (p.nc <= 64 && p.PL >= 512 && D >= 4 && D % 4 == 0 && !getenv("PCRL_IGEMM_NOROLL")) ? 1 : 0;
   p.mt = (flat >= 256) ? 2 : 1;
   {  // tuning overrides (experiments only)
     const char* e = getenv("PCRL_IGEMM_MT");
@@ -611,8 +910,13 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
     if (e && atoi(e) > 0 && p.P > 1) { p.P = atoi(e); while (p.P > 1 && D % p.P) p.P >>= 1; }
     while (p.mt > 1 && p.mt * p.P * p.nc > 512) p.mt >>= 1;
   }
+  if (p.roll) { p.mt = 2; p.P = 4; }
   p.m_cta = p.mt * 128;
-  if (p.P > 1) {
+  if (p.roll) {
+    p.seg_len = p.PL;
+    p.groups = 1;
+    p.tiles_per_plane = (p.PL + p.m_cta - 1) / p.m_cta;
+  } else if (p.P > 1) {
     p.seg_len = p.PL;
     p.groups = D / p.P;
   } else {
@@ -639,6 +943,7 @@ int conv3d_k3_igemm(const void* x, const void* w, void* y, double* stats, int st
   if (rc) return rc;
   rc = make_b_maps(L, w, Cin, Cout, 27);
   if (rc) return rc;
+  if (p.roll) return launch_roll(L, stream);
   return finish_and_launch(L, stream);
 }
 
