@@ -85,7 +85,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         for r in self.rows:
             f = [t.strip() for t in r.split(",")]
             if len(f) < 7:
@@ -95,11 +95,16 @@ class ClockSampler:
                 mx = float(f[1])
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw) if pw else None}
 
 
 def measured_peaks():
@@ -336,13 +341,22 @@ def measure(args, precision, host, rank, world, dev):
     if gs is not None:
         for i in range(2):
             eager_step(i)
-        ke = max(3, args.steps // 3)
-        out["eager"] = {"ms_per_step": timed(eager_step, ke) / ke, "host_ms_per_step": host_cost(eager_step),
-                        "steps": ke}
+        ke = max(6, args.steps // 2)
+        smp = ClockSampler(dev.index)
+        smp.start()
+        ms_e = timed(eager_step, ke) / ke
+        ck_e = smp.stop()
+        out["eager"] = {"ms_per_step": ms_e, "host_ms_per_step": host_cost(eager_step), "steps": ke,
+                        "sm_mhz": ck_e.get("sm_mhz"), "power_w": ck_e.get("power_w")}
         # the graph step again, right after the eager one (same thermal / power state): what an A/B of
-        # the two step kinds should be read from
+        # the two step kinds should be read from, with the clocks and board power each ran at
         graph_step(0)
+        smp = ClockSampler(dev.index)
+        smp.start()
         out["eager"]["graph_ms_per_step_measured_right_after"] = timed(graph_step, ke) / ke
+        ck_g = smp.stop()
+        out["eager"]["graph_sm_mhz"] = ck_g.get("sm_mhz")
+        out["eager"]["graph_power_w"] = ck_g.get("power_w")
 
     # ---- per-kernel roofline: one instrumented EAGER step (events around every entry point).  Every
     # rank runs it (the step contains the gradient all-reduce); only rank 0 reports.

@@ -309,15 +309,20 @@ static int launch_wgrad(WgradParams& p, const CUtensorMap& ta, const CUtensorMap
                         cudaStream_t stream) {
   if (p.b_views < 1) { p.b_views = 1; p.ncm = p.nc; }
   const int stage_bytes = p.a_chunks * p.a_chunk_bytes + p.b_chunks * p.b_views * p.b_chunk_bytes;
-  p.stages = 3;
-  while (p.stages > 2 && (size_t)p.stages * stage_bytes > 200 * 1024) p.stages--;
-  if ((size_t)p.stages * stage_bytes > 210 * 1024)
+  if (p.stages < 2) {
+    p.stages = 3;
+    while (p.stages > 2 && (size_t)p.stages * stage_bytes > 200 * 1024) p.stages--;
+  }
+  if ((size_t)p.stages * stage_bytes > 225 * 1024)
     return fail(PCRL_ERR_ARG, "wgrad: stage of %d bytes does not fit shared memory", stage_bytes);
   p.nacc = (2 * p.ntaps * p.ncm <= 512 && !getenv("PCRL_WGRAD_NACC1")) ? 2 : 1;
   int cols = p.nacc * p.ntaps * p.ncm, t = 32;
   while (t < cols) t <<= 1;
   p.tmem_cols = t;
   const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+  if (getenv("PCRL_WGRAD_VERBOSE"))
+    fprintf(stderr, "[wgrad] mode %d tf32 %d mc %d nc %d nrows %d kr %d ksteps %d stages %d stage_bytes %d grid %u x %u pair %d npair %d stack %d\n",
+            p.mode, p.tf32, p.mc, p.nc, p.nrows, p.kr, p.ksteps, p.stages, stage_bytes, grid.x, grid.y, p.pair, p.npair, p.stack_dx);
   static bool configured = false;
   if (!configured) {
     PCRL_CHECK_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<0>,
@@ -359,24 +364,34 @@ int conv3d_k3_wgrad_igemm(const void* dy, const void* x, float* dw, int N, int D
   p.npair = (tf32 && p.nc == 64 && p.b_chunks == 2 && !getenv("PCRL_WGRAD_NONPAIR")) ? 1 : 0;
   p.b_views = p.npair ? 2 : 1;
   p.ncm = p.nc * p.b_views;
-  // merged rows per stage: start from ~128 reduction rows (64 for fp32 operands) and shrink until
-  // three stages fit in shared memory (latency hiding needs the depth more than the stage size);
-  // if even one merged row per stage does not allow three, take the largest two-stage tiling
-  const int target = tf32 ? 64 : 128;
-  int nrows0 = (target + p.Wp - 1) / p.Wp;
+  // Merged rows per K-stage and pipeline depth.  Measured on B200 (tools/sweep_wgrad.py,
+  // profiles/r02p_sweep_wgrad.txt): what matters first is a LONG stage -- a stage of >= ~160 reduction
+  // rows amortises the per-stage barrier round trip and the zero-padded last k-step (kr is rarely a
+  // multiple of the MMA K) -- and only then the depth: two stages of the largest tiling that fits
+  // beat three stages of a shorter one by 10-30 %, three stages win by a few % once they are long too.
+  const int target = 272;                                   // reduction rows per stage worth having
+  int nrows0 = target / p.Wp;
+  if (nrows0 < 1) nrows0 = 1;
   if (nrows0 > p.MR) nrows0 = p.MR;
-  if (nrows0 > 256) return fail(PCRL_ERR_UNSUPPORTED, "conv3d_k3_wgrad: W too small");
-  if (const char* e = getenv("PCRL_WGRAD_NROWS")) { if (atoi(e) > 0 && atoi(e) <= p.MR) nrows0 = atoi(e); }
-  int chosen = 0;
-  for (int want = 3; want >= 2 && !chosen; want--) {
+  if (nrows0 > 256) nrows0 = 256;
+  if (const char* e = getenv("PCRL_WGRAD_NROWS")) { if (atoi(e) > 0 && atoi(e) <= p.MR && atoi(e) <= 256) nrows0 = atoi(e); }
+  auto largest_fit = [&](int want) {
     for (int nr = nrows0; nr >= 1; nr--) {
       const int ks = (nr * p.Wp + p.krows - 1) / p.krows;
       const int ab = round_up((ks * p.krows + 1) * p.a_row_bytes, 1024);
       const int bb = round_up((ks * p.krows + 3) * p.b_row_bytes, 1024);
-      const bool padded_ok = want == 2 || 100 * ks * p.krows <= 115 * nr * p.Wp;   // <= 15 % zero rows
-      if (padded_ok && (size_t)want * (p.a_chunks * ab + p.b_chunks * p.b_views * bb) <= 200 * 1024) { chosen = nr; break; }
-      if (want == 3 && 2 * nr <= nrows0) break;       // do not shrink the stage below half the target
+      if ((size_t)want * (p.a_chunks * ab + p.b_chunks * p.b_views * bb) <= 225 * 1024) return nr;
     }
+    return 0;
+  };
+  int chosen = 0;
+  if (const char* e = getenv("PCRL_WGRAD_STAGES")) {
+    if (atoi(e) >= 2 && atoi(e) <= 4) { p.stages = atoi(e); chosen = largest_fit(p.stages); }
+  }
+  if (!chosen) {
+    const int nr3 = largest_fit(3), nr2 = largest_fit(2);
+    if (nr3 > 0 && (nr3 == nr2 || nr3 * p.Wp >= 160)) { chosen = nr3; p.stages = 3; }
+    else { chosen = nr2; p.stages = 2; }
   }
   if (!chosen) return fail(PCRL_ERR_ARG, "conv3d_k3_wgrad: no stage tiling fits shared memory");
   p.nrows = chosen;
