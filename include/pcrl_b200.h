@@ -277,6 +277,43 @@ int pcrl_sgd_flat_dev(float* params, const float* grads, float* momentum_buf,
                       const long long* seg_offsets, const int* seg_active, const int* seg_first,
                       int nseg, const float* hyper, const float* guard, void* stream);
 
+/* ---- 2-D path: reference models/pcrlv2_model.py + the torchvision ResNet-18 its smp encoder
+ * wraps.  Activations are H-padded NHWC = the layout above with D = 1: [N][H+1][W][C].  Convolutions run as
+ * im2col -> pcrl_gemm_nt(_stats) / pcrl_gemm_tn -> col2im; `dtype` is PCRL_DTYPE_BF16 or PCRL_DTYPE_F32. ---- */
+/* col[(n,ho',wo)][(ky*k+kx)*C + c] = x[n][ho*stride-pad+ky][wo*stride-pad+kx][c] (zero outside the image, in row
+ * ho' = 0 and in the K padding kk*C..Kp-1).  image_nchw: x is the network input, fp32 [N][C][H][W] (any C);
+ * otherwise x is an H-padded NHWC activation with C % 8 == 0.  F.conv2d of torchvision resnet.py (conv1 7x7/2,
+ * the 3x3/2 and 1x1/2 convolutions) and of md.Conv2dReLU, models/pcrlv2_model.py:51-64,78-93 */
+int pcrl_im2col2d(const void* x, void* col, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
+                  int Wo, int Kp, int image_nchw, int dtype, void* stream);
+/* data gradient of the same convolution from dcol = dY * W: dx [N][H+1][W][C] (gather form, no atomics) */
+int pcrl_col2im2d(const void* dcol, void* dx, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
+                  int Wo, int Kp, int dtype, void* stream);
+/* nn.MaxPool2d(3, stride 2, padding 1) of the ResNet stem and its backward (first maximum wins, as torch);
+ * y / dy [N][(H-1)/2+2][(W-1)/2+1][C] */
+int pcrl_maxpool2d_3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+int pcrl_maxpool2d_3x3s2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
+                             void* stream);
+/* residual join of BasicBlock (`out += identity; relu`): op 0: out = relu(a+b); op 1: out = b * (a > 0)
+ * (a = forward output, b = incoming gradient); op 2: out = a + b.  n elements, n % 8 == 0 */
+int pcrl_add_relu(const void* a, const void* b, void* out, long long n, int op, int dtype, void* stream);
+/* F.interpolate(scale_factor=2, mode='nearest'), models/pcrlv2_model.py:114: x [N][H+1][W][C] ->
+ * y [N][2H+1][2W][C]; backward: g fine -> dx coarse (sum of the four children) */
+int pcrl_upsample_nearest2x_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+int pcrl_upsample_nearest2x_bwd(const void* g, void* dx, int N, int H, int W, int C, int dtype, void* stream);
+/* F.interpolate(scale_factor=s, mode='bilinear') (align_corners=False) of the deep-supervision masks,
+ * models/pcrlv2_model.py:192: fp32 [NC][H][W] -> [NC][H*s][W*s]; backward ADDS into dx (zeroed by the caller) */
+int pcrl_bilinear2d_fwd(const float* x, float* y, int NC, int H, int W, int scale, void* stream);
+int pcrl_bilinear2d_bwd(const float* g, float* dx, int NC, int H, int W, int scale, void* stream);
+/* Conv2d(C -> 3, k = 1 or 3, padding k/2) with bias: the deep-supervision output conv (models/pcrlv2_model.py:106)
+ * and smp's segmentation head (:208).  a [N][H+1][W][Cs] (channels 0..C-1 used), w fp32 [3][C][k][k] (state_dict
+ * layout), out fp32 NCHW [N][3][H][W].  Backward: da (nullable) [N][H+1][W][Cs], dw [3][C][k][k] and db [3]
+ * (nullable together; ADDED to, zeroed by the caller) */
+int pcrl_conv2d_c3_fwd(const void* a, const float* w, const float* bias, float* out, int N, int H, int W, int C,
+                       int Cs, int k, int dtype, void* stream);
+int pcrl_conv2d_c3_bwd(const void* a, const float* w, const float* dout, void* da, float* dw, float* db, int N,
+                       int H, int W, int C, int Cs, int k, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

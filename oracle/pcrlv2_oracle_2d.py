@@ -117,6 +117,16 @@ def is_cancelling(key: str) -> bool:
 
 
 # --------------------------------------------------------------------------- forward
+# Every convolution goes through this hook so that oracle/operand_emulation_2d.py can restate the SAME forward
+# with the operand rounding of the precision modes (TF32 / bf16 tensor-core operands); the default is F.conv2d.
+# kind: "tc" = a convolution the CUDA path runs on the tensor cores, "c3" = one of the 3-output-channel convs.
+CONV_IMPL = [lambda x, w, b, stride, pad, kind: F.conv2d(x, w, b, stride, pad)]
+
+
+def _conv(x, w, b=None, stride=1, pad=0, kind="tc"):
+    return CONV_IMPL[0](x, w, b, stride, pad, kind)
+
+
 def _bn(x, sd, prefix, training):
     """nn.BatchNorm2d / nn.BatchNorm1d (momentum 0.1, eps 1e-5), buffers updated in train mode."""
     if training:
@@ -127,10 +137,10 @@ def _bn(x, sd, prefix, training):
 
 def _basic_block(x, sd, p, stride, training):
     """torchvision.models.resnet.BasicBlock.forward."""
-    out = F.relu(_bn(F.conv2d(x, sd[f"{p}.conv1.weight"], None, stride, 1), sd, f"{p}.bn1", training))
-    out = _bn(F.conv2d(out, sd[f"{p}.conv2.weight"], None, 1, 1), sd, f"{p}.bn2", training)
+    out = F.relu(_bn(_conv(x, sd[f"{p}.conv1.weight"], None, stride, 1), sd, f"{p}.bn1", training))
+    out = _bn(_conv(out, sd[f"{p}.conv2.weight"], None, 1, 1), sd, f"{p}.bn2", training)
     if f"{p}.downsample.0.weight" in sd:
-        x = _bn(F.conv2d(x, sd[f"{p}.downsample.0.weight"], None, stride, 0), sd, f"{p}.downsample.1", training)
+        x = _bn(_conv(x, sd[f"{p}.downsample.0.weight"], None, stride, 0), sd, f"{p}.downsample.1", training)
     return F.relu(out + x)
 
 
@@ -138,7 +148,7 @@ def encoder(sd, x, training=True):
     """smp ResNetEncoder.forward for resnet18, depth 5: six features, the first is the input."""
     e = "model.encoder"
     feats = [x]
-    x = F.relu(_bn(F.conv2d(x, sd[f"{e}.conv1.weight"], None, 2, 3), sd, f"{e}.bn1", training))
+    x = F.relu(_bn(_conv(x, sd[f"{e}.conv1.weight"], None, 2, 3), sd, f"{e}.bn1", training))
     feats.append(x)
     x = F.max_pool2d(x, 3, 2, 1)
     for name, _cin, _cout, stride in LAYERS:
@@ -151,11 +161,11 @@ def encoder(sd, x, training=True):
 def decoder_block(x, sd, p, training):
     """DecoderBlock.forward, models/pcrlv2_model.py:113-128 (skip connection commented out :115-117)."""
     x = F.interpolate(x, scale_factor=2, mode="nearest")
-    x = F.relu(_bn(F.conv2d(x, sd[f"{p}.conv1.0.weight"], None, 1, 1), sd, f"{p}.conv1.1", training))
-    x = F.relu(_bn(F.conv2d(x, sd[f"{p}.conv2.0.weight"], None, 1, 1), sd, f"{p}.conv2.1", training))
+    x = F.relu(_bn(_conv(x, sd[f"{p}.conv1.0.weight"], None, 1, 1), sd, f"{p}.conv1.1", training))
+    x = F.relu(_bn(_conv(x, sd[f"{p}.conv2.0.weight"], None, 1, 1), sd, f"{p}.conv2.1", training))
     h = f"{p}.deep_supervision_head"
-    m = F.relu(_bn(F.conv2d(x, sd[f"{h}.0.weight"], sd[f"{h}.0.bias"], 1, 1), sd, f"{h}.1", training))
-    m = F.conv2d(m, sd[f"{h}.3.weight"], sd[f"{h}.3.bias"])
+    m = F.relu(_bn(_conv(x, sd[f"{h}.0.weight"], sd[f"{h}.0.bias"], 1, 1), sd, f"{h}.1", training))
+    m = _conv(m, sd[f"{h}.3.weight"], sd[f"{h}.3.bias"], 1, 0, "c3")
     pro = _bn(F.adaptive_avg_pool2d(x, (1, 1)).flatten(1), sd, f"{p}.bn", training)
     q = f"{p}.predictor_head"
     pre = F.linear(pro, sd[f"{q}.0.weight"], sd[f"{q}.0.bias"])
@@ -176,7 +186,7 @@ def forward(sd, x, local=False, training=True):
         masks.append(F.interpolate(m, scale_factor=2 ** (4 - i), mode="bilinear"))   # :191-193
     mask = None
     if not local:
-        mask = F.conv2d(h, sd["model.segmentation_head.0.weight"], sd["model.segmentation_head.0.bias"], 1, 1)
+        mask = _conv(h, sd["model.segmentation_head.0.weight"], sd["model.segmentation_head.0.bias"], 1, 1, "c3")
     return outs, mask, masks
 
 

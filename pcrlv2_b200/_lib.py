@@ -75,6 +75,18 @@ SIGNATURES = {
     "pcrl_sigmoid_bwd": [_P, _P, _P, _L, _P],
     "pcrl_upsample_trilinear_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "pcrl_upsample_trilinear_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    # 2-D path (planar.cu)
+    "pcrl_im2col2d": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_col2im2d": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_maxpool2d_3x3s2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_maxpool2d_3x3s2_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_add_relu": [_P, _P, _P, _L, _I, _I, _P],
+    "pcrl_upsample_nearest2x_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_upsample_nearest2x_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "pcrl_bilinear2d_fwd": [_P, _P, _I, _I, _I, _I, _P],
+    "pcrl_bilinear2d_bwd": [_P, _P, _I, _I, _I, _I, _P],
+    "pcrl_conv2d_c3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_conv2d_c3_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
 }
 
 _lib = None

@@ -69,6 +69,17 @@ int aug_znorm(const float*, float*, int, int, cudaStream_t);
 int hu_window(const float*, float*, long long, double, double, cudaStream_t);
 int depth_scan(const float*, float*, float*, double*, int, int, int, int, int, float, cudaStream_t);
 
+
+// planar.cu (2-D path)
+int im2col2d(const void*, void*, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int col2im2d(const void*, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int maxpool2d_3x3s2(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int add_relu(const void*, const void*, void*, long long, int, int, cudaStream_t);
+int upsample_nearest2x(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int bilinear2d(const float*, float*, int, int, int, int, int, cudaStream_t);
+int conv2d_c3_fwd(const void*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int conv2d_c3_bwd(const void*, const float*, const float*, void*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+
 }  // namespace pcrl
 
 using namespace pcrl;
@@ -366,6 +377,60 @@ int pcrl_sgd_flat_dev(float* params, const float* grads, float* momentum_buf, co
   NONNULL(params); NONNULL(grads); NONNULL(momentum_buf); NONNULL(seg_offsets); NONNULL(seg_active); NONNULL(seg_first);
   NONNULL(hyper);
   return sgd_flat_dev(params, grads, momentum_buf, seg_offsets, seg_active, seg_first, nseg, hyper, guard, ST(stream));
+}
+
+// ---- 2-D path (planar.cu)
+#define CHECK_DTYPE2(d) PCRL_REQUIRE((d) == PCRL_DTYPE_BF16 || (d) == PCRL_DTYPE_F32, "%s: dtype %d (bf16 or fp32 storage)", __func__, (d))
+int pcrl_im2col2d(const void* x, void* col, int N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                  int Kp, int image_nchw, int dtype, void* stream) {
+  NONNULL(x); NONNULL(col); CHECK_DTYPE2(dtype);
+  PCRL_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0, "pcrl_im2col2d: bad dims");
+  return im2col2d(x, col, N, H, W, C, k, stride, pad, Ho, Wo, Kp, image_nchw, dtype, ST(stream));
+}
+int pcrl_col2im2d(const void* dcol, void* dx, int N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                  int Kp, int dtype, void* stream) {
+  NONNULL(dcol); NONNULL(dx); CHECK_DTYPE2(dtype);
+  PCRL_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0, "pcrl_col2im2d: bad dims");
+  return col2im2d(dcol, dx, N, H, W, C, k, stride, pad, Ho, Wo, Kp, dtype, ST(stream));
+}
+int pcrl_maxpool2d_3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream) {
+  NONNULL(x); NONNULL(y); CHECK_DTYPE2(dtype);
+  return maxpool2d_3x3s2(x, nullptr, y, N, H, W, C, 0, dtype, ST(stream));
+}
+int pcrl_maxpool2d_3x3s2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
+                             void* stream) {
+  NONNULL(x); NONNULL(dy); NONNULL(dx); CHECK_DTYPE2(dtype);
+  return maxpool2d_3x3s2(x, dy, dx, N, H, W, C, 1, dtype, ST(stream));
+}
+int pcrl_add_relu(const void* a, const void* b, void* out, long long n, int op, int dtype, void* stream) {
+  NONNULL(a); NONNULL(b); NONNULL(out); CHECK_DTYPE2(dtype);
+  return add_relu(a, b, out, n, op, dtype, ST(stream));
+}
+int pcrl_upsample_nearest2x_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream) {
+  NONNULL(x); NONNULL(y); CHECK_DTYPE2(dtype);
+  return upsample_nearest2x(x, y, N, H, W, C, 0, dtype, ST(stream));
+}
+int pcrl_upsample_nearest2x_bwd(const void* g, void* dx, int N, int H, int W, int C, int dtype, void* stream) {
+  NONNULL(g); NONNULL(dx); CHECK_DTYPE2(dtype);
+  return upsample_nearest2x(g, dx, N, H, W, C, 1, dtype, ST(stream));
+}
+int pcrl_bilinear2d_fwd(const float* x, float* y, int NC, int H, int W, int scale, void* stream) {
+  NONNULL(x); NONNULL(y);
+  return bilinear2d(x, y, NC, H, W, scale, 0, ST(stream));
+}
+int pcrl_bilinear2d_bwd(const float* g, float* dx, int NC, int H, int W, int scale, void* stream) {
+  NONNULL(g); NONNULL(dx);
+  return bilinear2d(g, dx, NC, H, W, scale, 1, ST(stream));
+}
+int pcrl_conv2d_c3_fwd(const void* a, const float* w, const float* bias, float* out, int N, int H, int W, int C,
+                       int Cs, int k, int dtype, void* stream) {
+  NONNULL(a); NONNULL(w); NONNULL(bias); NONNULL(out); CHECK_DTYPE2(dtype);
+  return conv2d_c3_fwd(a, w, bias, out, N, H, W, C, Cs, k, dtype, ST(stream));
+}
+int pcrl_conv2d_c3_bwd(const void* a, const float* w, const float* dout, void* da, float* dw, float* db, int N,
+                       int H, int W, int C, int Cs, int k, int dtype, void* stream) {
+  NONNULL(a); NONNULL(w); NONNULL(dout); CHECK_DTYPE2(dtype);
+  return conv2d_c3_bwd(a, w, dout, da, dw, db, N, H, W, C, Cs, k, dtype, ST(stream));
 }
 
 }  // extern "C"

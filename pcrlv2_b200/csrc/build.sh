@@ -10,7 +10,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
 FAST="--use_fast_math"
 mkdir -p $BUILD
 pids=()
-for f in api igemm_kmajor igemm_mnmajor streaming heads losses augment; do
+for f in api igemm_kmajor igemm_mnmajor streaming heads losses augment planar; do
   if [ ! -f $BUILD/$f.o ] || [ $f.cu -nt $BUILD/$f.o ] || [ sm100.cuh -nt $BUILD/$f.o ] || [ common.cuh -nt $BUILD/$f.o ]; then
     EXTRA=""; case $f in igemm_*) EXTRA=$FAST;; esac
     nvcc $FLAGS $EXTRA -c $f.cu -o $BUILD/$f.o > $BUILD/$f.log 2>&1 &
@@ -18,5 +18,5 @@ for f in api igemm_kmajor igemm_mnmajor streaming heads losses augment; do
   fi
 done
 for p in "${pids[@]}"; do wait $p || { cat $BUILD/*.log | grep -E "error|Error" ; exit 1; }; done
-nvcc -shared -o $OUT $BUILD/api.o $BUILD/igemm_kmajor.o $BUILD/igemm_mnmajor.o $BUILD/streaming.o $BUILD/heads.o $BUILD/losses.o $BUILD/augment.o -lcudart
+nvcc -shared -o $OUT $BUILD/api.o $BUILD/igemm_kmajor.o $BUILD/igemm_mnmajor.o $BUILD/streaming.o $BUILD/heads.o $BUILD/losses.o $BUILD/augment.o $BUILD/planar.o -lcudart
 echo "built $(realpath $OUT)"

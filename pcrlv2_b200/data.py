@@ -29,8 +29,43 @@ class SyntheticLunaPretask(torch.utils.data.Dataset):
         return x1, x2, gt1, gt2, local
 
 
+class SyntheticChestPretask(torch.utils.data.Dataset):
+    """Batch contract of datasets/chestDataset.py:31-48: two global 3x224x224 crops, their targets, six local
+    3x96x96 crops (inputs normalised ~ N(0,1), targets in [0,1))."""
+
+    def __init__(self, length=64, size=(224, 224), local=(96, 96), n_local=6, seed=42):
+        self.length, self.size, self.local, self.n_local, self.seed = length, size, local, n_local, seed
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, index):
+        g = torch.Generator().manual_seed(self.seed * 1000003 + index)
+        x1 = torch.randn((3,) + tuple(self.size), generator=g)
+        x2 = torch.randn((3,) + tuple(self.size), generator=g)
+        gt1 = torch.rand((3,) + tuple(self.size), generator=g)
+        gt2 = torch.rand((3,) + tuple(self.size), generator=g)
+        local = [torch.randn((3,) + tuple(self.local), generator=g) for _ in range(self.n_local)]
+        return x1, x2, gt1, gt2, local
+
+
 class DataGenerator:
-    """Mirror of the reference DataGenerator (data.py:9-12) for the one loader the 3-D path uses."""
+    """Mirror of the reference DataGenerator (data.py:9-12): the LUNA (3-D) and chest (2-D) pretask loaders."""
+
+    def pcrlv2_chest_pretask(self):
+        """reference data.py:14-61 (PNG decoding + torchvision transforms on the CPU): synthetic batches of the
+        same contract here."""
+        args = self.config
+        if str(getattr(args, "data", "synthetic")) != "synthetic":
+            raise NotImplementedError("only --data synthetic is built for the chest pretask")
+        world = int(__import__("os").environ.get("WORLD_SIZE", "1"))
+        rank = int(__import__("os").environ.get("RANK", "0"))
+        ds = SyntheticChestPretask(length=getattr(args, "synthetic_items", 64 * max(1, args.b)),
+                                   seed=getattr(args, "seed", 42) + rank)
+        loader = torch.utils.data.DataLoader(ds, batch_size=max(2, args.b // world), shuffle=False,
+                                             num_workers=getattr(args, "workers", 0), pin_memory=True,
+                                             drop_last=True)
+        return {"train": loader, "eval": loader}
 
     def __init__(self, config):
         self.config = config

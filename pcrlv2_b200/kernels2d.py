@@ -1,0 +1,170 @@
+"""Python wrappers of the 2-D path's entry points (csrc/planar.cu + the plain tensor-core GEMMs).
+
+Activations: H-padded NHWC ``[N, 1, H+1, W, C]`` (the 3-D layout with D = 1) in the storage type
+(bf16 or fp32/TF32); the 3-channel network input, masks and targets are plain fp32 NCHW.
+Convolution = im2col -> GEMM (+ BatchNorm statistics in the epilogue) -> col2im for the data gradient.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .kernels import BF16, _dt, _chk, gemm_nt, gemm_tn
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def out_size(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+def dims2(p):
+    """(N, H, W, C) of an H-padded NHWC activation."""
+    n, d, h1, w, c = p.shape
+    assert d == 1
+    return n, h1 - 1, w, c
+
+
+def round_operand(w32, dtype):
+    """fp32 weights -> GEMM operand in the storage type (fp32: cvt.rna.tf32 of the magnitude bits)."""
+    if dtype == torch.float32:
+        return ((w32.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return w32.to(dtype).contiguous()
+
+
+def pack_conv2d_weights(w, cs, dtype):
+    """nn.Conv2d.weight (Cout, Cin, k, k) fp32 -> (wmat [CoutP][Kp], wt [Kp][CoutP]) GEMM operands.
+    K index = (ky*k + kx)*cs + c with ``cs`` the channel stride of the input activation (>= Cin; the channels
+    above Cin and the K padding are zero); CoutP = Cout rounded up to a multiple of 32."""
+    cout, cin, k, _ = w.shape
+    coutp = _round_up(cout, 32)
+    kp = _round_up(k * k * cs, 64)
+    m = torch.zeros((coutp, k * k, cs), dtype=torch.float32, device=w.device)
+    m[:cout, :, :cin] = w.detach().permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    wmat = torch.zeros((coutp, kp), dtype=torch.float32, device=w.device)
+    wmat[:, : k * k * cs] = m.reshape(coutp, k * k * cs)
+    return round_operand(wmat, dtype), round_operand(wmat.t().contiguous(), dtype)
+
+
+def unpack_conv2d_wgrad(dwmat, cout, cin, k, cs):
+    """[CoutP][Kp] fp32 -> (Cout, Cin, k, k)."""
+    g = dwmat[:cout, : k * k * cs].reshape(cout, k, k, cs)[..., :cin]
+    return g.permute(0, 3, 1, 2).contiguous()
+
+
+def im2col2d(x, k, s, p, dtype, image=False, cs=None):
+    """x: H-padded NHWC activation, or (image=True) the fp32 NCHW network input.  Returns (col, Ho, Wo)."""
+    if image:
+        _chk(x, torch.float32)
+        n, c, h, w = x.shape
+    else:
+        _chk(x, dtype)
+        n, h, w, c = dims2(x)
+    ho, wo = out_size(h, k, s, p), out_size(w, k, s, p)
+    kp = _round_up(k * k * c, 64)
+    col = torch.empty((n * (ho + 1) * wo, kp), dtype=dtype, device=x.device)
+    _lib.call("pcrl_im2col2d", x, col, n, h, w, c, k, s, p, ho, wo, kp, int(image), 0 if dtype == BF16 else 1)
+    return col, ho, wo
+
+
+def col2im2d(dcol, n, h, w, c, k, s, p):
+    ho, wo = out_size(h, k, s, p), out_size(w, k, s, p)
+    dx = torch.empty((n, 1, h + 1, w, c), dtype=dcol.dtype, device=dcol.device)
+    _lib.call("pcrl_col2im2d", dcol, dx, n, h, w, c, k, s, p, ho, wo, dcol.shape[1], _dt(dcol))
+    return dx
+
+
+def gemm_nt_stats(a, b, stats):
+    """C = A * B^T in the storage type with per-column (sum, sum of squares) ADDED to ``stats`` [1][cols][2] fp64."""
+    _chk(a), _chk(b, a.dtype)
+    rows, k = a.shape
+    cols = b.shape[0]
+    c = torch.empty((rows, cols), dtype=a.dtype, device=a.device)
+    _lib.call("pcrl_gemm_nt_stats", a, b, c, stats, rows, k, cols, _dt(a))
+    return c
+
+
+def conv2d_wgrad(dy2d, col):
+    """dW [CoutP][Kp] fp32 = dY^T * col on the tensor cores (operand roles swapped for CoutP = 32, where the
+    M = 64 minimum of the MMA would be half empty)."""
+    coutp = dy2d.shape[1]
+    if coutp % 64 == 0:
+        return gemm_tn(dy2d, col)
+    return gemm_tn(col, dy2d).t().contiguous()
+
+
+def maxpool_fwd(x):
+    n, h, w, c = dims2(x)
+    y = torch.empty((n, 1, (h - 1) // 2 + 2, (w - 1) // 2 + 1, c), dtype=x.dtype, device=x.device)
+    _lib.call("pcrl_maxpool2d_3x3s2_fwd", x, y, n, h, w, c, _dt(x))
+    return y
+
+
+def maxpool_bwd(x, dy):
+    n, h, w, c = dims2(x)
+    dx = torch.empty_like(x)
+    _lib.call("pcrl_maxpool2d_3x3s2_bwd", x, dy, dx, n, h, w, c, _dt(x))
+    return dx
+
+
+def add_relu(a, b, op=0):
+    _chk(a), _chk(b, a.dtype)
+    out = torch.empty_like(a)
+    _lib.call("pcrl_add_relu", a, b, out, a.numel(), op, _dt(a))
+    return out
+
+
+def up_nearest_fwd(x):
+    n, h, w, c = dims2(x)
+    y = torch.empty((n, 1, 2 * h + 1, 2 * w, c), dtype=x.dtype, device=x.device)
+    _lib.call("pcrl_upsample_nearest2x_fwd", x, y, n, h, w, c, _dt(x))
+    return y
+
+
+def up_nearest_bwd(g):
+    n, h2, w2, c = dims2(g)
+    dx = torch.empty((n, 1, h2 // 2 + 1, w2 // 2, c), dtype=g.dtype, device=g.device)
+    _lib.call("pcrl_upsample_nearest2x_bwd", g, dx, n, h2 // 2, w2 // 2, c, _dt(g))
+    return dx
+
+
+def bilinear_fwd(x, sf):
+    _chk(x, torch.float32)
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, h * sf, w * sf), dtype=torch.float32, device=x.device)
+    _lib.call("pcrl_bilinear2d_fwd", x, y, n * c, h, w, sf)
+    return y
+
+
+def bilinear_bwd(g, sf):
+    _chk(g, torch.float32)
+    n, c, h2, w2 = g.shape
+    dx = torch.zeros((n, c, h2 // sf, w2 // sf), dtype=torch.float32, device=g.device)
+    _lib.call("pcrl_bilinear2d_bwd", g, dx, n * c, h2 // sf, w2 // sf, sf)
+    return dx
+
+
+def conv_c3_fwd(a, w, bias, c):
+    """Conv2d(c -> 3, k, padding k//2) + bias on an H-padded activation (channels 0..c-1) -> fp32 NCHW."""
+    _chk(a), _chk(w, torch.float32)
+    n, h, wd, cs = dims2(a)
+    k = w.shape[-1]
+    out = torch.empty((n, 3, h, wd), dtype=torch.float32, device=a.device)
+    _lib.call("pcrl_conv2d_c3_fwd", a, w, bias, out, n, h, wd, c, cs, k, _dt(a))
+    return out
+
+
+def conv_c3_bwd(a, w, dout, c, need_da=True):
+    _chk(a), _chk(dout, torch.float32)
+    n, h, wd, cs = dims2(a)
+    k = w.shape[-1]
+    da = torch.empty_like(a) if need_da else None
+    dw = torch.zeros_like(w)
+    db = torch.zeros((3,), dtype=torch.float32, device=a.device)
+    _lib.call("pcrl_conv2d_c3_bwd", a, w, dout, da, dw, db, n, h, wd, c, cs, k, _dt(a))
+    return da, dw, db
+
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,4 +1,4 @@
-"""CLI mirror of the reference main.py:21-50 for the 3-D pre-training path.
+"""CLI mirror of the reference main.py:21-50: the 3-D (--n luna --d 3) and 2-D (--n chest --d 2) pre-training paths.
 
 Flags are the reference's (main.py:23-39).  ``--gpus`` keeps its meaning as the visible device
 list, but multi-GPU runs are launched one process per GPU:
@@ -13,6 +13,7 @@ import warnings
 import torch
 
 from .data import DataGenerator
+from .train_2d import train_pcrlv2
 from .train_3d import train_pcrlv2_3d
 
 warnings.filterwarnings('ignore')
@@ -60,11 +61,12 @@ def main(argv=None):
     random.seed(args.seed)
     torch.manual_seed(args.seed)
     data_loader = get_dataloader(args)
-    if args.model == 'pcrlv2' and args.phase == 'pretask' and args.d == 3:
+    if args.model == 'pcrlv2' and args.phase == 'pretask' and args.d == 2:
+        train_pcrlv2(args, data_loader)
+    elif args.model == 'pcrlv2' and args.phase == 'pretask' and args.d == 3:
         train_pcrlv2_3d(args, data_loader)
     else:
-        raise NotImplementedError("only --model pcrlv2 --phase pretask --d 3 is part of this build "
-                                  "(the 2-D path is listed as 'next' in SURVEY section 8f)")
+        raise NotImplementedError("only --model pcrlv2 --phase pretask with --d 2 or --d 3 is part of this build")
 
 
 if __name__ == '__main__':
