@@ -211,6 +211,10 @@ int pcrl_mse_scaled_bwd(const float* p, const float* t, const float* g, const fl
  * channels: HOST int[3] (C_s <= 256).  out2[0] += loss2, out2[1] += local_loss. */
 int pcrl_contrastive_fwd_bwd(const void* const* ptrs, const int* channels, int B, int n_local,
                              const int* draws, float* out2, float eps, void* stream);
+/* the same for S scales (1..5; the 2-D model has five decoder blocks, train_2d.py:111-117,143-155): ptrs = 9*S
+ * pointers in the same group order, channels HOST int[S] */
+int pcrl_contrastive_fwd_bwd_s(const void* const* ptrs, const int* channels, int S, int B, int n_local,
+                               const int* draws, float* out2, float eps, void* stream);
 /* torch.sigmoid of the 1-channel output volume (models/pcrlv2_model_3d.py:79,132) and its autograd */
 int pcrl_sigmoid_fwd(const float* x, float* y, long long n, void* stream);
 int pcrl_sigmoid_bwd(const float* y, const float* dy, float* dx, long long n, void* stream);

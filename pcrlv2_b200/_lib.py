@@ -56,6 +56,7 @@ SIGNATURES = {
     "pcrl_mse_scaled_fwd": [_P, _P, _P, _P, _L, _P],
     "pcrl_mse_scaled_bwd": [_P, _P, _P, _P, _P, _L, _P],
     "pcrl_contrastive_fwd_bwd": [_P, _P, _I, _I, _P, _P, _F, _P],
+    "pcrl_contrastive_fwd_bwd_s": [_P, _P, _I, _I, _I, _P, _P, _F, _P],
     "pcrl_sgd_flat_dev": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "pcrl_aug_flip": [_P, _P, _P, _I, _I, _I, _I, _P],
     "pcrl_aug_blur_axis": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

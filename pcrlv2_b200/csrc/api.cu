@@ -54,6 +54,7 @@ int cosine_mean_fwd_bwd(const float*, const float*, float*, float*, int, int, fl
 int mse_fwd(const float*, const float*, float*, long long, const float*, cudaStream_t);
 int mse_bwd(const float*, const float*, const float*, float*, long long, const float*, cudaStream_t);
 int contrastive_fwd_bwd(const void* const*, const int*, int, int, const int*, float*, float, cudaStream_t);
+int contrastive_fwd_bwd_s(const void* const*, const int*, int, int, int, const int*, float*, float, cudaStream_t);
 int sgd_flat_dev(float*, const float*, float*, const long long*, const int*, const int*, int, const float*, const float*, cudaStream_t);
 int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
 int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
@@ -306,6 +307,11 @@ int pcrl_contrastive_fwd_bwd(const void* const* ptrs, const int* channels, int B
                              float* out2, float eps, void* stream) {
   NONNULL(ptrs); NONNULL(channels); NONNULL(draws); NONNULL(out2);
   return contrastive_fwd_bwd(ptrs, channels, B, n_local, draws, out2, eps, ST(stream));
+}
+int pcrl_contrastive_fwd_bwd_s(const void* const* ptrs, const int* channels, int S, int B, int n_local,
+                               const int* draws, float* out2, float eps, void* stream) {
+  NONNULL(ptrs); NONNULL(channels); NONNULL(draws); NONNULL(out2);
+  return contrastive_fwd_bwd_s(ptrs, channels, S, B, n_local, draws, out2, eps, ST(stream));
 }
 int pcrl_sigmoid_fwd(const float* x, float* y, long long n, void* stream) {
   NONNULL(x); NONNULL(y);

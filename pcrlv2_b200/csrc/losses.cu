@@ -264,11 +264,13 @@ int cosine_mean_fwd_bwd(const float* x, const float* y, float* mean_out, float* 
 //   out[0] += loss2      = -1/2 (mean cos(pre1_s, pro2_s) + mean cos(pre2_s, pro1_s)),  s = draws[0]
 //   out[1] += local_loss = 1/(2 n_local) sum_i [ -1/2 (mean cos(pre1_a, proL_a[i]) + mean cos(preL_a[i], pro1_a))
 //                                               -1/2 (mean cos(pre2_b, proL_b[i]) + mean cos(preL_b[i], pro2_b)) ]
+#define PCRL_MAX_SCALES 5      // 3 (3-D model: up_tr256/128/64) or 5 (2-D model: the five decoder blocks)
 struct ContrastiveArgs {
-  const float* pre1[3]; const float* pro1[3]; const float* pre2[3]; const float* pro2[3];
-  const float* preL[3]; const float* proL[3];
-  float* dpre1[3]; float* dpre2[3]; float* dpreL[3];
-  int C[3];
+  const float* pre1[PCRL_MAX_SCALES]; const float* pro1[PCRL_MAX_SCALES]; const float* pre2[PCRL_MAX_SCALES];
+  const float* pro2[PCRL_MAX_SCALES]; const float* preL[PCRL_MAX_SCALES]; const float* proL[PCRL_MAX_SCALES];
+  float* dpre1[PCRL_MAX_SCALES]; float* dpre2[PCRL_MAX_SCALES]; float* dpreL[PCRL_MAX_SCALES];
+  int C[PCRL_MAX_SCALES];
+  int S;
   int B, n_local;
   const int* draws;
   float* out;
@@ -301,7 +303,7 @@ contrastive_kernel(const ContrastiveArgs a) {
   const int wid = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   const int B = a.B, nl = a.n_local;
   const int per_scale = B * (2 + nl);
-  if (wid >= 3 * per_scale) return;
+  if (wid >= a.S * per_scale) return;
   const int s = wid / per_scale;
   int r = wid % per_scale;
   const int C = a.C[s];
@@ -345,26 +347,31 @@ contrastive_kernel(const ContrastiveArgs a) {
   }
 }
 
-// ptrs: 27 device pointers in the order pre1[3], pro1[3], pre2[3], pro2[3], preL[3], proL[3], dpre1[3],
-// dpre2[3], dpreL[3] (scale index 0..2 = up_tr256, up_tr128, up_tr64)
-int contrastive_fwd_bwd(const void* const* ptrs, const int* C3, int B, int n_local, const int* draws,
-                        float* out2, float eps, cudaStream_t s) {
-  PCRL_REQUIRE(B >= 1 && n_local >= 1, "contrastive: bad dims");
+// ptrs: 9*S device pointers in the order pre1[S], pro1[S], pre2[S], pro2[S], preL[S], proL[S], dpre1[S],
+// dpre2[S], dpreL[S] (3-D model: scale index 0..2 = up_tr256, up_tr128, up_tr64; 2-D model: decoder blocks 0..4)
+int contrastive_fwd_bwd_s(const void* const* ptrs, const int* Cs, int S, int B, int n_local, const int* draws,
+                          float* out2, float eps, cudaStream_t s) {
+  PCRL_REQUIRE(B >= 1 && n_local >= 1 && S >= 1 && S <= PCRL_MAX_SCALES, "contrastive: bad dims (S=%d)", S);
   ContrastiveArgs a;
-  for (int i = 0; i < 3; i++) {
-    PCRL_REQUIRE(C3[i] >= 1 && C3[i] <= 256, "contrastive: C=%d must be in 1..256", C3[i]);
-    a.C[i] = C3[i];
-    a.pre1[i] = (const float*)ptrs[0 + i]; a.pro1[i] = (const float*)ptrs[3 + i];
-    a.pre2[i] = (const float*)ptrs[6 + i]; a.pro2[i] = (const float*)ptrs[9 + i];
-    a.preL[i] = (const float*)ptrs[12 + i]; a.proL[i] = (const float*)ptrs[15 + i];
-    a.dpre1[i] = (float*)ptrs[18 + i]; a.dpre2[i] = (float*)ptrs[21 + i]; a.dpreL[i] = (float*)ptrs[24 + i];
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < S; i++) {
+    PCRL_REQUIRE(Cs[i] >= 1 && Cs[i] <= 256, "contrastive: C=%d must be in 1..256", Cs[i]);
+    a.C[i] = Cs[i];
+    a.pre1[i] = (const float*)ptrs[0 * S + i]; a.pro1[i] = (const float*)ptrs[1 * S + i];
+    a.pre2[i] = (const float*)ptrs[2 * S + i]; a.pro2[i] = (const float*)ptrs[3 * S + i];
+    a.preL[i] = (const float*)ptrs[4 * S + i]; a.proL[i] = (const float*)ptrs[5 * S + i];
+    a.dpre1[i] = (float*)ptrs[6 * S + i]; a.dpre2[i] = (float*)ptrs[7 * S + i]; a.dpreL[i] = (float*)ptrs[8 * S + i];
   }
-  for (int i = 0; i < 27; i++) PCRL_REQUIRE(ptrs[i] != nullptr, "contrastive: pointer %d is NULL", i);
-  a.B = B; a.n_local = n_local; a.draws = draws; a.out = out2; a.eps = eps;
-  const int warps = 3 * B * (2 + n_local);
+  for (int i = 0; i < 9 * S; i++) PCRL_REQUIRE(ptrs[i] != nullptr, "contrastive: pointer %d is NULL", i);
+  a.S = S; a.B = B; a.n_local = n_local; a.draws = draws; a.out = out2; a.eps = eps;
+  const int warps = S * B * (2 + n_local);
   contrastive_kernel<<<(warps + 7) / 8, 256, 0, s>>>(a);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
+}
+int contrastive_fwd_bwd(const void* const* ptrs, const int* C3, int B, int n_local, const int* draws,
+                        float* out2, float eps, cudaStream_t s) {
+  return contrastive_fwd_bwd_s(ptrs, C3, 3, B, n_local, draws, out2, eps, s);
 }
 
 // ------------------------------------------------------------------------------ MSE

@@ -113,12 +113,13 @@ class _ContrastiveFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, draws, drawn, *tensors):
-        pre1, pro1, pre2, pro2, pre_l, pro_l = (list(tensors[3 * i:3 * i + 3]) for i in range(6))
+        S = len(tensors) // 6
+        pre1, pro1, pre2, pro2, pre_l, pro_l = (list(tensors[S * i:S * i + S]) for i in range(6))
         out, grads = K.contrastive_fwd_bwd([t.contiguous() for t in pre1], [t.detach().contiguous() for t in pro1],
                                            [t.contiguous() for t in pre2], [t.detach().contiguous() for t in pro2],
                                            [t.contiguous() for t in pre_l], [t.detach().contiguous() for t in pro_l],
                                            draws)
-        ctx.drawn = drawn
+        ctx.drawn, ctx.S = drawn, S
         ctx.save_for_backward(*(grads[0] + grads[1] + grads[2]))
         parts = out.detach().clone()
         ctx.mark_non_differentiable(parts)
@@ -126,12 +127,12 @@ class _ContrastiveFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _gparts):
-        saved = ctx.saved_tensors
-        dpre1, dpre2, dpre_l = saved[0:3], saved[3:6], saved[6:9]
+        saved, S = ctx.saved_tensors, ctx.S
+        dpre1, dpre2, dpre_l = saved[0:S], saved[S:2 * S], saved[2 * S:3 * S]
 
         def sel(group):
-            return [None if (ctx.drawn is not None and s not in ctx.drawn) else group[s] * g for s in range(3)]
-        none3 = [None, None, None]
+            return [None if (ctx.drawn is not None and s not in ctx.drawn) else group[s] * g for s in range(S)]
+        none3 = [None] * S
         return (None, None, *sel(dpre1), *none3, *sel(dpre2), *none3, *sel(dpre_l), *none3)
 
 

@@ -521,20 +521,21 @@ def mse_bwd(p, t, g, weight=None):
 
 def contrastive_fwd_bwd(pre1, pro1, pre2, pro2, pre_l, pro_l, draws, eps=1e-8):
     """The 1 + 2*n_local cos_loss terms of a step and their gradients in one launch.
-    pre1/pro1/pre2/pro2: 3 tensors [B, C_s] each; pre_l/pro_l: 3 tensors [n_local*B, C_s];
-    draws: int32 device tensor [1 + 2*n_local].  Returns (out [2] = (loss2, local_loss),
-    (dpre1[3], dpre2[3], dpre_l[3]))."""
+    pre1/pro1/pre2/pro2: S tensors [B, C_s] each (S = 3 for the 3-D model, 5 for the 2-D one); pre_l/pro_l:
+    S tensors [n_local*B, C_s]; draws: int32 device tensor [1 + 2*n_local].  Returns (out [2] = (loss2,
+    local_loss), (dpre1[S], dpre2[S], dpre_l[S]))."""
     import ctypes
     b = pre1[0].shape[0]
+    S = len(pre1)
     n_local = pre_l[0].shape[0] // b
     assert draws.dtype == torch.int32 and draws.is_cuda and draws.numel() >= 1 + 2 * n_local
     ins = [_f32c(t) for grp in (pre1, pro1, pre2, pro2, pre_l, pro_l) for t in grp]
     grads = [torch.empty_like(t) for grp in (pre1, pre2, pre_l) for t in grp]
-    ptrs = (ctypes.c_void_p * 27)(*[t.data_ptr() for t in ins + grads])
-    chans = (ctypes.c_int * 3)(*[int(t.shape[1]) for t in pre1])
+    ptrs = (ctypes.c_void_p * (9 * S))(*[t.data_ptr() for t in ins + grads])
+    chans = (ctypes.c_int * S)(*[int(t.shape[1]) for t in pre1])
     out = torch.zeros(2, dtype=torch.float32, device=draws.device)
-    _lib.call("pcrl_contrastive_fwd_bwd", ptrs, chans, b, n_local, draws, out, float(eps))
-    return out, (grads[0:3], grads[3:6], grads[6:9])
+    _lib.call("pcrl_contrastive_fwd_bwd_s", ptrs, chans, S, b, n_local, draws, out, float(eps))
+    return out, (grads[0:S], grads[S:2 * S], grads[2 * S:3 * S])
 
 
 def sigmoid_fwd(x):

@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from . import functional as Fn
 from .models.pcrlv2_model import PCRLv2
-from .train_3d import FlatSGD, _mse, _is_plain_cosine, _rank, init_distributed
+from .train_3d import (FlatSGD, GraphedStep, _mse, _is_plain_cosine, _is_plain_mse, _rank, init_distributed)
 from .utils import adjust_learning_rate, AverageMeter
 
 
@@ -41,11 +41,21 @@ def cos_loss(cosine, output1, output2):
     return loss, index
 
 
-def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine):
-    """Forward part of one iteration, reference train_2d.py:141-163.  Returns (loss, loss1, loss2, local_loss)."""
+def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine, static=None):
+    """Forward part of one iteration, reference train_2d.py:141-163.  Returns (loss, loss1, loss2, local_loss).
+    ``static`` (a train_3d._StaticCtl, captured-graph mode): the 13 cos_loss terms are ONE kernel that reads the
+    drawn scales from device memory, beta comes from the device, and the host constant ``static.index2`` selects
+    which deep-supervision mask enters the loss (one captured graph per value)."""
     bsz = x1.size(0)
     decoder_outputs1, mask1, middle_masks1 = model(x1)
     decoder_outputs2, _mask2, _ = model(x2, need_masks=False)
+    if static is not None:
+        local_views_outputs, _, _ = model(torch.cat(local_views, dim=0), local=True, need_masks=False)
+        closs, parts = Fn.contrastive_losses(decoder_outputs1, decoder_outputs2, local_views_outputs, static.draws, None)
+        loss1 = Fn.mse_loss(mask1, gt)
+        k = static.index2
+        loss4 = Fn.mse_loss(middle_masks1[k], gt, static.w4[k:k + 1])
+        return loss1 + closs + loss4, loss1, parts[0], parts[1]
     loss2, index2 = cos_loss(cosine, decoder_outputs1, decoder_outputs2)
     local_loss = 0.0
     local_input = torch.cat(local_views, dim=0)
@@ -67,6 +77,55 @@ def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine):
     return loss, loss1, loss2, local_loss
 
 
+class GraphedStep2d(GraphedStep):
+    """The 2-D iteration captured into CUDA graphs (see train_3d.GraphedStep): five scales, hence five graphs keyed by
+    index2, captured lazily into one memory pool; 3-channel static input buffers.  Without it the 2-D step is
+    launch-bound: ~1240 kernel launches from Python per 47 ms step at b=8 (profiles/r02s_bench_2d_eager.jsonl)."""
+    n_scales = 5
+    in_channels = 3
+
+    def _step_loss(self, views, crit, cos):
+        return pcrlv2_step_loss(self.model, self.x1, self.x2, self.gt, views, 0, crit, cos, static=self.ctl)
+
+    def _reached(self, draws):
+        """Parameters the reference's autograd graph reaches for these draws (note N3): everything except the
+        deep-supervision heads of the blocks != draws[0] (only middle_masks1[index2] enters the loss,
+        train_2d.py:158) and the BatchNorm1d + prediction head of a block no cos_loss term drew."""
+        names = getattr(self, "_names", None)
+        if names is None:
+            by_id = {id(p): n for n, p in self.model.named_parameters()}
+            names = self._names = [by_id[id(p)] for p in self.opt._ps]
+        drawn = set(int(d) for d in draws)
+        out = []
+        for n in names:
+            ok = True
+            if n.startswith("model.decoder.blocks."):
+                i, _, rest = n[len("model.decoder.blocks."):].partition(".")
+                if rest.startswith("deep_supervision_head."):
+                    ok = int(i) == int(draws[0])
+                elif rest.startswith("bn.") or rest.startswith("predictor_head."):
+                    ok = int(i) in drawn
+            out.append(ok)
+        return out
+
+
+def graphed_step_for(model, optimizer, criterion, cosine, x1, local_views):
+    """The cached GraphedStep2d of (model, optimizer) for this batch geometry, or None when the step cannot be
+    captured (foreign optimizer / criterion / similarity, PCRL_GRAPH=0)."""
+    if os.environ.get("PCRL_GRAPH", "1") == "0":
+        return None
+    if not (isinstance(model, PCRLv2) and isinstance(optimizer, FlatSGD) and _is_plain_mse(criterion)
+            and _is_plain_cosine(cosine) and model.training):
+        return None
+    key = (x1.shape[0], tuple(x1.shape[2:]), tuple(local_views[0].shape[2:]), len(local_views))
+    cache = optimizer.__dict__.setdefault("_graphed", {})
+    gs = cache.get(key)
+    if gs is None:
+        cache.clear()
+        gs = cache[key] = GraphedStep2d(model, optimizer, key[0], key[1], key[2], key[3])
+    return gs
+
+
 def train_pcrlv2_inner(args, epoch, train_loader, model, optimizer, criterion, cosine):
     """one epoch training for instance discrimination -- reference train_2d.py:120-195"""
     model.train()
@@ -81,20 +140,28 @@ def train_pcrlv2_inner(args, epoch, train_loader, model, optimizer, criterion, c
     for idx, (input1, input2, gt, gt2, local_views) in enumerate(train_loader):
         data_time.update(time.time() - end)
         bsz = input1.size(0)
-        x1 = input1.float().to(dev, non_blocking=True)
-        x2 = input2.float().to(dev, non_blocking=True)
-        gt = gt.float().to(dev, non_blocking=True)
-        local_views = [v.float().to(dev, non_blocking=True) for v in local_views]
-        loss, loss1, loss2, local_loss = pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine)
-        # ===================backward=====================
-        optimizer.zero_grad()
-        loss.backward()
-        optimizer.step()
+        gs = graphed_step_for(model, optimizer, criterion, cosine, input1, local_views)
+        if gs is not None:
+            # captured step: inputs go into the graph's static buffers, one replay, one read-back of the scalars
+            gs.load(input1.float(), input2.float(), gt.float(), [v.float() for v in local_views])
+            loss_v, loss1_v, loss2_v, local_v = gs.run(epoch, skip_guard=False).tolist()
+        else:
+            x1 = input1.float().to(dev, non_blocking=True)
+            x2 = input2.float().to(dev, non_blocking=True)
+            gt = gt.float().to(dev, non_blocking=True)
+            local_views = [v.float().to(dev, non_blocking=True) for v in local_views]
+            loss, loss1, loss2, local_loss = pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine)
+            # ===================backward=====================
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            loss_v, loss1_v, loss2_v = loss.item(), loss1.item(), loss2.item()
+            local_v = local_loss.item() if torch.is_tensor(local_loss) else float(local_loss)
         # ===================meters=====================
-        mg_loss_meter.update(loss1.item(), bsz)
-        loss_meter.update(loss2.item(), bsz)
-        prob_meter.update(local_loss.item() if torch.is_tensor(local_loss) else float(local_loss), bsz)
-        all_loss_meter.update(loss.item(), bsz)
+        mg_loss_meter.update(loss1_v, bsz)
+        loss_meter.update(loss2_v, bsz)
+        prob_meter.update(local_v, bsz)
+        all_loss_meter.update(loss_v, bsz)
         torch.cuda.synchronize()
         batch_time.update(time.time() - end)
         end = time.time()

@@ -315,19 +315,20 @@ def pcrlv2_step_loss(model, x1, x2, gt, local_views, epoch, criterion, cosine, s
 
 
 class _StaticCtl:
-    """Device-resident control block of a captured step: draws int32[16], w4 float32[4] (beta * one-hot
-    of the drawn deep-supervision scale), hyper float32[8] ([lr, momentum, weight_decay, grad_scale,
-    skip_threshold]); one pinned host mirror, one asynchronous copy per step."""
+    """Device-resident control block of a captured step: draws int32[16], w4 float32[8] (beta * one-hot
+    of the drawn deep-supervision scale; 3 scales in the 3-D model, 5 in the 2-D one), hyper float32[8]
+    ([lr, momentum, weight_decay, grad_scale, skip_threshold]); one pinned host mirror, one asynchronous
+    copy per step."""
 
     def __init__(self, dev):
-        self.host = torch.zeros(28, dtype=torch.int32).pin_memory()
-        self.dev = torch.zeros(28, dtype=torch.int32, device=dev)
+        self.host = torch.zeros(32, dtype=torch.int32).pin_memory()
+        self.dev = torch.zeros(32, dtype=torch.int32, device=dev)
         self.draws = self.dev[0:16]
-        self.w4 = self.dev[16:20].view(torch.float32)
-        self.hyper = self.dev[20:28].view(torch.float32)
+        self.w4 = self.dev[16:24].view(torch.float32)
+        self.hyper = self.dev[24:32].view(torch.float32)
         self._h_draws = self.host[0:16]
-        self._h_w4 = self.host[16:20].view(torch.float32)
-        self._h_hyper = self.host[20:28].view(torch.float32)
+        self._h_w4 = self.host[16:24].view(torch.float32)
+        self._h_hyper = self.host[24:32].view(torch.float32)
         self._event = None
         self.index2 = 0          # host constant of the graph being captured (see GraphedStep)
 
@@ -366,15 +367,18 @@ class GraphedStep:
     ``num_batches_tracked`` are updated in place by the captured kernels.  Results are bit-compatible
     with the eager path up to the order of floating-point atomics (tests/test_graph_gpu.py)."""
 
+    n_scales = 3          # scales a cos_loss draw chooses from (= graphs keyed by index2)
+    in_channels = 1
+
     def __init__(self, model, optimizer, bsz, vol, local, n_local, warmup=1):
         if not isinstance(optimizer, FlatSGD):
             raise TypeError("GraphedStep needs a FlatSGD optimizer")
         dev = optimizer._flat_p.device
         self.model, self.opt, self.key = model, optimizer, (bsz, tuple(vol), tuple(local), n_local)
-        self.x1 = torch.zeros((bsz, 1) + tuple(vol), device=dev)
+        self.x1 = torch.zeros((bsz, self.in_channels) + tuple(vol), device=dev)
         self.x2 = torch.zeros_like(self.x1)
         self.gt = torch.zeros_like(self.x1)
-        self.local = torch.zeros((n_local * bsz, 1) + tuple(local), device=dev)
+        self.local = torch.zeros((n_local * bsz, self.in_channels) + tuple(local), device=dev)
         self.ctl = _StaticCtl(dev)
         self.out = torch.zeros(4, device=dev)          # loss, loss1, loss2, local_loss of the last replay
         self.n_local, self.bsz = n_local, bsz
@@ -384,13 +388,19 @@ class GraphedStep:
         self._warmup = warmup
         self._capture(0)
 
+    # -- model-specific pieces (overridden by the 2-D path, train_2d.GraphedStep2d)
+    def _step_loss(self, views, crit, cos):
+        return pcrlv2_step_loss(self.model, self.x1, self.x2, self.gt, views, 0, crit, cos, static=self.ctl)
+
+    def _reached(self, draws):
+        return self.opt.reached_from_draws(self.model, draws)
+
     # -- the step as it is captured
     def _static_step(self):
         bump_param_epoch()     # the tensor-core operand copies of the weights are re-packed INSIDE the graph
         crit, cos = nn.MSELoss(), nn.CosineSimilarity()
         views = [self.local[i * self.bsz:(i + 1) * self.bsz] for i in range(self.n_local)]
-        loss, loss1, loss2, local_loss = pcrlv2_step_loss(self.model, self.x1, self.x2, self.gt, views, 0,
-                                                          crit, cos, static=self.ctl)
+        loss, loss1, loss2, local_loss = self._step_loss(views, crit, cos)
         self.opt.zero_grad()
         loss.backward()
         self.opt.step_static(self.ctl.hyper, loss)
@@ -447,8 +457,8 @@ class GraphedStep:
         torch.cuda.synchronize()
 
     def capture_all(self):
-        """Capture the graphs of all three index2 values now (otherwise: lazily on first use)."""
-        for k in range(3):
+        """Capture the graphs of all index2 values now (otherwise: lazily on first use)."""
+        for k in range(self.n_scales):
             if k not in self.graphs:
                 self._capture(k)
         return self
@@ -467,14 +477,14 @@ class GraphedStep:
         replay.  Returns the device tensor [loss, loss1, loss2, local_loss] (no host sync here)."""
         opt = self.opt
         group = opt.param_groups[0]
-        draws = draw_scales(self.n_local)
+        draws = draw_scales(self.n_local, self.n_scales)
         if draws[0] not in self.graphs:
             self._capture(draws[0])
         beta = 0.5 * (1. + math.cos(math.pi * epoch / 240))
         world = dist.get_world_size(opt._pg) if opt._distributed else 1
         thr = 1000.0 if (skip_guard and epoch > 10) else float("inf")
         self.ctl.upload(draws, beta, group["lr"], group["momentum"], group["weight_decay"], 1.0 / world, thr)
-        reached = opt.reached_from_draws(self.model, draws)
+        reached = self._reached(draws)
         opt.upload_flags(reached)
         self.graphs[draws[0]].replay()
         self.last_reached, self.last_draws = reached, draws

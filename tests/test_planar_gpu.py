@@ -322,6 +322,62 @@ def test_full_step_2d_vs_reference_fixture(precision):
     assert med < 1.5, med
 
 
+@pytest.mark.parametrize("nsteps", [1, 3])
+def test_graphed_step_2d_matches_eager_step(nsteps):
+    """The captured 2-D step (five graphs keyed by index2, draws / beta / lr as device data) against the eager step
+    from the same state and the same Python RNG: loss scalars, which parameters own a momentum buffer afterwards
+    (= the reached-parameter rule against autograd's own record, note N3), parameters and BatchNorm buffers.
+    Not bitwise: two forwards of the SAME input from the SAME state already differ (tools/diag_2d_det.py: the
+    statistics' atomics order moves a BatchNorm scale by an fp32 ulp, the tf32 rounding of the stored activation
+    turns that into a tf32 ulp in a few elements, and this network amplifies it to 1e-2 of the mask's range by the
+    last block), so one step is compared at that noise level and three steps (lr 1e-2, b=4) loosely."""
+    from pcrlv2_b200 import train_2d as T2
+    from pcrlv2_b200.train_3d import FlatSGD
+    crit, cos = torch.nn.MSELoss(), torch.nn.CosineSimilarity()
+    batches = [orc.synthetic_batch(4, seed=50 + i, size=(64, 64), local=(32, 32)) for i in range(nsteps)]
+    loader = [(b[0], b[1], b[2], b[2], b[3]) for b in batches]
+    args = types.SimpleNamespace(lr=1e-2, momentum=0.9, weight_decay=1e-4, amp=False, epochs=240)
+    res = {}
+    for mode in ("eager", "eager2", "graph"):
+        os.environ["PCRL_GRAPH"] = "0" if mode.startswith("eager") else "1"
+        try:
+            m, sd0 = build2d("fp32")
+            opt = FlatSGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+            random.seed(77)
+            meters = T2.train_pcrlv2_inner(args, 0, loader, m, opt, crit, cos)
+            torch.cuda.synchronize()
+            if mode == "graph":
+                gs = next(iter(opt._graphed.values()))
+                assert isinstance(gs, T2.GraphedStep2d) and len(gs.graphs) >= 1
+            name_of = {id(p): n for n, p in m.named_parameters()}
+            res[mode] = dict(meters=meters, sd={k: v.detach().cpu().clone() for k, v in m.state_dict().items()},
+                             owned={name_of[id(p)] for p in opt.state if "momentum_buffer" in opt.state[p]})
+            opt.__dict__.pop("_graphed", None)
+        finally:
+            os.environ.pop("PCRL_GRAPH", None)
+    e, e2, g = res["eager"], res["eager2"], res["graph"]
+    log(f"[2d graph, {nsteps} step(s)] meters (cos, mg, local) eager {e['meters']} eager again {e2['meters']} graph {g['meters']}")
+    for a, a2, b in zip(e["meters"], e2["meters"], g["meters"]):
+        assert abs(a - b) < 3 * abs(a - a2) + (1e-3 if nsteps == 1 else 3e-2), (e["meters"], e2["meters"], g["meters"])
+    assert e["owned"] == g["owned"] == e2["owned"], sorted(e["owned"] ^ g["owned"])
+
+    def update_errors(x, y):
+        errs = []
+        for k, v in x["sd"].items():
+            if k.endswith("num_batches_tracked"):
+                assert int(v) == int(y["sd"][k]), k
+            elif orc.is_param(k) and not orc.is_cancelling(k) and k in x["owned"]:
+                du, dv = v.double() - sd0[k].double(), y["sd"][k].double() - sd0[k].double()
+                errs.append(((du - dv).norm() / du.norm().clamp_min(1e-30)).item())
+        return float(np.median(errs)), max(errs)
+
+    noise, graph = update_errors(e, e2), update_errors(e, g)
+    log(f"[2d graph, {nsteps} step(s)] update rel-L2 (median, worst): eager vs eager again {noise[0]:.3e} {noise[1]:.3e}; "
+        f"graph vs eager {graph[0]:.3e} {graph[1]:.3e}")
+    # the captured step must be no further from the eager step than the eager step is from itself
+    assert graph[0] <= 2.0 * noise[0] + 0.02, (graph, noise)
+
+
 def test_trainer_2d_entry_point(tmp_path):
     """pcrlv2_b200.main --n chest --d 2: epoch loop, LR schedule, the encoder-only checkpoint of train_2d.py:99."""
     from pcrlv2_b200 import main as M

@@ -2,7 +2,7 @@
 3x224x224 crops + six local 3x96x96 crops per item, synthetic data, random-init weights.
 
 Prints one JSON line per precision: images/s of the full pre-training step (three forwards, loss, backward, SGD)
-of this library (eager launches; the 2-D step is not captured into a CUDA graph yet), the host cost of a step, the
+of this library (captured CUDA-graph step by default, --eager for Python launches), the host cost of a step, the
 end-to-end number through train_2d.train_pcrlv2_inner with pinned host batches, and -- the competitor on the same
 GPU -- the SAME network written with torch's own ops (the oracle's functional restatement of the reference model
 run on CUDA tensors = PyTorch/cuDNN eager with cudnn.benchmark, TF32 allowed as by default; bf16 via autocast).
@@ -58,18 +58,28 @@ def ours(precision, args):
     data = [batch(args.batch, 42 + i, args.size, args.local, dev) for i in range(nb)]
     random.seed(42)
 
-    def step(i):
+    def eager_step(i):
         x1, x2, gt, lv = data[i % nb]
         loss, *_ = T2.pcrlv2_step_loss(m, x1, x2, gt, lv, 0, crit, cos)
         opt.zero_grad()
         loss.backward()
         opt.step()
 
+    gs = None
+    if not args.eager:
+        gs = T2.graphed_step_for(m, opt, crit, cos, data[0][0], data[0][3]).capture_all()
+
+    def graph_step(i):
+        x1, x2, gt, lv = data[i % nb]
+        gs.load(x1, x2, gt, lv)          # device -> device into the graph's static buffers
+        gs.run(0, skip_guard=False)
+
+    step = eager_step if gs is None else graph_step
     for i in range(args.warmup):
         step(i)
     _lib.launch_count[0] = 0
     ms = timed(step, args.steps)
-    launches = _lib.launch_count[0] / args.steps
+    launches = (gs.launches if gs is not None else _lib.launch_count[0] / args.steps)
     host = []
     for i in range(3):
         torch.cuda.synchronize()
@@ -92,7 +102,13 @@ def ours(precision, args):
     finally:
         sys.stdout = so
     h2d = sum(t.numel() * 4 for t in hb[0][:3]) + sum(t.numel() * 4 for t in hb[0][3])
+    eager = None
+    if gs is not None:
+        for i in range(2):
+            eager_step(i)
+        eager = {"ms_per_step": timed(eager_step, max(3, args.steps // 2))}
     return {"ms_per_step": ms, "value": args.batch / ms * 1e3, "host_ms_per_step": statistics.median(host),
+            "step": "eager (Python launches)" if gs is None else "CUDA graph replay", "eager_step": eager,
             "gpu_launches_per_step": launches,
             "e2e": {"value": args.batch * k2 / (t1 - t0), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 16, "steps": k2},
@@ -140,6 +156,7 @@ def main():
     ap.add_argument("--local", type=int, nargs=2, default=(96, 96))
     ap.add_argument("--channels_last", action="store_true")
     ap.add_argument("--skip_torch", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time the eager step instead of the captured graph")
     args = ap.parse_args()
     for precision in ("fp32", "bf16"):
         r = ours(precision, args)
@@ -148,7 +165,8 @@ def main():
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32" if precision == "fp32" else "bf16", "data": "synthetic",
                 "config": {"workload": "NIH ChestX-ray 2D pretrain ResNet-18 UNet, b=%d/GPU, 2 x 3x%dx%d + 6 x 3x%dx%d, %s"
-                           % (args.batch, *args.size, *args.local, precision), "step": "eager (Python launches)"},
+                           % (args.batch, *args.size, *args.local, precision), "step": r["step"]},
+                "eager_step": r["eager_step"],
                 "host_ms_per_step": r["host_ms_per_step"], "gpu_launches": r["gpu_launches_per_step"] * args.steps,
                 "launches_per_step": r["gpu_launches_per_step"], "e2e": r["e2e"], "peak_mem_gb": r["peak_mem_gb"]}
         if not args.skip_torch:
