@@ -318,6 +318,14 @@ int pcrl_conv2d_c3_fwd(const void* a, const float* w, const float* bias, float* 
 int pcrl_conv2d_c3_bwd(const void* a, const float* w, const float* dout, void* da, float* dw, float* db, int N,
                        int H, int W, int C, int Cs, int k, int dtype, void* stream);
 
+/* nn.Conv2d.weight (Cout,Cin,k,k) fp32 -> the GEMM operands of the im2col convolution: wmat [CoutP][Kp] (forward)
+ * and wt [Kp][CoutP] (data gradient), K index = (ky*k+kx)*cs + c, zero padding, rounded to the operand type;
+ * and the way back for the weight gradient the GEMM produced ([CoutP][Kp] fp32, or its transpose) */
+int pcrl_pack_conv2d_weights(const float* w, void* wmat, void* wt, int Cout, int Cin, int k, int cs, int CoutP,
+                             int Kp, int dtype, void* stream);
+int pcrl_unpack_conv2d_wgrad(const float* dw_gemm, float* g, int Cout, int Cin, int k, int cs, int CoutP, int Kp,
+                             int transposed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,8 @@ SIGNATURES = {
     "pcrl_bilinear2d_bwd": [_P, _P, _I, _I, _I, _I, _P],
     "pcrl_conv2d_c3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pcrl_conv2d_c3_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_pack_conv2d_weights": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pcrl_unpack_conv2d_wgrad": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
 }
 
 _lib = None

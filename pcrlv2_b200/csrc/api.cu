@@ -80,6 +80,8 @@ int upsample_nearest2x(const void*, void*, int, int, int, int, int, int, cudaStr
 int bilinear2d(const float*, float*, int, int, int, int, int, cudaStream_t);
 int conv2d_c3_fwd(const void*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int conv2d_c3_bwd(const void*, const float*, const float*, void*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int pack_conv2d_weights(const float*, void*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int unpack_conv2d_wgrad(const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 
 }  // namespace pcrl
 
@@ -437,6 +439,17 @@ int pcrl_conv2d_c3_bwd(const void* a, const float* w, const float* dout, void* d
                        int H, int W, int C, int Cs, int k, int dtype, void* stream) {
   NONNULL(a); NONNULL(w); NONNULL(dout); CHECK_DTYPE2(dtype);
   return conv2d_c3_bwd(a, w, dout, da, dw, db, N, H, W, C, Cs, k, dtype, ST(stream));
+}
+
+int pcrl_pack_conv2d_weights(const float* w, void* wmat, void* wt, int Cout, int Cin, int k, int cs, int CoutP, int Kp,
+                             int dtype, void* stream) {
+  NONNULL(w); NONNULL(wmat); NONNULL(wt); CHECK_DTYPE2(dtype);
+  return pack_conv2d_weights(w, wmat, wt, Cout, Cin, k, cs, CoutP, Kp, dtype, ST(stream));
+}
+int pcrl_unpack_conv2d_wgrad(const float* dw_gemm, float* g, int Cout, int Cin, int k, int cs, int CoutP, int Kp,
+                             int transposed, void* stream) {
+  NONNULL(dw_gemm); NONNULL(g);
+  return unpack_conv2d_wgrad(dw_gemm, g, Cout, Cin, k, cs, CoutP, Kp, transposed, ST(stream));
 }
 
 }  // extern "C"

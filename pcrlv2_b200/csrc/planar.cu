@@ -523,6 +523,37 @@ __global__ void conv_c3_bwd_weight_kernel(const T* __restrict__ a, const float* 
   }
 }
 
+
+// ------------------------------------------------------------------------------ weight layout converters
+// nn.Conv2d.weight (Cout, Cin, k, k) fp32 -> wmat [CoutP][Kp] and wt [Kp][CoutP] in the operand type;
+// K index = (ky*k + kx)*cs + c (cs = channel stride of the input activation), zero outside.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_conv2d_kernel(const float* __restrict__ w, T* __restrict__ wmat, T* __restrict__ wt, int Cout, int Cin, int k,
+                   int cs, int CoutP, int Kp) {
+  const long long total = (long long)CoutP * Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Kp), co = (int)(i / Kp);
+    const int tap = q / cs, c = q - tap * cs;
+    float v = 0.f;
+    if (co < Cout && tap < k * k && c < Cin) v = w[((size_t)co * Cin + c) * k * k + tap];
+    store1(wmat + i, v);
+    store1(wt + (size_t)q * CoutP + co, v);
+  }
+}
+// dW as the GEMM left it ([CoutP][Kp], or transposed [Kp][CoutP]) -> (Cout, Cin, k, k) fp32
+__global__ void __launch_bounds__(256)
+unpack_conv2d_wgrad_kernel(const float* __restrict__ dwm, float* __restrict__ g, int Cout, int Cin, int k, int cs,
+                           int CoutP, int Kp, int transposed) {
+  const int kk = k * k;
+  const long long total = (long long)Cout * Cin * kk;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % kk), c = (int)((i / kk) % Cin), co = (int)(i / ((long long)kk * Cin));
+    const int q = tap * cs + c;
+    g[i] = transposed ? dwm[(size_t)q * CoutP + co] : dwm[(size_t)co * Kp + q];
+  }
+}
+
 // ------------------------------------------------------------------------------ launchers
 #define DISPATCH_T(dtype, KERNEL, grid, block, smem, stream, ...)                                        \
   do {                                                                                                   \
@@ -661,6 +692,23 @@ int conv2d_c3_bwd(const void* a, const float* w, const float* dout, void* da, fl
     else conv_c3_bwd_weight_kernel<float><<<(unsigned)blocks, k * k * C, 0, st>>>((const float*)a, dout, dw, db, N, H, W, C, Cs, k, chunk);
     PCRL_CHECK_LAUNCH();
   }
+  return PCRL_OK;
+}
+
+int pack_conv2d_weights(const float* w, void* wmat, void* wt, int Cout, int Cin, int k, int cs, int CoutP, int Kp,
+                        int dtype, cudaStream_t st) {
+  PCRL_REQUIRE(CoutP >= Cout && cs >= Cin && Kp >= k * k * cs, "pack_conv2d_weights: bad padded dims");
+  const long long total = (long long)CoutP * Kp;
+  if (dtype == PCRL_DTYPE_BF16) pack_conv2d_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>(w, (bf16_t*)wmat, (bf16_t*)wt, Cout, Cin, k, cs, CoutP, Kp);
+  else pack_conv2d_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(w, (float*)wmat, (float*)wt, Cout, Cin, k, cs, CoutP, Kp);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+int unpack_conv2d_wgrad(const float* dwm, float* g, int Cout, int Cin, int k, int cs, int CoutP, int Kp, int transposed,
+                        cudaStream_t st) {
+  const long long total = (long long)Cout * Cin * k * k;
+  unpack_conv2d_wgrad_kernel<<<grid_for(total, 256), 256, 0, st>>>(dwm, g, Cout, Cin, k, cs, CoutP, Kp, transposed);
+  PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
 

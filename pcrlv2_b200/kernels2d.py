@@ -41,17 +41,19 @@ def pack_conv2d_weights(w, cs, dtype):
     cout, cin, k, _ = w.shape
     coutp = _round_up(cout, 32)
     kp = _round_up(k * k * cs, 64)
-    m = torch.zeros((coutp, k * k, cs), dtype=torch.float32, device=w.device)
-    m[:cout, :, :cin] = w.detach().permute(0, 2, 3, 1).reshape(cout, k * k, cin)
-    wmat = torch.zeros((coutp, kp), dtype=torch.float32, device=w.device)
-    wmat[:, : k * k * cs] = m.reshape(coutp, k * k * cs)
-    return round_operand(wmat, dtype), round_operand(wmat.t().contiguous(), dtype)
+    wmat = torch.empty((coutp, kp), dtype=dtype, device=w.device)
+    wt = torch.empty((kp, coutp), dtype=dtype, device=w.device)
+    _lib.call("pcrl_pack_conv2d_weights", w.detach().contiguous(), wmat, wt, cout, cin, k, cs, coutp, kp,
+              0 if dtype == BF16 else 1)
+    return wmat, wt
 
 
-def unpack_conv2d_wgrad(dwmat, cout, cin, k, cs):
-    """[CoutP][Kp] fp32 -> (Cout, Cin, k, k)."""
-    g = dwmat[:cout, : k * k * cs].reshape(cout, k, k, cs)[..., :cin]
-    return g.permute(0, 3, 1, 2).contiguous()
+def unpack_conv2d_wgrad(dwmat, cout, cin, k, cs, transposed=False):
+    """[CoutP][Kp] fp32 (``transposed``: [Kp][CoutP]) -> (Cout, Cin, k, k)."""
+    kp, coutp = (dwmat.shape if transposed else dwmat.shape[::-1])
+    g = torch.empty((cout, cin, k, k), dtype=torch.float32, device=dwmat.device)
+    _lib.call("pcrl_unpack_conv2d_wgrad", dwmat, g, cout, cin, k, cs, coutp, kp, int(transposed))
+    return g
 
 
 def im2col2d(x, k, s, p, dtype, image=False, cs=None):
@@ -86,13 +88,13 @@ def gemm_nt_stats(a, b, stats):
     return c
 
 
-def conv2d_wgrad(dy2d, col):
-    """dW [CoutP][Kp] fp32 = dY^T * col on the tensor cores (operand roles swapped for CoutP = 32, where the
-    M = 64 minimum of the MMA would be half empty)."""
+def conv2d_wgrad(dy2d, col, cout, cin, k, cs):
+    """dW (Cout, Cin, k, k) fp32 = dY^T * col on the tensor cores (operand roles swapped for CoutP = 32, where the
+    M = 64 minimum of the MMA would be half empty), unpacked from the GEMM layout."""
     coutp = dy2d.shape[1]
     if coutp % 64 == 0:
-        return gemm_tn(dy2d, col)
-    return gemm_tn(col, dy2d).t().contiguous()
+        return unpack_conv2d_wgrad(gemm_tn(dy2d, col), cout, cin, k, cs)
+    return unpack_conv2d_wgrad(gemm_tn(col, dy2d), cout, cin, k, cs, transposed=True)
 
 
 def maxpool_fwd(x):

@@ -136,14 +136,14 @@ class _Conv2dBNFn(torch.autograd.Function):
         dy, sums = K.norm_act_bwd(y, g_a.contiguous() if g_a is not None else None, None, gavg, scale, shift,
                                   mean, invstd, gamma, cfg.act, None, pool=False, per_sample=False,
                                   batch_stats=cfg.training)
-        sums = sums.sum(0).float()
-        grads[3] = sums[:cout, 1].contiguous()
-        grads[4] = sums[:cout, 0].contiguous()
+        sums = sums[0].float()              # one statistics group (BatchNorm); views below, no copies
+        grads[3] = sums[:cout, 1]
+        grads[4] = sums[:cout, 0]
         if ctx.has_bias:
             grads[2] = torch.zeros(cout, dtype=torch.float32, device=y.device)     # cancels in the BatchNorm
         dy2d = dy.view(n * (ho + 1) * wo, coutp)
         col, _, _ = K2.im2col2d(x, cfg.k, cfg.s, cfg.p, cfg.dtype, image=cfg.image)
-        grads[1] = K2.unpack_conv2d_wgrad(K2.conv2d_wgrad(dy2d, col), cout, cfg.conv.weight.shape[1], cfg.k, cs)
+        grads[1] = K2.conv2d_wgrad(dy2d, col, cout, cfg.conv.weight.shape[1], cfg.k, cs)
         del col
         if ctx.needs_input_grad[0]:
             _, wt = _packed2d(cfg.conv, cs, cfg.dtype)

@@ -118,6 +118,28 @@ def _worker(rank, world, port, out_path):
     T.train_pcrlv2_inner(args, 0, [(s2[0][sl], s2[1][sl], s2[2][sl], s2[2][sl], [v[sl] for v in s2[3]])], m2, opt2, crit, cos)
     dist.all_gather(gathered, opt2._flat_p.clone())
     assert all(torch.equal(gathered[0], t) for t in gathered)
+    # ---- the 2-D path: two captured data-parallel steps, replicas bit-identical, gradient all-reduce active
+    from oracle import pcrlv2_oracle_2d as orc2
+    from pcrlv2_b200.models import PCRLv2
+    from pcrlv2_b200 import train_2d as T2
+    m3 = PCRLv2(precision="fp32")
+    m3.load_state_dict(orc2.clone_state(orc2.init_state(0)))
+    m3 = m3.to(dev).train()
+    opt3 = T.FlatSGD(m3.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+    assert opt3._distributed
+    p0 = opt3._flat_p.clone()
+    random.seed(3)
+    for seed in (21, 22):
+        f2 = orc2.synthetic_batch(4 * world, seed=seed, size=(64, 64), local=(32, 32))
+        sl = slice(4 * rank, 4 * rank + 4)
+        T2.train_pcrlv2_inner(args, 0, [(f2[0][sl], f2[1][sl], f2[2][sl], f2[2][sl], [v[sl] for v in f2[3]])],
+                              m3, opt3, crit, cos)
+    assert opt3.__dict__.get("_graphed"), "the 2-D trainer did not take the captured-graph step"
+    g3 = [torch.zeros_like(opt3._flat_p) for _ in range(world)]
+    dist.all_gather(g3, opt3._flat_p.clone())
+    assert all(torch.equal(g3[0], t) for t in g3), "2-D replicas diverged"
+    assert not torch.equal(opt3._flat_p, p0)
+    log.append(f"rank {rank}: 2-D path, two captured data-parallel steps: replicas bit-identical")
     dist.barrier()
     if rank == 0:
         open(out_path, "w").write("ok\n" + "\n".join(log))
@@ -125,7 +147,8 @@ def _worker(rank, world, port, out_path):
     # (destroy_process_group otherwise waits forever)
     import gc
     opt2._graphed.clear()
-    del m2, opt2
+    opt3._graphed.clear()
+    del m2, opt2, m3, opt3
     gc.collect()
     torch.cuda.synchronize()
     dist.destroy_process_group()

@@ -103,7 +103,7 @@ def test_conv2d_im2col_gemm_fwd_bwd(cfg, dtype):
     dyp = torch.zeros((n, 1, ho + 1, wo, coutp), dtype=dtype, device="cuda")
     dyp[:, 0, 1:, :, :cout] = dy.permute(0, 2, 3, 1).to(dtype)
     dy2d = dyp.view(-1, coutp)
-    dw = K2.unpack_conv2d_wgrad(K2.conv2d_wgrad(dy2d, col), cout, cin, k, cs)
+    dw = K2.conv2d_wgrad(dy2d, col, cout, cin, k, cs)
     assert rl2(dw, wr.grad) < 2e-5, rl2(dw, wr.grad)
     if not image:
         dcol = K.gemm_nt(dy2d, wtr, out_fp32=False)
