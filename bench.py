@@ -394,8 +394,9 @@ def measure(args, precision, host, rank, world, dev):
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full) of the dominant kernel's
 # largest launch (up_tr64.ops.0 forward at b=32) and its algorithmic bytes: CONSTANTS from the
-# committed capture profiles/r01c_ncu_tensor_kernels.md, not re-measured by a bench run
-NCU_TRAFFIC = {"bf16": (1.0910e9 + 0.5056e9, 1.640e9), "fp32": (2.1829e9 + 1.0389e9, 3.279e9)}
+# committed capture profiles/r02z_ncu_tensor_kernels.md (igemm_roll_kernel, the variant of the family that runs this
+# launch since round 2), not re-measured by a bench run
+NCU_TRAFFIC = {"bf16": (1.097394e9 + 0.506811e9, 1.640e9), "fp32": (2.195162e9 + 1.040620e9, 3.279e9)}
 
 
 def roofline_of(r, precision, peaks, peak_src, dev):
@@ -434,7 +435,7 @@ def roofline_of(r, precision, peaks, peak_src, dev):
     fl = flops_per_sample()
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak else None, "traffic": traffic,
-            "traffic_note": ("CONSTANT from profiles/r01c_ncu_tensor_kernels.md (ncu --set full, dram__bytes_read.sum + "
+            "traffic_note": ("CONSTANT from profiles/r02z_ncu_tensor_kernels.md (ncu --set full, dram__bytes_read.sum + "
                              "dram__bytes_write.sum of this kernel's largest launch, up_tr64.ops.0 forward at b=32; "
                              "algorithmic bytes %.3f GB); not re-measured by this run" % (algo_bytes / 1e9)),
             **extra,

@@ -27,7 +27,7 @@ bytes for a 3x3); the implicit-GEMM kernel of the 3-D path needs 2-D spatial til
 """
 from __future__ import annotations
 
-import math
+import os as _os
 
 import torch
 import torch.nn as nn
@@ -99,7 +99,7 @@ def _conv_stats(x, cfg):
         shift = (beta - mean * scale).contiguous()
         mean, invstd = mean.contiguous(), invstd.contiguous()
     y = y.view(n, 1, ho + 1, wo, coutp)
-    return y, scale, shift, mean, invstd, gamma, (n, ho, wo, cout, coutp, cs)
+    return y, scale, shift, mean, invstd, gamma, (n, ho, wo, cout, coutp, cs), col
 
 
 class _Conv2dBNFn(torch.autograd.Function):
@@ -110,13 +110,16 @@ class _Conv2dBNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma_, beta_, cfg):
         ctx.set_materialize_grads(False)
-        y, scale, shift, mean, invstd, gamma, dims = _conv_stats(x, cfg)
+        y, scale, shift, mean, invstd, gamma, dims, col = _conv_stats(x, cfg)
         n, ho, wo, cout, coutp, cs = dims
         a, _, avg = K.norm_act_fwd(y, scale, shift, cfg.act, None, want_full=True, want_pool=False,
                                    want_avg=bool(cfg.want_avg))
         ctx.cfg, ctx.dims = cfg, dims
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x, y, scale, shift, mean, invstd, gamma)
+        # the im2col matrix is kept for the weight gradient (9x the activation bytes of a 3x3, ~9 GB per b=8 step
+        # in fp32: cheaper than a second im2col pass on a 180 GB part); PCRL_2D_SAVE_COL=0 recomputes it instead
+        keep = _os.environ.get("PCRL_2D_SAVE_COL", "1") != "0"
+        ctx.save_for_backward(x, y, scale, shift, mean, invstd, gamma, col if keep else None)
         if cfg.want_avg:
             return a, (avg[:, :cout] * (1.0 / float(ho * wo))).contiguous()
         return a
@@ -124,7 +127,7 @@ class _Conv2dBNFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_a, g_avg=None):
         cfg = ctx.cfg
-        x, y, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        x, y, scale, shift, mean, invstd, gamma, col = ctx.saved_tensors
         n, ho, wo, cout, coutp, cs = ctx.dims
         grads = [None] * 6
         if g_a is None and g_avg is None:
@@ -142,7 +145,8 @@ class _Conv2dBNFn(torch.autograd.Function):
         if ctx.has_bias:
             grads[2] = torch.zeros(cout, dtype=torch.float32, device=y.device)     # cancels in the BatchNorm
         dy2d = dy.view(n * (ho + 1) * wo, coutp)
-        col, _, _ = K2.im2col2d(x, cfg.k, cfg.s, cfg.p, cfg.dtype, image=cfg.image)
+        if col is None:
+            col, _, _ = K2.im2col2d(x, cfg.k, cfg.s, cfg.p, cfg.dtype, image=cfg.image)
         grads[1] = K2.conv2d_wgrad(dy2d, col, cout, cfg.conv.weight.shape[1], cfg.k, cs)
         del col
         if ctx.needs_input_grad[0]:

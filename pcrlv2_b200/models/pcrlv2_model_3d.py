@@ -53,6 +53,7 @@ def bump_param_epoch():
 import os as _os
 
 _SIDE = {}            # device index -> side stream
+_SIDE_DIRTY = set()   # device indices whose side stream has weight-gradient work queued since the last join
 _JOIN_PENDING = [None]    # id of the autograd graph task that already queued the join callback
 _EXPLICIT_JOIN = [False]  # captured-graph step: the caller joins the side stream itself (FlatSGD.step_static)
 
@@ -66,9 +67,13 @@ def _side_stream(device):
 
 
 def join_side_streams():
-    """Make the current stream wait for everything queued on the side streams."""
-    for st in _SIDE.values():
-        torch.cuda.current_stream(st.device).wait_stream(st)
+    """Make the current stream wait for the weight-gradient work queued on the side streams.  Streams with
+    nothing queued since the last join are left alone: waiting on an idle stream that is not part of an ongoing
+    CUDA-graph capture (the 2-D path never forks onto it) would invalidate the capture."""
+    for idx, st in _SIDE.items():
+        if idx in _SIDE_DIRTY:
+            torch.cuda.current_stream(st.device).wait_stream(st)
+    _SIDE_DIRTY.clear()
     _JOIN_PENDING[0] = None
 
 
@@ -84,6 +89,7 @@ def _overlap_target(weight):
 
 def _wgrad_overlapped(dy, x, weight, flat, exact=False):
     side = _side_stream(dy.device)
+    _SIDE_DIRTY.add(dy.device.index if dy.device.index is not None else torch.cuda.current_device())
     side.wait_stream(torch.cuda.current_stream())          # dy (and zero_grad) are ordered before
     with torch.cuda.stream(side):
         g = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x, exact=exact))
