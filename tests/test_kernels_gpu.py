@@ -34,6 +34,8 @@ CONV_SHAPES = [
     (1, 6, 10, 16, 128, 64),
     (1, 4, 6, 8, 64, 128),
     (2, 5, 3, 7, 64, 64),
+    (1, 4, 16, 32, 64, 64),      # plane of 561 rows, D % 4 == 0, 64 columns: the rolling plane-window kernel
+    (2, 8, 20, 24, 32, 64),      # the same kernel with the 32-channel chunk and two window tiles + a ragged third
 ]
 
 

@@ -25,15 +25,32 @@ from pcrlv2_b200.models import PCRLv2
 from pcrlv2_b200.train_3d import FlatSGD
 
 
-def timed(fn, steps):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import torch.distributed as dist
+
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def barrier():
+    if WORLD > 1:
+        dist.barrier()
     torch.cuda.synchronize()
+
+
+def timed(fn, steps):
+    """ms per step: CUDA events on this rank's stream between two barriers, max over the ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record()
     for i in range(steps):
         fn(i)
     e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+    if WORLD > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item()
 
 
 def batch(bsz, seed, size, local, dev=None, pin=False):
@@ -49,14 +66,17 @@ def batch(bsz, seed, size, local, dev=None, pin=False):
 
 
 def ours(precision, args):
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", LOCAL)
     torch.manual_seed(0)
     m = PCRLv2(precision=precision).to(dev).train()
+    if WORLD > 1:
+        for t in list(m.parameters()) + list(m.buffers()):
+            dist.broadcast(t.data, src=0)
     opt = FlatSGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
     crit, cos = torch.nn.MSELoss(), torch.nn.CosineSimilarity()
     nb = 3
-    data = [batch(args.batch, 42 + i, args.size, args.local, dev) for i in range(nb)]
-    random.seed(42)
+    data = [batch(args.batch, 42 + 100 * RANK + i, args.size, args.local, dev) for i in range(nb)]
+    random.seed(42)          # the same draws on every rank
 
     def eager_step(i):
         x1, x2, gt, lv = data[i % nb]
@@ -87,30 +107,42 @@ def ours(precision, args):
         step(i)
         host.append((time.perf_counter() - t0) * 1e3)
     # end to end: pinned host batches -> H2D every step, loss scalars read back (the public trainer call)
-    hb = [batch(args.batch, 42 + i, args.size, args.local, pin=True) for i in range(nb)]
+    hb = [batch(args.batch, 42 + 100 * RANK + i, args.size, args.local, pin=True) for i in range(nb)]
     k2 = max(3, args.steps // 2)
     loader = [(hb[i % nb][0], hb[i % nb][1], hb[i % nb][2], hb[i % nb][2], hb[i % nb][3]) for i in range(k2)]
     targs = types.SimpleNamespace(lr=1e-3, momentum=0.9, weight_decay=1e-4, amp=precision == "bf16", epochs=240)
     so = sys.stdout
     sys.stdout = open(os.devnull, "w")
     try:
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         T2.train_pcrlv2_inner(targs, 0, loader, m, opt, crit, cos)
-        torch.cuda.synchronize()
+        barrier()
         t1 = time.perf_counter()
     finally:
         sys.stdout = so
+    et = torch.tensor([t1 - t0], device=dev)
+    sync = None
+    if WORLD > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        chk = torch.stack([opt._flat_p.double().sum(), (opt._flat_p.double() ** 2).sum()])
+        allc = [torch.zeros_like(chk) for _ in range(WORLD)]
+        dist.all_gather(allc, chk)
+        sync = bool(all(torch.equal(allc[0], c) for c in allc))
+    t0, t1 = 0.0, et.item()
     h2d = sum(t.numel() * 4 for t in hb[0][:3]) + sum(t.numel() * 4 for t in hb[0][3])
     eager = None
     if gs is not None:
         for i in range(2):
             eager_step(i)
         eager = {"ms_per_step": timed(eager_step, max(3, args.steps // 2))}
-    return {"ms_per_step": ms, "value": args.batch / ms * 1e3, "host_ms_per_step": statistics.median(host),
+    if gs is not None:
+        opt.__dict__.get("_graphed", {}).clear()       # captured NCCL work must go before the communicator does
+    return {"ms_per_step": ms, "value": WORLD * args.batch / ms * 1e3, "host_ms_per_step": statistics.median(host),
+            "replicas_in_sync": sync,
             "step": "eager (Python launches)" if gs is None else "CUDA graph replay", "eager_step": eager,
             "gpu_launches_per_step": launches,
-            "e2e": {"value": args.batch * k2 / (t1 - t0), "unit": "images/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": WORLD * args.batch * k2 / (t1 - t0), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 16, "steps": k2},
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
 
@@ -158,10 +190,15 @@ def main():
     ap.add_argument("--skip_torch", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time the eager step instead of the captured graph")
     args = ap.parse_args()
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+        args.skip_torch = True
     for precision in ("fp32", "bf16"):
         r = ours(precision, args)
-        line = {"metric": "ChestX-ray 2D pretrain images/sec (configs[4], per-GPU shard b=%d)" % args.batch,
-                "value": r["value"], "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": "ChestX-ray 2D pretrain images/sec (configs[4]: b=%d per GPU x %d GPU(s))" % (args.batch, WORLD),
+                "value": r["value"], "unit": "images/s", "n_gpus": WORLD, "steps": args.steps, "warmup": args.warmup,
+                "replicas_in_sync": r["replicas_in_sync"],
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32" if precision == "fp32" else "bf16", "data": "synthetic",
                 "config": {"workload": "NIH ChestX-ray 2D pretrain ResNet-18 UNet, b=%d/GPU, 2 x 3x%dx%d + 6 x 3x%dx%d, %s"
@@ -176,7 +213,13 @@ def main():
                                                           note="the oracle's functional restatement of the reference model on CUDA tensors")
             except Exception as e:   # noqa: BLE001
                 line["torch_cudnn_eager_same_gpu"] = {"error": repr(e)[:200]}
-        print(json.dumps(line), flush=True)
+        if RANK == 0:
+            print(json.dumps(line), flush=True)
+    if WORLD > 1:
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
