@@ -198,3 +198,73 @@ def test_c_abi_argument_errors_without_gpu():
     # norm/act channel count must be 8 * 2^k
     assert lib.pcrl_norm_act_fwd(fake, fake, fake, None, fake, None, None, 0, 0, 0, 1, 4, 4, 4, 24, 0, None) == -1
     assert b"8 * 2^k" in lib.pcrl_last_error()
+
+
+# ------------------------------------------------------------------------------ 2-D path, host side
+def test_model2d_surface_matches_reference_layout():
+    from oracle import pcrlv2_oracle_2d as orc2
+    from pcrlv2_b200.models import PCRLv2
+    m = PCRLv2()
+    sd = m.state_dict()
+    spec = orc2.state_spec()
+    assert [k for k, _, _ in spec] == list(sd.keys())            # = the reference PCRLv2().state_dict() (make_golden_2d.py)
+    for k, shape, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    m.load_state_dict(orc2.init_state(1))
+    # the checkpoint of train_2d.py:99 is the ENCODER's state_dict: torchvision resnet18 minus fc
+    import torchvision
+    ref = torchvision.models.resnet18()
+    del ref.fc
+    ref.load_state_dict(m.model.encoder.state_dict(), strict=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 3, 32, 32))
+    with pytest.raises(NotImplementedError):
+        PCRLv2(n_class=1)
+    with pytest.raises(ValueError):
+        PCRLv2(precision="fp16")
+
+
+def test_reached_parameter_rule_2d_matches_the_oracles_autograd():
+    """note N3 for the 2-D model: GraphedStep2d._reached(draws) (what the captured step tells SGD) against the set of
+    parameters that actually receive a gradient in the oracle's autograd graph, for several draw patterns."""
+    from oracle import pcrlv2_oracle_2d as orc2
+    from pcrlv2_b200.models import PCRLv2
+    from pcrlv2_b200.train_2d import GraphedStep2d
+
+    class FixedDraws:
+        def __init__(self, seq):
+            self.seq = list(seq)
+
+        def randint(self, a, b):
+            v = self.seq.pop(0)
+            assert a <= v <= b
+            return v
+
+    m = PCRLv2()
+    names = [n for n, _ in m.named_parameters()]
+    fake = types.SimpleNamespace(model=m, opt=types.SimpleNamespace(_ps=[p for _, p in m.named_parameters()]))
+    sd0 = orc2.init_state(0)
+    x1, x2, gt, lv = orc2.synthetic_batch(2, seed=1, size=(32, 32), local=(32, 32), n_local=2)
+    for draws in ([0, 0, 0, 0, 0], [3, 1, 1, 4, 1], [4, 2, 0, 2, 0], [2, 2, 2, 2, 2]):
+        sd = orc2.clone_state(sd0)
+        keys = [k for k in sd if orc2.is_param(k)]
+        for k in keys:
+            sd[k].requires_grad_(True)
+        loss, _, got = orc2.step_loss(sd, x1, x2, gt, lv, 0, FixedDraws(draws))
+        assert got == draws
+        grads = torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)
+        reached_ref = {k: g is not None for k, g in zip(keys, grads)}
+        rule = dict(zip(names, GraphedStep2d._reached(fake, draws)))
+        assert rule == reached_ref, [k for k in names if rule[k] != reached_ref[k]][:8]
+        fake.__dict__.pop("_names", None)
+
+
+def test_synthetic_chest_batch_contract_and_cli_dispatch():
+    from pcrlv2_b200.data import DataGenerator
+    args = types.SimpleNamespace(data="synthetic", b=4, workers=0, seed=42, synthetic_items=8)
+    loader = DataGenerator(args).pcrlv2_chest_pretask()["train"]
+    x1, x2, g1, g2, lv = next(iter(loader))
+    assert x1.shape == (4, 3, 224, 224) and g2.shape == x2.shape and len(lv) == 6 and lv[0].shape == (4, 3, 96, 96)
+    assert float(g1.min()) >= 0.0 and float(g1.max()) < 1.0
+    from pcrlv2_b200 import main as M
+    assert M.train_pcrlv2.__module__ == "pcrlv2_b200.train_2d"      # main.py:47-48 dispatches --d 2 to train_2d

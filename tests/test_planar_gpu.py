@@ -256,6 +256,59 @@ def test_model2d_forward_vs_oracle(precision):
     assert worst < (5e-3 if precision == "fp32" else 5e-2)
 
 
+def test_model2d_need_masks_false_keeps_the_state_trajectory():
+    """The trainer's forwards for x2 / local views skip the mask heads' output (need_masks=False, an extension).
+    They must leave exactly the state the full forward leaves: every BatchNorm buffer and counter, and the same
+    (pro, pre) outputs."""
+    x = orc.synthetic_batch(4, seed=7, size=(64, 64), local=(32, 32))[0].cuda()
+    outs = {}
+    for need in (True, False):
+        m, _ = build2d("fp32")
+        with torch.no_grad():
+            dec, mask, mm = m(x, need_masks=need)
+        outs[need] = (dec, {k: v.detach().clone() for k, v in m.state_dict().items()})
+        assert (mask is None) == (not need) and len(mm) == (5 if need else 0)
+    for (p1, q1), (p2, q2) in zip(outs[True][0], outs[False][0]):
+        assert rl2(p2, p1) < 5e-2 and rl2(q2, q1) < 0.2           # run-to-run noise level (tools/diag_2d_det.py)
+    for k, v in outs[True][1].items():
+        w = outs[False][1][k]
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(w), k
+        elif k.endswith("running_mean") or k.endswith("running_var"):
+            assert (v - w).abs().max().item() <= 2e-3 * max(1.0, v.abs().max().item()), k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_model2d_eval_mode_forward(precision):
+    """model.eval(): BatchNorm2d / BatchNorm1d normalise with the running statistics; buffers do not move."""
+    from oracle import operand_emulation_2d as emu
+    m, sd0 = build2d(precision)
+    # non-trivial running statistics: one train-mode forward on both sides first
+    x0, x1 = (orc.synthetic_batch(4, seed=s, size=(64, 64), local=(32, 32))[0] for s in (11, 12))
+    sd = orc.clone_state(sd0)
+    with torch.no_grad():
+        orc.forward(sd, x0)
+        m(x0.cuda())
+        m.eval()
+        before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        sde = orc.clone_state(sd)
+        o_dec, o_mask, o_mm = orc.forward(sd, x1, training=False)
+        with emu.rounding(EMU[precision]):
+            e_dec, e_mask, e_mm = orc.forward(sde, x1, training=False)
+        dec, mask, mm = m(x1.cuda())
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    f, tol, _ = SLACK[precision]
+    e, ee = rl2(mask, o_mask), rl2(e_mask, o_mask)
+    log(f"[2d eval {precision}] mask CUDA vs fp32 oracle {e:.3e}; emulation {ee:.3e}")
+    # the running statistics of the two sides already differ by the train-mode forward's noise: a wider factor
+    assert e <= 2.5 * f * ee + 5 * tol, (e, ee)
+    for s_ in range(5):
+        em, ep = rl2(mm[s_], o_mm[s_]), rl2(dec[s_][0], o_dec[s_][0])
+        log(f"[2d eval {precision}] scale {s_}: middle mask {em:.3e} (emulation {rl2(e_mm[s_], o_mm[s_]):.3e}) pro {ep:.3e}")
+        assert em <= 2.5 * f * rl2(e_mm[s_], o_mm[s_]) + 5 * tol
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_full_step_2d_vs_reference_fixture(precision):
     """One full iteration (three forwards, four loss terms, backward, SGD) at the fixture configuration (b=8,
