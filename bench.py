@@ -550,9 +550,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default 32; 8 for --workload large)")
-    ap.add_argument("--workload", default="luna64", choices=["luna64", "large"],
+    ap.add_argument("--workload", default="luna64", choices=["luna64", "large", "chest2d"],
                     help="luna64: 64x64x32 crops (configs[1]/[2], the headline); large: configs[3], 128x128x64 "
-                         "crops, b=8, bf16 -- its line is recorded under profiles/, it is not the headline")
+                         "crops, b=8, bf16 -- its line is recorded under profiles/, it is not the headline; "
+                         "chest2d: configs[4], the 2-D path (b=8 per GPU, bf16 unless --precision is given; "
+                         "tools/bench_2d.py does the measuring)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["bf16", "fp32"],
                     help="activation storage / tensor-core operand type of the headline measurement "
@@ -562,6 +564,12 @@ def main():
     ap.add_argument("--no-also", action="store_true",
                     help="skip the device-resident measurement at the other precision ('also' key)")
     args = ap.parse_args()
+    if args.workload == "chest2d":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_2d
+        argv = ["--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(args.batch or 8), "--skip_torch",
+                "--precision", args.precision if "--precision" in sys.argv else "bf16"] + (["--eager"] if args.eager else [])
+        return bench_2d.main(argv)
     set_workload(args.workload)
     if args.batch is None:
         args.batch = 8 if args.workload == "large" else 32

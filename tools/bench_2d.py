@@ -179,7 +179,7 @@ def torch_eager(precision, args):
     return {"ms_per_step": ms, "value": args.batch / ms * 1e3}
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--steps", type=int, default=10)
@@ -189,12 +189,13 @@ def main():
     ap.add_argument("--channels_last", action="store_true")
     ap.add_argument("--skip_torch", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time the eager step instead of the captured graph")
-    args = ap.parse_args()
+    ap.add_argument("--precision", default="both", choices=["both", "fp32", "bf16"])
+    args = ap.parse_args(argv)
     torch.cuda.set_device(LOCAL)
     if WORLD > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
         args.skip_torch = True
-    for precision in ("fp32", "bf16"):
+    for precision in (("fp32", "bf16") if args.precision == "both" else (args.precision,)):
         r = ours(precision, args)
         line = {"metric": "ChestX-ray 2D pretrain images/sec (configs[4]: b=%d per GPU x %d GPU(s))" % (args.batch, WORLD),
                 "value": r["value"], "unit": "images/s", "n_gpus": WORLD, "steps": args.steps, "warmup": args.warmup,
