@@ -388,7 +388,7 @@ int pcrl_sgd_flat_dev(float* params, const float* grads, float* momentum_buf, co
 }
 
 // ---- 2-D path (planar.cu)
-#define CHECK_DTYPE2(d) PCRL_REQUIRE((d) == PCRL_DTYPE_BF16 || (d) == PCRL_DTYPE_F32, "%s: dtype %d (bf16 or fp32 storage)", __func__, (d))
+#define CHECK_DTYPE2(d) CHECK_DTYPE(d)
 int pcrl_im2col2d(const void* x, void* col, int N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
                   int Kp, int image_nchw, int dtype, void* stream) {
   NONNULL(x); NONNULL(col); CHECK_DTYPE2(dtype);

@@ -53,6 +53,19 @@ __device__ __forceinline__ void copy8(const float* s, float* d) {
   reinterpret_cast<uint4*>(d)[0] = reinterpret_cast<const uint4*>(s)[0];
   reinterpret_cast<uint4*>(d)[1] = reinterpret_cast<const uint4*>(s)[1];
 }
+// fp32 stored exactly (PCRL_DTYPE_F32X, precision='fp32x3'): same memory format as float, no tf32 rounding on store
+struct f32x { float v; };
+__device__ __forceinline__ void load8(const f32x* p, float (&f)[8]) { load8(reinterpret_cast<const float*>(p), f); }
+__device__ __forceinline__ void store8(f32x* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void zero8(f32x* p) { zero8(reinterpret_cast<float*>(p)); }
+__device__ __forceinline__ void copy8(const f32x* s, f32x* d) {
+  copy8(reinterpret_cast<const float*>(s), reinterpret_cast<float*>(d));
+}
+__device__ __forceinline__ float to_float(f32x v) { return v.v; }
+__device__ __forceinline__ void store1(f32x* p, float v) { p->v = v; }
 __device__ __forceinline__ float to_float(bf16_t v) { return __bfloat162float(v); }
 __device__ __forceinline__ float to_float(float v) { return v; }
 __device__ __forceinline__ void store1(bf16_t* p, float v) { *p = __float2bfloat16(v); }
@@ -555,10 +568,12 @@ unpack_conv2d_wgrad_kernel(const float* __restrict__ dwm, float* __restrict__ g,
 }
 
 // ------------------------------------------------------------------------------ launchers
-#define DISPATCH_T(dtype, KERNEL, grid, block, smem, stream, ...)                                        \
-  do {                                                                                                   \
-    if ((dtype) == PCRL_DTYPE_BF16) KERNEL<bf16_t><<<grid, block, smem, stream>>>(__VA_ARGS__);          \
-    else KERNEL<float><<<grid, block, smem, stream>>>(__VA_ARGS__);                                      \
+// runs STMT with `T` = the storage type selected by `dtype`
+#define PCRL_DISPATCH3(dtype, STMT)                                   \
+  do {                                                                \
+    if ((dtype) == PCRL_DTYPE_BF16) { typedef bf16_t T; STMT; }       \
+    else if ((dtype) == PCRL_DTYPE_F32X) { typedef f32x T; STMT; }    \
+    else { typedef float T; STMT; }                                   \
   } while (0)
 
 int im2col2d(const void* x, void* col, int N, int H, int W, int C, int k, int s, int p, int Ho, int Wo, int Kp,
@@ -566,17 +581,12 @@ int im2col2d(const void* x, void* col, int N, int H, int W, int C, int k, int s,
   PCRL_REQUIRE(Kp % 8 == 0 && Kp >= k * k * C, "im2col2d: Kp=%d must be a multiple of 8 and >= k*k*C", Kp);
   PCRL_REQUIRE(Ho == (H + 2 * p - k) / s + 1 && Wo == (W + 2 * p - k) / s + 1, "im2col2d: output size mismatch");
   const long long total = (long long)N * (Ho + 1) * Wo * (Kp / 8);
+  const unsigned g = grid_for(total, 256);
   if (image_nchw) {
-    if (dtype == PCRL_DTYPE_BF16)
-      im2col2d_image_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (bf16_t*)col, N, H, W, C, k, s, p, Ho, Wo, Kp);
-    else
-      im2col2d_image_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)col, N, H, W, C, k, s, p, Ho, Wo, Kp);
+    PCRL_DISPATCH3(dtype, (im2col2d_image_kernel<T><<<g, 256, 0, st>>>((const float*)x, (T*)col, N, H, W, C, k, s, p, Ho, Wo, Kp)));
   } else {
     PCRL_REQUIRE(C % 8 == 0, "im2col2d: C=%d must be a multiple of 8", C);
-    if (dtype == PCRL_DTYPE_BF16)
-      im2col2d_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>((const bf16_t*)x, (bf16_t*)col, N, H, W, C, k, s, p, Ho, Wo, Kp);
-    else
-      im2col2d_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)col, N, H, W, C, k, s, p, Ho, Wo, Kp);
+    PCRL_DISPATCH3(dtype, (im2col2d_kernel<T><<<g, 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, k, s, p, Ho, Wo, Kp)));
   }
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
@@ -586,10 +596,7 @@ int col2im2d(const void* dcol, void* dx, int N, int H, int W, int C, int k, int 
              int dtype, cudaStream_t st) {
   PCRL_REQUIRE(C % 8 == 0 && Kp >= k * k * C, "col2im2d: C=%d must be a multiple of 8, Kp=%d >= k*k*C", C, Kp);
   const long long total = (long long)N * (H + 1) * W * (C / 8);
-  if (dtype == PCRL_DTYPE_BF16)
-    col2im2d_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>((const bf16_t*)dcol, (bf16_t*)dx, N, H, W, C, k, s, p, Ho, Wo, Kp);
-  else
-    col2im2d_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)dcol, (float*)dx, N, H, W, C, k, s, p, Ho, Wo, Kp);
+  PCRL_DISPATCH3(dtype, (col2im2d_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)dcol, (T*)dx, N, H, W, C, k, s, p, Ho, Wo, Kp)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -600,16 +607,10 @@ int maxpool2d_3x3s2(const void* x, const void* dy, void* out, int N, int H, int 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   if (!backward) {
     const long long total = (long long)N * (Ho + 1) * Wo * (C / 8);
-    if (dtype == PCRL_DTYPE_BF16)
-      maxpool3s2_fwd_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>((const bf16_t*)x, (bf16_t*)out, N, H, W, C, Ho, Wo);
-    else
-      maxpool3s2_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)out, N, H, W, C, Ho, Wo);
+    PCRL_DISPATCH3(dtype, (maxpool3s2_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)out, N, H, W, C, Ho, Wo)));
   } else {
     const long long total = (long long)N * (H + 1) * W * (C / 8);
-    if (dtype == PCRL_DTYPE_BF16)
-      maxpool3s2_bwd_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>((const bf16_t*)x, (const bf16_t*)dy, (bf16_t*)out, N, H, W, C, Ho, Wo);
-    else
-      maxpool3s2_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)out, N, H, W, C, Ho, Wo);
+    PCRL_DISPATCH3(dtype, (maxpool3s2_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)out, N, H, W, C, Ho, Wo)));
   }
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
@@ -620,15 +621,9 @@ int add_relu(const void* a, const void* b, void* out, long long n, int op, int d
   PCRL_REQUIRE(n % 8 == 0 && op >= 0 && op <= 2, "add_relu: n=%lld must be a multiple of 8, op in 0..2", n);
   const long long n8 = n / 8;
   const unsigned g = grid_for(n8, 256);
-  if (dtype == PCRL_DTYPE_BF16) {
-    if (op == 0) add_relu_fwd_kernel<bf16_t><<<g, 256, 0, st>>>((const bf16_t*)a, (const bf16_t*)b, (bf16_t*)out, n8);
-    else if (op == 1) add_relu_bwd_kernel<bf16_t><<<g, 256, 0, st>>>((const bf16_t*)a, (const bf16_t*)b, (bf16_t*)out, n8);
-    else add_kernel<bf16_t><<<g, 256, 0, st>>>((const bf16_t*)a, (const bf16_t*)b, (bf16_t*)out, n8);
-  } else {
-    if (op == 0) add_relu_fwd_kernel<float><<<g, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n8);
-    else if (op == 1) add_relu_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n8);
-    else add_kernel<float><<<g, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n8);
-  }
+  if (op == 0) PCRL_DISPATCH3(dtype, (add_relu_fwd_kernel<T><<<g, 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n8)));
+  else if (op == 1) PCRL_DISPATCH3(dtype, (add_relu_bwd_kernel<T><<<g, 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n8)));
+  else PCRL_DISPATCH3(dtype, (add_kernel<T><<<g, 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n8)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -638,12 +633,10 @@ int upsample_nearest2x(const void* x, void* y, int N, int H, int W, int C, int b
   // forward: x coarse [N][H+1][W][C] -> y fine [N][2H+1][2W][C]; backward: x = fine gradient, y = coarse gradient
   if (!backward) {
     const long long total = (long long)N * (2 * H + 1) * 2 * W * (C / 8);
-    if (dtype == PCRL_DTYPE_BF16) up_nearest2_fwd_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>((const bf16_t*)x, (bf16_t*)y, N, H, W, C);
-    else up_nearest2_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C);
+    PCRL_DISPATCH3(dtype, (up_nearest2_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C)));
   } else {
     const long long total = (long long)N * (H + 1) * W * (C / 8);
-    if (dtype == PCRL_DTYPE_BF16) up_nearest2_bwd_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>((const bf16_t*)x, (bf16_t*)y, N, H, W, C);
-    else up_nearest2_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C);
+    PCRL_DISPATCH3(dtype, (up_nearest2_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C)));
   }
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
@@ -664,8 +657,7 @@ int conv2d_c3_fwd(const void* a, const float* w, const float* bias, float* out, 
   const size_t smem = (size_t)k * k * C * 3 * sizeof(float);
   PCRL_REQUIRE(smem <= 48 * 1024, "conv2d_c3: k*k*C=%d too large", k * k * C);
   const long long total = (long long)N * H * W;
-  if (dtype == PCRL_DTYPE_BF16) conv_c3_fwd_kernel<bf16_t><<<grid_for(total, 128), 128, smem, st>>>((const bf16_t*)a, w, bias, out, N, H, W, C, Cs, k);
-  else conv_c3_fwd_kernel<float><<<grid_for(total, 128), 128, smem, st>>>((const float*)a, w, bias, out, N, H, W, C, Cs, k);
+  PCRL_DISPATCH3(dtype, (conv_c3_fwd_kernel<T><<<grid_for(total, 128), 128, smem, st>>>((const T*)a, w, bias, out, N, H, W, C, Cs, k)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -677,8 +669,7 @@ int conv2d_c3_bwd(const void* a, const float* w, const float* dout, void* da, fl
   PCRL_REQUIRE(smem <= 48 * 1024 && k * k * C <= 1024, "conv2d_c3: k*k*C=%d too large", k * k * C);
   if (da) {
     const long long total = (long long)N * (H + 1) * W * (Cs / 8);
-    if (dtype == PCRL_DTYPE_BF16) conv_c3_bwd_data_kernel<bf16_t><<<grid_for(total, 256), 256, smem, st>>>(dout, w, (bf16_t*)da, N, H, W, C, Cs, k);
-    else conv_c3_bwd_data_kernel<float><<<grid_for(total, 256), 256, smem, st>>>(dout, w, (float*)da, N, H, W, C, Cs, k);
+    PCRL_DISPATCH3(dtype, (conv_c3_bwd_data_kernel<T><<<grid_for(total, 256), 256, smem, st>>>(dout, w, (T*)da, N, H, W, C, Cs, k)));
     PCRL_CHECK_LAUNCH();
   }
   if (dw) {
@@ -688,8 +679,7 @@ int conv2d_c3_bwd(const void* a, const float* w, const float* dout, void* da, fl
     if (blocks > total) blocks = total;
     const long long chunk = (total + blocks - 1) / blocks;
     blocks = (total + chunk - 1) / chunk;
-    if (dtype == PCRL_DTYPE_BF16) conv_c3_bwd_weight_kernel<bf16_t><<<(unsigned)blocks, k * k * C, 0, st>>>((const bf16_t*)a, dout, dw, db, N, H, W, C, Cs, k, chunk);
-    else conv_c3_bwd_weight_kernel<float><<<(unsigned)blocks, k * k * C, 0, st>>>((const float*)a, dout, dw, db, N, H, W, C, Cs, k, chunk);
+    PCRL_DISPATCH3(dtype, (conv_c3_bwd_weight_kernel<T><<<(unsigned)blocks, k * k * C, 0, st>>>((const T*)a, dout, dw, db, N, H, W, C, Cs, k, chunk)));
     PCRL_CHECK_LAUNCH();
   }
   return PCRL_OK;
@@ -699,8 +689,7 @@ int pack_conv2d_weights(const float* w, void* wmat, void* wt, int Cout, int Cin,
                         int dtype, cudaStream_t st) {
   PCRL_REQUIRE(CoutP >= Cout && cs >= Cin && Kp >= k * k * cs, "pack_conv2d_weights: bad padded dims");
   const long long total = (long long)CoutP * Kp;
-  if (dtype == PCRL_DTYPE_BF16) pack_conv2d_kernel<bf16_t><<<grid_for(total, 256), 256, 0, st>>>(w, (bf16_t*)wmat, (bf16_t*)wt, Cout, Cin, k, cs, CoutP, Kp);
-  else pack_conv2d_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(w, (float*)wmat, (float*)wt, Cout, Cin, k, cs, CoutP, Kp);
+  PCRL_DISPATCH3(dtype, (pack_conv2d_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(w, (T*)wmat, (T*)wt, Cout, Cin, k, cs, CoutP, Kp)));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

@@ -38,13 +38,13 @@ from .. import kernels2d as K2
 from .pcrlv2_model_3d import _PARAM_EPOCH
 
 
-def _packed2d(conv, cs, dtype):
+def _packed2d(conv, cs, dtype, exact=False):
     w = conv.weight
-    key = (w._version, _PARAM_EPOCH[0], w.data_ptr(), dtype, cs)
+    key = (w._version, _PARAM_EPOCH[0], w.data_ptr(), dtype, cs, exact)
     cache = getattr(conv, "_pcrl_packed2d", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():
-            cache = (key, K2.pack_conv2d_weights(w, cs, dtype))
+            cache = (key, K2.pack_conv2d_weights(w, cs, dtype, exact))
         conv._pcrl_packed2d = cache
     return cache[1]
 
@@ -60,7 +60,7 @@ def _padv(v, n, fill=0.0):
 
 
 class _ConvCfg:
-    __slots__ = ("conv", "bn", "k", "s", "p", "act", "training", "dtype", "image", "want_avg")
+    __slots__ = ("conv", "bn", "k", "s", "p", "act", "training", "dtype", "image", "want_avg", "exact")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -70,18 +70,18 @@ class _ConvCfg:
 def _conv_stats(x, cfg):
     """im2col -> GEMM (+ per-channel sum / sum of squares) -> BatchNorm scale / shift (running statistics
     updated in train mode).  Returns (y, scale, shift, mean, invstd, dims)."""
-    conv, bn, dtype = cfg.conv, cfg.bn, cfg.dtype
+    conv, bn, dtype, ex = cfg.conv, cfg.bn, cfg.dtype, bool(cfg.exact)
     cout = conv.weight.shape[0]
     coutp = (cout + 31) // 32 * 32
-    col, ho, wo = K2.im2col2d(x, cfg.k, cfg.s, cfg.p, dtype, image=cfg.image)
+    col, ho, wo = K2.im2col2d(x, cfg.k, cfg.s, cfg.p, dtype, image=cfg.image, exact=ex)
     cs = x.shape[1] if cfg.image else x.shape[-1]
     n = x.shape[0]
-    wmat, _ = _packed2d(conv, cs, dtype)
+    wmat, _ = _packed2d(conv, cs, dtype, ex)
     bias = _padv(conv.bias, coutp) if conv.bias is not None else None
     gamma, beta = _padv(bn.weight, coutp), _padv(bn.bias, coutp)
     if cfg.training:
         stats = torch.zeros((1, coutp, 2), dtype=torch.float64, device=x.device)
-        y = K2.gemm_nt_stats(col, wmat, stats)
+        y = K2.gemm_nt_stats(col, wmat, stats, exact=ex)
         rm, rv = _padv(bn.running_mean, coutp), _padv(bn.running_var, coutp, 1.0)
         scale, shift, mean, invstd = K.norm_finalize(stats, n * ho * wo, gamma, beta, bias, rm, rv,
                                                      bn.num_batches_tracked, 0.1, 1e-5)
@@ -89,7 +89,7 @@ def _conv_stats(x, cfg):
             bn.running_mean.copy_(rm[:cout])
             bn.running_var.copy_(rv[:cout])
     else:
-        y = K.gemm_nt(col, wmat, out_fp32=False)
+        y = K2.gemm_nt_any(col, wmat, exact=ex)
         invstd = torch.rsqrt(_padv(bn.running_var, coutp, 1.0) + 1e-5).unsqueeze(0)
         mean = _padv(bn.running_mean, coutp)
         if bias is not None:
@@ -113,7 +113,7 @@ class _Conv2dBNFn(torch.autograd.Function):
         y, scale, shift, mean, invstd, gamma, dims, col = _conv_stats(x, cfg)
         n, ho, wo, cout, coutp, cs = dims
         a, _, avg = K.norm_act_fwd(y, scale, shift, cfg.act, None, want_full=True, want_pool=False,
-                                   want_avg=bool(cfg.want_avg))
+                                   want_avg=bool(cfg.want_avg), exact=bool(cfg.exact))
         ctx.cfg, ctx.dims = cfg, dims
         ctx.has_bias = bias is not None
         # the im2col matrix is kept for the weight gradient (9x the activation bytes of a 3x3, ~9 GB per b=8 step
@@ -138,76 +138,80 @@ class _Conv2dBNFn(torch.autograd.Function):
             gavg[:, :cout] = g_avg
         dy, sums = K.norm_act_bwd(y, g_a.contiguous() if g_a is not None else None, None, gavg, scale, shift,
                                   mean, invstd, gamma, cfg.act, None, pool=False, per_sample=False,
-                                  batch_stats=cfg.training)
+                                  batch_stats=cfg.training, exact=bool(cfg.exact))
         sums = sums[0].float()              # one statistics group (BatchNorm); views below, no copies
         grads[3] = sums[:cout, 1]
         grads[4] = sums[:cout, 0]
         if ctx.has_bias:
             grads[2] = torch.zeros(cout, dtype=torch.float32, device=y.device)     # cancels in the BatchNorm
         dy2d = dy.view(n * (ho + 1) * wo, coutp)
+        ex = bool(cfg.exact)
         if col is None:
-            col, _, _ = K2.im2col2d(x, cfg.k, cfg.s, cfg.p, cfg.dtype, image=cfg.image)
-        grads[1] = K2.conv2d_wgrad(dy2d, col, cout, cfg.conv.weight.shape[1], cfg.k, cs)
+            col, _, _ = K2.im2col2d(x, cfg.k, cfg.s, cfg.p, cfg.dtype, image=cfg.image, exact=ex)
+        grads[1] = K2.conv2d_wgrad(dy2d, col, cout, cfg.conv.weight.shape[1], cfg.k, cs, exact=ex)
         del col
         if ctx.needs_input_grad[0]:
-            _, wt = _packed2d(cfg.conv, cs, cfg.dtype)
-            dcol = K.gemm_nt(dy2d, wt, out_fp32=False)
+            _, wt = _packed2d(cfg.conv, cs, cfg.dtype, ex)
+            dcol = K2.gemm_nt_any(dy2d, wt, exact=ex)
             _, h, w, _ = K2.dims2(x)
-            grads[0] = K2.col2im2d(dcol, n, h, w, cs, cfg.k, cfg.s, cfg.p)
+            grads[0] = K2.col2im2d(dcol, n, h, w, cs, cfg.k, cfg.s, cfg.p, exact=ex)
         return tuple(grads)
 
 
 class _MaxPoolFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, exact=False):
         ctx.save_for_backward(x)
-        return K2.maxpool_fwd(x)
+        ctx.exact = exact
+        return K2.maxpool_fwd(x, exact=exact)
 
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
-        return K2.maxpool_bwd(x, g.contiguous())
+        return K2.maxpool_bwd(x, g.contiguous(), exact=ctx.exact), None
 
 
 class _AddReluFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b):
-        out = K2.add_relu(a, b, 0)
+    def forward(ctx, a, b, exact=False):
+        out = K2.add_relu(a, b, 0, exact=exact)
         ctx.save_for_backward(out)
+        ctx.exact = exact
         return out
 
     @staticmethod
     def backward(ctx, g):
         (out,) = ctx.saved_tensors
-        dg = K2.add_relu(out, g.contiguous(), 1)
-        return dg, dg
+        dg = K2.add_relu(out, g.contiguous(), 1, exact=ctx.exact)
+        return dg, dg, None
 
 
 class _UpNearestFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
-        return K2.up_nearest_fwd(x)
+    def forward(ctx, x, exact=False):
+        ctx.exact = exact
+        return K2.up_nearest_fwd(x, exact=exact)
 
     @staticmethod
     def backward(ctx, g):
-        return K2.up_nearest_bwd(g.contiguous())
+        return K2.up_nearest_bwd(g.contiguous(), exact=ctx.exact), None
 
 
 class _ConvC3Fn(torch.autograd.Function):
     """Conv2d(C -> 3, k in {1, 3}) + bias -> fp32 NCHW mask."""
 
     @staticmethod
-    def forward(ctx, a, weight, bias, c):
-        ctx.c = c
+    def forward(ctx, a, weight, bias, c, exact=False):
+        ctx.c, ctx.exact = c, exact
         ctx.save_for_backward(a, weight)
-        return K2.conv_c3_fwd(a, weight.detach().contiguous(), bias.detach().contiguous(), c)
+        return K2.conv_c3_fwd(a, weight.detach().contiguous(), bias.detach().contiguous(), c, exact=exact)
 
     @staticmethod
     def backward(ctx, g):
         a, weight = ctx.saved_tensors
         da, dw, db = K2.conv_c3_bwd(a, weight.detach().contiguous(), g.contiguous(), ctx.c,
-                                    need_da=ctx.needs_input_grad[0])
-        return da, dw, db, None
+                                    need_da=ctx.needs_input_grad[0], exact=ctx.exact)
+        return da, dw, db, None, None
 
 
 class _BilinearFn(torch.autograd.Function):
@@ -332,26 +336,33 @@ class _Unet(nn.Module):
 
 
 class PCRLv2(nn.Module):
-    """Drop-in for the reference ``PCRLv2`` (:197-209).  ``precision``: 'fp32' (default) or 'bf16'."""
+    """Drop-in for the reference ``PCRLv2`` (:197-209).  ``precision``: 'fp32' (default: fp32 storage / TF32
+    operands), 'bf16', or 'fp32x3' (3xTF32 split operands on unrounded fp32 storage: the parity mode)."""
 
     def __init__(self, n_class=3, low_dim=128, precision="fp32"):
         super().__init__()
         if n_class != 3:
             raise NotImplementedError("the 3-channel output convolutions are specialised for n_class == 3 "
                                       "(the reference default, train_2d.py:65)")
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "fp32x3"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp32x3'")
         self.model = _Unet(n_class)
         self.precision = precision
 
     @property
     def _dtype(self):
-        return torch.float32 if self.precision == "fp32" else torch.bfloat16
+        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+
+    @property
+    def _exact(self):
+        """precision='fp32x3': fp32 storage without tf32 rounding, every GEMM as three TF32 products of split
+        operands (fp32-equivalent products; the parity mode, ~3x the GEMM cost and 3x the im2col bytes)."""
+        return self.precision == "fp32x3"
 
     # ---- pieces
     def _cb(self, x, conv, bn, k, s, p, act="relu", image=False, want_avg=False):
         cfg = _ConvCfg(conv=conv, bn=bn, k=k, s=s, p=p, act=act, training=self.training, dtype=self._dtype,
-                       image=image, want_avg=want_avg)
+                       image=image, want_avg=want_avg, exact=self._exact)
         return _Conv2dBNFn.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, cfg)
 
     def _block(self, x, blk):
@@ -359,19 +370,19 @@ class PCRLv2(nn.Module):
         out = self._cb(out, blk.conv2, blk.bn2, 3, 1, 1, act="none")
         if blk.downsample is not None:
             x = self._cb(x, blk.downsample[0], blk.downsample[1], 1, blk.stride, 0, act="none")
-        return _AddReluFn.apply(out, x)
+        return _AddReluFn.apply(out, x, self._exact)
 
     def _encode(self, x):
         enc = self.model.encoder
         h = self._cb(x.float().contiguous(), enc.conv1, enc.bn1, 7, 2, 3, image=True)
-        h = _MaxPoolFn.apply(h)
+        h = _MaxPoolFn.apply(h, self._exact)
         for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
             for blk in layer:
                 h = self._block(h, blk)
         return h
 
     def _decode_block(self, h, blk, i, need_masks):
-        h = _UpNearestFn.apply(h)
+        h = _UpNearestFn.apply(h, self._exact)
         h = self._cb(h, blk.conv1[0], blk.conv1[1], 3, 1, 1)
         h, avg = self._cb(h, blk.conv2[0], blk.conv2[1], 3, 1, 1, want_avg=True)
         x_pro = Fn.batch_norm1d(avg, blk.bn)
@@ -382,14 +393,14 @@ class PCRLv2(nn.Module):
         mask = None
         if need_masks:
             m = self._cb(h, ds[0], ds[1], 3, 1, 1)
-            m = _ConvC3Fn.apply(m, ds[3].weight, ds[3].bias, cout)
+            m = _ConvC3Fn.apply(m, ds[3].weight, ds[3].bias, cout, self._exact)
             mask = _BilinearFn.apply(m, 2 ** (4 - i))
         elif self.training:
             # the mask is discarded by the caller, but BatchNorm2d of the head still sees the batch
             # (running statistics, num_batches_tracked): statistics only, no apply pass, no output conv
             with torch.no_grad():
                 _conv_stats(h, _ConvCfg(conv=ds[0], bn=ds[1], k=3, s=1, p=1, act="relu", training=True,
-                                        dtype=self._dtype, image=False, want_avg=False))
+                                        dtype=self._dtype, image=False, want_avg=False, exact=self._exact))
         return h, x_pro, x_pre, mask
 
     def forward(self, x, local=False, need_masks=True):
@@ -409,7 +420,7 @@ class PCRLv2(nn.Module):
         masks = None
         if not local and need_masks:
             seg = self.model.segmentation_head[0]
-            masks = _ConvC3Fn.apply(h, seg.weight, seg.bias, seg.weight.shape[1])
+            masks = _ConvC3Fn.apply(h, seg.weight, seg.bias, seg.weight.shape[1], self._exact)
         return outs, masks, middle
 
 
