@@ -95,11 +95,22 @@ __device__ __forceinline__ int floordiv(int a, int b) {
 struct TileCoord {
   int col0, n, f0, t_local;   // first output column, sample, first flat row, first row inside the segment
 };
-// step -> tile: column chunks outermost so that CTAs running concurrently share filter tiles in L2
+// step -> tile.  CONV: column chunks outermost, so that CTAs running concurrently share filter tiles in L2 (the
+// activations of the layers with more than one chunk fit in L2).  PLAIN GEMM: column chunks INNERMOST -- the CTAs
+// that run at the same time then read the same row tiles of A; with chunks outermost the ConvTranspose GEMM of
+// up_tr64 (A = 268 MB, eight chunks of 128 columns) re-read A from DRAM once per chunk: 2.2 GB of DRAM reads for
+// 0.27 GB of input (ncu, profiles/r02z_ncu_convt.md).  (That kernel is bound by its four epilogue warps, not by
+// DRAM: the order removes the traffic, not the time.)
 __device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, long long step) {
   TileCoord c;
-  const long long chunk = step / p.tiles_per_chunk;
-  const long long tile = step % p.tiles_per_chunk;
+  long long chunk, tile;
+  if (p.mode == IG_PLAIN) {
+    chunk = step % p.col_chunks;
+    tile = step / p.col_chunks;
+  } else {
+    chunk = step / p.tiles_per_chunk;
+    tile = step % p.tiles_per_chunk;
+  }
   const int t = (int)(tile % p.tiles_per_group);
   long long r = tile / p.tiles_per_group;
   const int g = (int)(r % p.groups);
