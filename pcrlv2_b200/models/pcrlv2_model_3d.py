@@ -25,6 +25,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .. import _lib
 from .. import functional as Fn
 from .. import kernels as K
 
@@ -51,6 +52,7 @@ def bump_param_epoch():
 # hooks on those weights do not observe it; use ``loss.backward()`` (what the trainer does) or set
 # PCRL_OVERLAP_WGRAD=0.
 import os as _os
+import types as _types
 
 _SIDE = {}            # device index -> side stream
 _SIDE_DIRTY = set()   # device indices whose side stream has weight-gradient work queued since the last join
@@ -274,6 +276,11 @@ class _LUConvFn(torch.autograd.Function):
             flat = _overlap_target(cfg.conv.weight)
             if flat is not None:
                 _wgrad_overlapped(dy, x, cfg.conv.weight, flat, ex)  # grads[1] stays None: added in place
+            elif cout % 64:
+                # 32 output channels on the tensor-core path only occur for the multi-channel stem: the weight-
+                # gradient kernel wants a 64-row operand, so dY is zero-padded for this one call
+                gpk = K.conv3d_k3_wgrad(torch.nn.functional.pad(dy, (0, 64 - cout % 64)), x, exact=ex)
+                grads[1] = K.unpack_conv3_wgrad(gpk)[:cout].contiguous()
             else:
                 grads[1] = K.unpack_conv3_wgrad(K.conv3d_k3_wgrad(dy, x, exact=ex))
             if cfg.up is not None:
@@ -385,12 +392,25 @@ class LUConv(nn.Module):
         """x: fp32 (N,1,D,H,W) for the stem, otherwise an H-padded activation in ``dtype``.
         ``up``: the ConvTranspose3d module to apply to x first (UpTransition).
         ``exact``: 3xTF32 split operands on unrounded fp32 storage (precision='fp32x3')."""
+        conv, weight = self.conv1, self.conv1.weight
+        if self.in_chan != 1 and self.in_chan < 32 and x.dim() == 5 and x.shape[1] == self.in_chan:
+            # multi-channel network input (in_channels > 1, reference :98,104): NCDHW fp32 -> H-padded NDHWC with
+            # the channels zero-padded to 32, the weight zero-padded likewise (autograd slices its gradient back);
+            # from here on it is an ordinary 32-channel layer of the tensor-core path
+            xp = torch.nn.functional.pad(K.pad_ndhwc(x, torch.float32), (0, 32 - self.in_chan))
+            if dtype == torch.bfloat16:
+                xp = xp.to(dtype)
+            elif not exact:      # fp32 storage holds tf32-rounded operands (cvt.rna on the magnitude bits)
+                xp = ((xp.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+            x = xp.contiguous()
+            weight = torch.nn.functional.pad(self.conv1.weight, (0, 0, 0, 0, 0, 0, 0, 32 - self.in_chan))
+            conv = _types.SimpleNamespace(weight=weight)
         cfg = _Cfg(stem=self.in_chan == 1, pool=pool, tail=tail is not None, final=final is not None,
-                   act=self.act, norm=self.norm, training=self.training, conv=self.conv1, bn=self.bn1,
+                   act=self.act, norm=self.norm, training=self.training, conv=conv, bn=self.bn1,
                    ds=tail.conv1 if tail is not None else None, fin=final, up=up, dtype=dtype, exact=exact)
         prelu = self.activation.weight if self.act == "prelu" else None
         return _LUConvFn.apply(
-            x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, prelu,
+            x, weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, prelu,
             tail.conv1.weight if tail is not None else None,
             tail.conv1.bias if tail is not None else None,
             final.weight if final is not None else None,
@@ -457,11 +477,62 @@ class UpTransition(nn.Module):
         return a, x_pro, x_pre, mask, y0
 
 
+class _FinalConvNFn(torch.autograd.Function):
+    """Conv3d(64 -> n_class > 1, kernel 1) as a tensor-core GEMM over the rows of the H-padded activation
+    (n_class == 1, the reference default, rides as a column of the deep-supervision head GEMM instead)."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, exact):
+        n, d, h, w, c = K.dims_of(a)
+        k = weight.shape[0]
+        if k > 32:
+            raise NotImplementedError("n_class <= 32")
+        wp = torch.zeros((32, c), dtype=torch.float32, device=a.device)
+        wp[:k] = weight.detach().reshape(k, c)
+        bp = torch.zeros((32,), dtype=torch.float32, device=a.device)
+        bp[:k] = bias.detach()
+        a2d = a.view(-1, c)
+        if exact:
+            y = torch.empty((a2d.shape[0], 32), dtype=torch.float32, device=a.device)
+            _lib.call("pcrl_gemm_nt", K.split3(a2d, 0), K.split3(wp, 1), y, bp, a2d.shape[0], 3 * c, 32, 32, 1, K.F32X)
+        else:
+            y = K.gemm_nt(a2d, K2_round(wp, a.dtype), bp, out_fp32=True)
+        ctx.save_for_backward(a, wp)
+        ctx.k, ctx.exact = k, exact
+        return y.view(n, d, h + 1, w, 32)[:, :, 1:, :, :k].permute(0, 4, 1, 2, 3).contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        a, wp = ctx.saved_tensors
+        n, d, h, w, c = K.dims_of(a)
+        k = ctx.k
+        g2 = torch.zeros((n, d, h + 1, w, 32), dtype=a.dtype, device=a.device)
+        g2[:, :, 1:, :, :k] = g.permute(0, 2, 3, 4, 1)
+        g2d, a2d = g2.view(-1, 32), a.view(-1, c)
+        wt = wp.t().contiguous()                       # [64][32]
+        if ctx.exact:
+            da = torch.empty_like(a)
+            _lib.call("pcrl_gemm_nt", K.split3(g2d, 0), K.split3(wt, 1), da, None, g2d.shape[0], 96, c, c, 1, K.F32X)
+            dwt = torch.zeros((c, 32), dtype=torch.float32, device=a.device)
+            _lib.call("pcrl_gemm_tn", K.split3(a2d, 1, stack=True), K.split3(g2d, 0, stack=True), dwt,
+                      3 * a2d.shape[0], c, 32, K.F32X)
+        else:
+            da = K.gemm_nt(g2d, K2_round(wt, a.dtype), out_fp32=False).view_as(a)
+            dwt = K.gemm_tn(a2d, g2d)
+        dw = dwt.t()[:k].reshape(k, c, 1, 1, 1).contiguous()
+        return da, dw, g.sum((0, 2, 3, 4)), None
+
+
+def K2_round(w32, dtype):
+    """fp32 weights -> GEMM operand in the storage type (fp32: cvt.rna.tf32 of the magnitude bits)."""
+    if dtype == torch.float32:
+        return ((w32.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return w32.to(dtype).contiguous()
+
+
 class OutputTransition(nn.Module):
     def __init__(self, inChans, n_labels):
         super().__init__()
-        if n_labels != 1:
-            raise NotImplementedError("the fused output head supports n_class == 1 (reference default)")
         self.final_conv = nn.Conv3d(inChans, n_labels, kernel_size=1)
         self.sigmoid = nn.Sigmoid()
 
@@ -483,8 +554,9 @@ class PCRLv23d(nn.Module):
         if precision not in ("bf16", "fp32", "fp32x3"):
             raise ValueError("precision must be 'fp32', 'bf16' or 'fp32x3'")
         self.precision = precision
-        if in_channels != 1:
-            raise NotImplementedError("in_channels must be 1 (CT sub-volumes, the reference default)")
+        if not (1 <= in_channels < 32) or not (1 <= n_class <= 32):
+            raise NotImplementedError("in_channels must be in 1..31 and n_class in 1..32")
+        self.in_channels, self.n_class = in_channels, n_class
         self.maxpool = nn.MaxPool3d(2)
         self.down_tr64 = DownTransition(in_channels, 0, act, norm)
         self.down_tr128 = DownTransition(64, 1, act, norm)
@@ -500,8 +572,8 @@ class PCRLv23d(nn.Module):
     def forward(self, x, local=False):
         if not x.is_cuda:
             raise RuntimeError("pcrlv2_b200.PCRLv23d runs on CUDA only (there is no CPU fallback)")
-        if x.dim() != 5 or x.shape[1] != 1 or any(s % 8 for s in x.shape[2:]):
-            raise ValueError("expected (B,1,D,H,W) with D,H,W multiples of 8, got %s" % (tuple(x.shape),))
+        if x.dim() != 5 or x.shape[1] != self.in_channels or any(s % 8 for s in x.shape[2:]):
+            raise ValueError("expected (B,%d,D,H,W) with D,H,W multiples of 8, got %s" % (self.in_channels, tuple(x.shape)))
         x = x.float().contiguous()
         dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
         ex = self.precision == "fp32x3"
@@ -511,7 +583,12 @@ class PCRLv23d(nn.Module):
         h = self.down_tr512.run(h, pool=False, dtype=dt, exact=ex)
         h, pro_256, pre_256, m256, _ = self.up_tr256.run(h, dtype=dt, exact=ex)
         h, pro_128, pre_128, m128, _ = self.up_tr128.run(h, dtype=dt, exact=ex)
-        h, pro_64, pre_64, m64, y0 = self.up_tr64.run(h, final=self.out_tr.final_conv, dtype=dt, exact=ex)
+        if self.n_class == 1:      # the 1x1x1 output conv rides in the deep-supervision head GEMM
+            h, pro_64, pre_64, m64, y0 = self.up_tr64.run(h, final=self.out_tr.final_conv, dtype=dt, exact=ex)
+        else:
+            h, pro_64, pre_64, m64, _ = self.up_tr64.run(h, dtype=dt, exact=ex)
+            fc = self.out_tr.final_conv
+            y0 = _FinalConvNFn.apply(h, fc.weight, fc.bias, ex)
         middle_masks = []
         if not local:
             middle_masks.append(Fn.upsample_trilinear(m256, 4))

@@ -452,3 +452,43 @@ def test_lr_schedule_reaches_flat_sgd():
     opt.step()
     want = p0 - opt.param_groups[0]["lr"] * (g0 + 1e-4 * p0)
     assert rl2(m.out_tr.final_conv.weight, want) < 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "fp32", "bf16"])
+def test_multi_channel_input_and_multi_class_output(precision):
+    """``PCRLv23d(n_class=2, in_channels=3)`` (reference models/pcrlv2_model_3d.py:98,104,110): the multi-channel stem
+    runs as a 32-channel layer of the tensor-core path (zero-padded channels and weights), the 64 -> n_class output
+    conv as a GEMM.  Forward against the oracle, restoration gradients of the stem / output conv / a trunk layer."""
+    from pcrlv2_b200.models import PCRLv23d
+    sd0 = orc.init_state(0, in_channels=3, n_class=2)
+    m = PCRLv23d(n_class=2, in_channels=3, precision=precision)
+    m.load_state_dict(orc.clone_state(sd0))
+    m = m.cuda().train()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((4, 3, 32, 32, 16), generator=g)
+    gt = torch.rand((4, 2, 32, 32, 16), generator=g)
+    sd = orc.clone_state(sd0)
+    keys = [k for k in sd if orc.is_param(k)]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    o_out, o_feats, o_masks = orc.forward(sd, x)
+    o_loss = torch.nn.functional.mse_loss(o_out, gt)
+    o_grads = dict(zip(keys, torch.autograd.grad(o_loss, [sd[k] for k in keys], allow_unused=True)))
+    out, feats, masks = m(x.cuda())
+    assert out.shape == (4, 2, 32, 32, 16)
+    tol = FWD_BOUNDS[precision]
+    e = rl2(out, o_out)
+    log(f"[n_class=2, in_channels=3 {precision}] out rel-L2 {e:.3e}; masks {[round(rl2(a, b), 5) for a, b in zip(masks, o_masks)]}")
+    assert e < tol
+    for a, b in zip(masks, o_masks):
+        assert rl2(a, b) < 3 * tol
+    loss = torch.nn.functional.mse_loss(out, gt.cuda())
+    assert abs(loss.item() - o_loss.item()) < 10 * tol * abs(o_loss.item()) + 1e-6
+    loss.backward()
+    gb = {"fp32x3": 4e-2, "fp32": 0.3, "bf16": 0.8}[precision]        # STEP_BOUNDS: the trunk-gradient noise floors
+    for n in ("out_tr.final_conv.weight", "out_tr.final_conv.bias", "up_tr64.ops.1.conv1.weight",
+              "down_tr64.ops.1.conv1.weight", "down_tr64.ops.0.conv1.weight"):
+        p = dict(m.named_parameters())[n]
+        eg = rl2(p.grad, o_grads[n])
+        log(f"[n_class=2, in_channels=3 {precision}] {n:34s} grad rel-L2 {eg:.3e}")
+        assert p.grad.shape == o_grads[n].shape and eg < gb, (n, eg)
