@@ -27,25 +27,37 @@ def get_dataloader(args):
     return dataloader
 
 
+# (flag, default, type, help) -- the reference's command line (main.py:23-39), flag for flag, plus --synthetic_items
+_FLAGS = (
+    ("data", "synthetic", str, "path to dataset ('synthetic' = generated batches of the reference's shapes)"),
+    ("model", "pcrlv2", str, "choose the model"),
+    ("phase", "pretask", str, "pretask or finetune or train from scratch"),
+    ("b", 16, int, "batch size"),
+    ("epochs", 100, int, "epochs to train"),
+    ("lr", 1e-3, float, "learning rate"),
+    ("output", "./model_genesis_pretrain", str, "output path"),
+    ("n", "luna", str, "dataset to use"),
+    ("d", 3, int, "3d or 2d to run"),
+    ("workers", 4, int, "num of workers"),
+    ("gpus", "0,1,2,3", str, "gpu indexs"),
+    ("ratio", 0.8, float, "ratio of data used for pretraining"),
+    ("momentum", 0.9, None, None),
+    ("weight_decay", 1e-4, None, None),
+    ("seed", 42, int, None),
+    ("synthetic_items", 64, int, "items per epoch of the synthetic loader"),
+)
+
+
 def build_parser():
-    parser = argparse.ArgumentParser(description='Self Training benchmark')
-    parser.add_argument('--data', metavar='DIR', default='synthetic', help='path to dataset')
-    parser.add_argument('--model', metavar='MODEL', default='pcrlv2', help='choose the model')
-    parser.add_argument('--phase', default='pretask', type=str, help='pretask or finetune or train from scratch')
-    parser.add_argument('--b', default=16, type=int, help='batch size')
-    parser.add_argument('--epochs', default=100, type=int, help='epochs to train')
-    parser.add_argument('--lr', default=1e-3, type=float, help='learning rate')
-    parser.add_argument('--output', default='./model_genesis_pretrain', type=str, help='output path')
-    parser.add_argument('--n', default='luna', type=str, help='dataset to use')
-    parser.add_argument('--d', default=3, type=int, help='3d or 2d to run')
-    parser.add_argument('--workers', default=4, type=int, help='num of workers')
-    parser.add_argument('--gpus', default='0,1,2,3', type=str, help='gpu indexs')
-    parser.add_argument('--ratio', default=0.8, type=float, help='ratio of data used for pretraining')
-    parser.add_argument('--momentum', default=0.9)
-    parser.add_argument('--weight_decay', default=1e-4)
-    parser.add_argument('--seed', default=42, type=int)
-    parser.add_argument('--amp', action='store_true', default=False)
-    parser.add_argument('--synthetic_items', default=64, type=int, help='items per epoch of the synthetic loader')
+    parser = argparse.ArgumentParser(description="Self Training benchmark")
+    for name, default, typ, text in _FLAGS:
+        kw = {"default": default}
+        if typ is not None:
+            kw["type"] = typ
+        if text is not None:
+            kw["help"] = text
+        parser.add_argument("--" + name, **kw)
+    parser.add_argument("--amp", action="store_true", default=False)
     return parser
 
 
